@@ -1,0 +1,90 @@
+"""ctypes binding of libfreud_b200.so (the C ABI declared in include/freud_b200.h).
+
+There is no CPU fallback: if the library is missing or a call fails this raises.  The reference has no FFI
+(its hot path is ATen ops); see INTEGRATION.md for how these entry points map onto its call sites.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfreud_b200.so")
+
+MAX_TENSORS = 8
+BF16, FP32 = 0, 1
+
+
+class TensorList(C.Structure):
+    _fields_ = [
+        ("count", C.c_int32),
+        ("param", C.c_void_p * MAX_TENSORS),
+        ("grad", C.c_void_p * MAX_TENSORS),
+        ("exp_avg", C.c_void_p * MAX_TENSORS),
+        ("exp_avg_sq", C.c_void_p * MAX_TENSORS),
+        ("bf16_shadow", C.c_void_p * MAX_TENSORS),
+        ("numel", C.c_int64 * MAX_TENSORS),
+    ]
+
+
+_p, _i64, _i, _f, _d = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_double
+
+# name -> argtypes, exactly the prototypes of include/freud_b200.h
+SIGNATURES = {
+    "freud_topk_prep_x": [_p, _p, _p, _p, _p, _i64, _i64, _i64, _i, _p],
+    "freud_split_operand": [_p, _p, _p, _i64, _i, _p],
+    "freud_topk_encode": [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i, _p],
+    "freud_gemm_nt": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i, _i, _p],
+    "freud_row_topk": [_p, _p, _p, _p, _i64, _i64, _i64, _p],
+    "freud_topk_decode": [_p, _p, _p, _i, _p, _p, _p, _p, _i, _p, _p, _i64, _i64, _i64, _p],
+    "freud_topk_dacts": [_p, _i, _p, _p, _i, _p, _i64, _i64, _i64, _p],
+    "freud_axpby": [_p, _p, _p, _p, _i, _i64, _p],
+    "freud_csc_build": [_p, _i64, _i64, _i64, _p, _p, _p, _p],
+    "freud_topk_sparse_grads": [_p, _p, _p, _p, _p, _i, _p, _i, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i, _p],
+    "freud_topk_bdec_grad": [_p, _p, _p, _p, _p, _i64, _i64, _i, _p],
+    "freud_topk_loss_scalars": [_p, _p, _p, _i64, _p],
+    "freud_dead_latent_update": [_p, _p, _i64, _i64, _p],
+    "freud_rownorm_project": [_p, _i64, _i64, _f, _p],
+    "freud_remove_parallel_grad": [_p, _p, _i64, _i64, _p],
+    "freud_l1_colnorm": [_p, _p, _i64, _i64, _p],
+    "freud_l1_loss_reduce": [_p, _p, _p, _p, _p, _i64, _i64, _i64, _p],
+    "freud_l1_dz": [_p, _p, _p, _p, _i64, _i64, _p],
+    "freud_l1_weight_grad": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _p],
+    "freud_grad_sumsq": [C.POINTER(TensorList), _p, _p],
+    "freud_clip_grads": [C.POINTER(TensorList), _p, _f, _p, _p],
+    "freud_adam_step": [C.POINTER(TensorList), _d, _d, _d, _d, _i64, _p, _f, _p],
+    "freud_radam_step": [C.POINTER(TensorList), _d, _d, _d, _d, _d, _i64, _p, _f, _p],
+    "freud_search_dense": [_p, _i, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p],
+    "freud_search_indexed": [_p, _p, _i, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p],
+    "freud_search_topn": [_p, _p, _i64, _i, _i, _d, _i, _d, _i64, _p, _p, _p],
+}
+
+_lib = None
+launch_count = 0  # number of C-ABI calls that enqueued kernels (bench.py reports it as gpu_launches evidence)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -m freud_b200.build` (there is no CPU fallback)")
+        handle = C.CDLL(LIB_PATH)
+        handle.freud_last_error.restype = C.c_char_p
+        handle.freud_last_error.argtypes = []
+        handle.freud_version.restype = C.c_int
+        handle.freud_version.argtypes = []
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.argtypes = argtypes
+            fn.restype = C.c_int
+        _lib = handle
+    return _lib
+
+
+def call(name, *args):
+    """Invoke a C-ABI entry point; raise RuntimeError(freud_last_error()) on a non-zero status."""
+    global launch_count
+    handle = lib()
+    rc = getattr(handle, name)(*args)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {handle.freud_last_error().decode()}")
+    launch_count += 1

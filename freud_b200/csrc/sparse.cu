@@ -1,0 +1,656 @@
+// Bandwidth-bound kernels of the TopK SAE step: operand preparation + total variance, sparse decode,
+// gather-dot activation gradients, feature-major (CSC) index, row-sparse weight gradients, bias gradients,
+// loss scalars, dead-latent counters and the decoder norm helpers.  All are gather / stream kernels bounded by
+// L2 / HBM bandwidth; none is reshaped into a GEMM.
+#include "device_utils.cuh"
+#include "host_common.h"
+#include "../../include/freud_b200.h"
+
+namespace freud {
+
+// ------------------------------------------------------------------------------------------------ prep_x
+// One thread per (t, 4 channels); loops over the batch axis so the per-(t,c) mean of topkautoencoder.py:104 is a
+// private register reduction.  Shifted sums (shift = x[0,t,c]) keep sum((x-mean)^2) = s2 - s1^2/B well conditioned.
+template <int MODE>  // 0: bf16 out, 1: tf32 hi/lo out
+__global__ void __launch_bounds__(256) prep_x_kernel(const float* __restrict__ x, const float* __restrict__ b_dec,
+                                                     void* __restrict__ out_hi, void* __restrict__ out_lo,
+                                                     double* __restrict__ tv, int B, int64_t T, int d) {
+  __shared__ double scratch[32];
+  const int d4 = d >> 2;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  double part = 0.0;
+  if (idx < T * d4) {
+    const int64_t t = idx / d4;
+    const int c = static_cast<int>(idx - t * d4) * 4;
+    const float4 bd = load4(b_dec + c);
+    const int64_t stride = T * d;
+    const float* px = x + t * d + c;
+    const float4 sh = load4(px);
+    float4 s1 = make_float4(0, 0, 0, 0), s2 = make_float4(0, 0, 0, 0);
+#pragma unroll 4
+    for (int b = 0; b < B; ++b) {
+      const float4 v = load4(px + b * stride);
+      const float4 xc = make_float4(v.x - bd.x, v.y - bd.y, v.z - bd.z, v.w - bd.w);
+      const int64_t o = b * stride + t * d + c;
+      if (MODE == 0) {
+        store4(reinterpret_cast<__nv_bfloat16*>(out_hi) + o, xc);
+      } else {
+        const float4 hi = make_float4(to_tf32(xc.x), to_tf32(xc.y), to_tf32(xc.z), to_tf32(xc.w));
+        const float4 lo = make_float4(to_tf32(xc.x - hi.x), to_tf32(xc.y - hi.y), to_tf32(xc.z - hi.z),
+                                      to_tf32(xc.w - hi.w));
+        store4(reinterpret_cast<float*>(out_hi) + o, hi);
+        store4(reinterpret_cast<float*>(out_lo) + o, lo);
+      }
+      const float4 dv = make_float4(v.x - sh.x, v.y - sh.y, v.z - sh.z, v.w - sh.w);
+      s1.x += dv.x; s1.y += dv.y; s1.z += dv.z; s1.w += dv.w;
+      s2.x += dv.x * dv.x; s2.y += dv.y * dv.y; s2.z += dv.z * dv.z; s2.w += dv.w * dv.w;
+    }
+    const double inv = 1.0 / B;
+    part = (double)s2.x - (double)s1.x * s1.x * inv + (double)s2.y - (double)s1.y * s1.y * inv +
+           (double)s2.z - (double)s1.z * s1.z * inv + (double)s2.w - (double)s1.w * s1.w * inv;
+  }
+  const double tot = block_sum(part, scratch);
+  if (threadIdx.x == 0 && tot != 0.0) atomicAdd(tv, tot);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) split_operand_kernel(const float* __restrict__ w, void* __restrict__ hi,
+                                                            void* __restrict__ lo, int64_t n4) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 v = load4(w + i * 4);
+    if (MODE == 0) {
+      store4(reinterpret_cast<__nv_bfloat16*>(hi) + i * 4, v);
+    } else {
+      const float4 h = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+      const float4 l = make_float4(to_tf32(v.x - h.x), to_tf32(v.y - h.y), to_tf32(v.z - h.z), to_tf32(v.w - h.w));
+      store4(reinterpret_cast<float*>(hi) + i * 4, h);
+      store4(reinterpret_cast<float*>(lo) + i * 4, l);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ decode
+// One warp per token.  Lane l owns channels {4l + 128i .. +3}; the k gathered decoder rows stream through
+// registers 4 at a time (independent 16-byte loads in flight), fp32 accumulate.
+template <typename WT, typename RT, int CH>
+__global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ top_vals,
+                                                     const int32_t* __restrict__ top_idx, const WT* __restrict__ W,
+                                                     const float* __restrict__ b_dec, const float* __restrict__ target,
+                                                     float* __restrict__ sae_out, RT* __restrict__ resid,
+                                                     double* __restrict__ sse, float* __restrict__ colsum, int64_t N,
+                                                     int d, int k) {
+  __shared__ double scratch[32];
+  extern __shared__ float colsum_s[];  // [d] per-CTA partial of the residual column sums
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  if (colsum) {
+    for (int c = threadIdx.x; c < d; c += blockDim.x) colsum_s[c] = 0.f;
+    __syncthreads();
+  }
+  double sq = 0.0;
+  float4 csum[CH];
+#pragma unroll
+  for (int i = 0; i < CH; ++i) csum[i] = make_float4(0, 0, 0, 0);
+  for (int64_t t = static_cast<int64_t>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); t < N;
+       t += static_cast<int64_t>(gridDim.x) * warps_per_block) {
+    float4 acc[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const int c = lane * 4 + i * 128;
+      acc[i] = c < d ? load4(b_dec + c) : make_float4(0, 0, 0, 0);
+    }
+    for (int j0 = 0; j0 < k; j0 += 32) {
+      const int jn = min(32, k - j0);
+      const float my_a = lane < jn ? __ldg(top_vals + t * k + j0 + lane) : 0.f;
+      const int my_i = lane < jn ? __ldg(top_idx + t * k + j0 + lane) : 0;
+#pragma unroll 4
+      for (int j = 0; j < jn; ++j) {
+        const float a = __shfl_sync(0xffffffffu, my_a, j);
+        const int64_t f = __shfl_sync(0xffffffffu, my_i, j);
+        const WT* wr = W + f * d;
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+          const int c = lane * 4 + i * 128;
+          if (c < d) {
+            const float4 w = load4(wr + c);
+            acc[i].x = fmaf(a, w.x, acc[i].x);
+            acc[i].y = fmaf(a, w.y, acc[i].y);
+            acc[i].z = fmaf(a, w.z, acc[i].z);
+            acc[i].w = fmaf(a, w.w, acc[i].w);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const int c = lane * 4 + i * 128;
+      if (c < d) {
+        store4(sae_out + t * d + c, acc[i]);
+        if (target) {
+          const float4 xv = load4(target + t * d + c);
+          const float4 e = make_float4(acc[i].x - xv.x, acc[i].y - xv.y, acc[i].z - xv.z, acc[i].w - xv.w);
+          if (resid) store4(resid + t * d + c, e);
+          sq += (double)(e.x * e.x + e.y * e.y) + (double)(e.z * e.z + e.w * e.w);
+          csum[i].x += e.x; csum[i].y += e.y; csum[i].z += e.z; csum[i].w += e.w;
+        }
+      }
+    }
+  }
+  if (colsum) {
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const int c = lane * 4 + i * 128;
+      if (c < d) {
+        atomicAdd(colsum_s + c + 0, csum[i].x);
+        atomicAdd(colsum_s + c + 1, csum[i].y);
+        atomicAdd(colsum_s + c + 2, csum[i].z);
+        atomicAdd(colsum_s + c + 3, csum[i].w);
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < d; c += blockDim.x) atomicAdd(colsum + c, colsum_s[c]);
+  }
+  if (sse) {
+    const double tot = block_sum(sq, scratch);
+    if (threadIdx.x == 0) atomicAdd(sse, tot);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ dacts
+// One warp per token: g row in registers, each gathered decoder row reduced to a per-lane partial dot;
+// 32 rows are reduced together with a 31-shuffle transposing reduction so lane j ends with row j's dot.
+template <typename GT, typename WT, int CH>
+__global__ void __launch_bounds__(256) dacts_kernel(const GT* __restrict__ g, const int32_t* __restrict__ top_idx,
+                                                    const WT* __restrict__ W, float* __restrict__ dacts, int64_t N,
+                                                    int d, int k) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  for (int64_t t = static_cast<int64_t>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); t < N;
+       t += static_cast<int64_t>(gridDim.x) * warps_per_block) {
+    float4 gv[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const int c = lane * 4 + i * 128;
+      gv[i] = c < d ? load4(g + t * d + c) : make_float4(0, 0, 0, 0);
+    }
+    for (int j0 = 0; j0 < k; j0 += 32) {
+      const int jn = min(32, k - j0);
+      const int my_i = lane < jn ? __ldg(top_idx + t * k + j0 + lane) : -1;
+      float part[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int64_t f = __shfl_sync(0xffffffffu, my_i, j);
+        float s = 0.f;
+        if (f >= 0) {
+          const WT* wr = W + f * d;
+#pragma unroll
+          for (int i = 0; i < CH; ++i) {
+            const int c = lane * 4 + i * 128;
+            if (c < d) {
+              const float4 w = load4(wr + c);
+              s = fmaf(gv[i].x, w.x, s);
+              s = fmaf(gv[i].y, w.y, s);
+              s = fmaf(gv[i].z, w.z, s);
+              s = fmaf(gv[i].w, w.w, s);
+            }
+          }
+        }
+        part[j] = s;
+      }
+      const float tot = warp_transpose_reduce32(part, lane);
+      if (lane < jn) dacts[t * k + j0 + lane] = tot;
+    }
+  }
+}
+
+template <typename OT>
+__global__ void __launch_bounds__(256) axpby_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                    const float* __restrict__ coef, OT* __restrict__ out, int64_t n4) {
+  const float alpha = coef[0], beta = coef[1];
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 av = load4(a + i * 4);
+    float4 o = make_float4(alpha * av.x, alpha * av.y, alpha * av.z, alpha * av.w);
+    if (b) {
+      const float4 bv = load4(b + i * 4);
+      o.x = fmaf(beta, bv.x, o.x); o.y = fmaf(beta, bv.y, o.y); o.z = fmaf(beta, bv.z, o.z); o.w = fmaf(beta, bv.w, o.w);
+    }
+    store4(out + i * 4, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ CSC index
+__global__ void __launch_bounds__(256) csc_hist_kernel(const int32_t* __restrict__ top_idx, int64_t total,
+                                                       int32_t* __restrict__ counts) {
+  for (int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p < total;
+       p += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    atomicAdd(counts + __ldg(top_idx + p), 1);
+}
+
+// Single-block exclusive scan of counts[0..n) -> offsets[0..n]; cursor[f] = offsets[f].
+__global__ void __launch_bounds__(1024) csc_scan_kernel(int32_t* __restrict__ offsets, int32_t* __restrict__ cursor,
+                                                        int n) {
+  __shared__ int32_t warp_tot[32];
+  __shared__ int32_t carry_s;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int32_t v = i < n ? offsets[i] : 0;  // offsets holds the raw counts on entry
+    int32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += u;
+    }
+    if (lane == 31) warp_tot[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+      int32_t t = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int32_t u = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += u;
+      }
+      warp_tot[lane] = t;
+    }
+    __syncthreads();
+    const int32_t carry = carry_s;
+    const int32_t excl = carry + (w > 0 ? warp_tot[w - 1] : 0) + incl - v;
+    if (i < n) {
+      offsets[i] = excl;
+      cursor[i] = excl;
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + warp_tot[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) offsets[n] = carry_s;
+}
+
+__global__ void __launch_bounds__(256) csc_fill_kernel(const int32_t* __restrict__ top_idx, int64_t total,
+                                                       int32_t* __restrict__ cursor, int32_t* __restrict__ entries) {
+  for (int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p < total;
+       p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int32_t pos = atomicAdd(cursor + __ldg(top_idx + p), 1);
+    entries[pos] = static_cast<int32_t>(p);
+  }
+}
+
+// Sort each feature's list ascending (token order) so the fp32 accumulation order -- and therefore the
+// gradients -- are run-to-run deterministic despite the atomic fill.  One CTA per feature, bitonic sort in
+// shared memory; lists longer than kSortMax entries are left in fill order (still correct, not bit-stable).
+constexpr int kSortMax = 4096;
+__global__ void __launch_bounds__(256) csc_sort_kernel(const int32_t* __restrict__ offsets,
+                                                       int32_t* __restrict__ entries) {
+  __shared__ int32_t buf[kSortMax];
+  const int f = blockIdx.x;
+  const int beg = offsets[f], len = offsets[f + 1] - beg;
+  if (len <= 1 || len > kSortMax) return;
+  int m = 2;
+  while (m < len) m <<= 1;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) buf[i] = i < len ? entries[beg + i] : 0x7fffffff;
+  __syncthreads();
+  for (int k = 2; k <= m; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const int l = i ^ j;
+        if (l > i) {
+          const int32_t a = buf[i], b = buf[l];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) {
+            buf[i] = b;
+            buf[l] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < len; i += blockDim.x) entries[beg + i] = buf[i];
+}
+
+// ------------------------------------------------------------------------------------------------ weight grads
+// One CTA per feature f.  Thread c4 owns 4 channels; the CTA walks list(f) and accumulates
+//   dW_dec[f,:] += a_p * g[t_p,:]      dW_enc[f,:] += dpre_p * xc[t_p,:]
+// with 4 list entries in flight.  Gathers are whole contiguous rows (coalesced across the CTA).
+template <typename GT, typename XT>
+__global__ void __launch_bounds__(256) sparse_grads_kernel(
+    const int32_t* __restrict__ offsets, const int32_t* __restrict__ entries, const float* __restrict__ top_vals,
+    const float* __restrict__ dacts, const GT* __restrict__ g, const XT* __restrict__ xc,
+    const float* __restrict__ b_dec, const float* __restrict__ scales, float* __restrict__ dW_dec,
+    float* __restrict__ dW_enc, float* __restrict__ db_enc, int d, int k, int accumulate) {
+  const int f = blockIdx.x;
+  const int beg = offsets[f], end = offsets[f + 1];
+  const float s_dec = scales[0], s_enc = scales[1];
+  constexpr bool kRecenter = sizeof(XT) == 4;  // fp32 path: xc = x - b_dec recomputed on the fly
+  __shared__ int32_t tok_s[256];
+  __shared__ float a_s[256];
+  __shared__ float dp_s[256];
+  float dpsum = 0.f;
+  const int chunk = blockDim.x;
+  const int num_pass = (d + chunk * 4 - 1) / (chunk * 4);  // 1 for d <= 1024 (block sized to d/4 threads)
+  for (int pass = 0; pass < num_pass; ++pass) {
+    const int c = (pass * chunk + threadIdx.x) * 4;
+    const bool active = c < d;
+    float4 accd = make_float4(0, 0, 0, 0), acce = make_float4(0, 0, 0, 0);
+    float4 bd = make_float4(0, 0, 0, 0);
+    if (kRecenter && active) bd = load4(b_dec + c);
+    for (int base = beg; base < end; base += chunk) {
+      const int cnt = min(chunk, end - base);
+      __syncthreads();
+      if (threadIdx.x < cnt) {
+        const int p = entries[base + threadIdx.x];
+        const float a = top_vals[p];
+        tok_s[threadIdx.x] = p / k;
+        a_s[threadIdx.x] = a * s_dec;
+        const float dp = a > 0.f ? dacts[p] * s_enc : 0.f;
+        dp_s[threadIdx.x] = dp;
+        if (pass == 0) dpsum += dp;
+      }
+      __syncthreads();
+      if (active) {
+        int i = 0;
+        for (; i + 4 <= cnt; i += 4) {
+          float4 gv[4], xv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int64_t t = tok_s[i + u];
+            gv[u] = load4(g + t * d + c);
+            xv[u] = load4(xc + t * d + c);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float a = a_s[i + u], dp = dp_s[i + u];
+            accd.x = fmaf(a, gv[u].x, accd.x); accd.y = fmaf(a, gv[u].y, accd.y);
+            accd.z = fmaf(a, gv[u].z, accd.z); accd.w = fmaf(a, gv[u].w, accd.w);
+            acce.x = fmaf(dp, xv[u].x - bd.x, acce.x); acce.y = fmaf(dp, xv[u].y - bd.y, acce.y);
+            acce.z = fmaf(dp, xv[u].z - bd.z, acce.z); acce.w = fmaf(dp, xv[u].w - bd.w, acce.w);
+          }
+        }
+        for (; i < cnt; ++i) {
+          const int64_t t = tok_s[i];
+          const float4 gv = load4(g + t * d + c);
+          const float4 xv = load4(xc + t * d + c);
+          const float a = a_s[i], dp = dp_s[i];
+          accd.x = fmaf(a, gv.x, accd.x); accd.y = fmaf(a, gv.y, accd.y);
+          accd.z = fmaf(a, gv.z, accd.z); accd.w = fmaf(a, gv.w, accd.w);
+          acce.x = fmaf(dp, xv.x - bd.x, acce.x); acce.y = fmaf(dp, xv.y - bd.y, acce.y);
+          acce.z = fmaf(dp, xv.z - bd.z, acce.z); acce.w = fmaf(dp, xv.w - bd.w, acce.w);
+        }
+      }
+    }
+    if (active) {
+      float* pd = dW_dec + static_cast<int64_t>(f) * d + c;
+      float* pe = dW_enc + static_cast<int64_t>(f) * d + c;
+      if (accumulate) {
+        const float4 od = *reinterpret_cast<const float4*>(pd), oe = *reinterpret_cast<const float4*>(pe);
+        accd.x += od.x; accd.y += od.y; accd.z += od.z; accd.w += od.w;
+        acce.x += oe.x; acce.y += oe.y; acce.z += oe.z; acce.w += oe.w;
+      }
+      store4(pd, accd);
+      store4(pe, acce);
+    }
+  }
+  // db_enc[f] = sum of dpre over the list (each entry was loaded by exactly one thread in the first pass)
+  __shared__ float red[8];
+  dpsum = warp_sum(dpsum);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dpsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) tot += red[w];
+    db_enc[f] = accumulate ? db_enc[f] + tot : tot;
+  }
+}
+
+// db_dec[c] (+)= s*colsum[c] - sum_f db_enc[f] * W_enc[f,c]; grid over column chunks x feature slabs.
+__global__ void __launch_bounds__(256) bdec_grad_kernel(const float* __restrict__ colsum,
+                                                        const float* __restrict__ scales,
+                                                        const float* __restrict__ db_enc,
+                                                        const float* __restrict__ W_enc, float* __restrict__ db_dec,
+                                                        int n, int d, int slab) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  const int f0 = blockIdx.y * slab, f1 = min(n, f0 + slab);
+  float acc = 0.f;
+  if (db_enc) {
+    for (int f = f0; f < f1; ++f) acc = fmaf(-__ldg(db_enc + f), __ldg(W_enc + static_cast<int64_t>(f) * d + c), acc);
+  }
+  if (blockIdx.y == 0 && colsum) acc = fmaf(scales[0], colsum[c], acc);
+  atomicAdd(db_dec + c, acc);
+}
+
+__global__ void loss_scalars_kernel(const double* __restrict__ sse, const double* __restrict__ tv,
+                                    float* __restrict__ out, double inv_numel) {
+  double t = *tv;
+  if (t == 0.0) t = 1.0;  // topkautoencoder.py:105-106
+  const double s = *sse;
+  out[0] = static_cast<float>(s / t);
+  out[1] = static_cast<float>(s * inv_numel);
+  out[2] = static_cast<float>(2.0 / t);
+  out[3] = out[2];
+  out[4] = static_cast<float>(t);
+}
+
+__global__ void __launch_bounds__(256) dead_update_kernel(const int32_t* __restrict__ offsets,
+                                                          int64_t* __restrict__ frames, int n, int64_t n_tokens) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f < n) frames[f] = offsets[f + 1] > offsets[f] ? 0 : frames[f] + n_tokens;
+}
+
+// One warp per row.
+__global__ void __launch_bounds__(256) rownorm_kernel(float* __restrict__ W, int64_t rows, int cols, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  float* w = W + r * cols;
+  float s = 0.f;
+  for (int c = lane; c < cols; c += 32) s = fmaf(w[c], w[c], s);
+  s = warp_sum(s);
+  const float inv = 1.f / (sqrtf(s) + eps);
+  for (int c = lane; c < cols; c += 32) w[c] *= inv;
+}
+__global__ void __launch_bounds__(256) remove_parallel_kernel(float* __restrict__ G, const float* __restrict__ W,
+                                                              int64_t rows, int cols) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  float* gr = G + r * cols;
+  const float* w = W + r * cols;
+  float s = 0.f;
+  for (int c = lane; c < cols; c += 32) s = fmaf(gr[c], w[c], s);
+  s = warp_sum(s);
+  for (int c = lane; c < cols; c += 32) gr[c] = fmaf(-s, w[c], gr[c]);
+}
+
+static inline int grid_for(int64_t work, int block, int max_blocks) {
+  int64_t g = (work + block - 1) / block;
+  if (g > max_blocks) g = max_blocks;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+}  // namespace freud
+
+using namespace freud;
+#define STREAM static_cast<cudaStream_t>(stream)
+
+extern "C" int freud_topk_prep_x(const float* x, const float* b_dec, void* xc_hi, void* xc_lo, double* tv, int64_t B,
+                                 int64_t T, int64_t d, int precision, void* stream) {
+  FREUD_REQUIRE(B > 0 && T > 0 && d > 0 && d % 4 == 0, "prep_x needs d % 4 == 0");
+  FREUD_CHECK_CUDA(cudaMemsetAsync(tv, 0, sizeof(double), STREAM));
+  const int64_t work = T * (d / 4);
+  const int grid = static_cast<int>((work + 255) / 256);
+  if (precision == FREUD_BF16)
+    prep_x_kernel<0><<<grid, 256, 0, STREAM>>>(x, b_dec, xc_hi, xc_lo, tv, (int)B, T, (int)d);
+  else
+    prep_x_kernel<1><<<grid, 256, 0, STREAM>>>(x, b_dec, xc_hi, xc_lo, tv, (int)B, T, (int)d);
+  FREUD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int freud_split_operand(const float* w, void* hi, void* lo, int64_t numel, int precision, void* stream) {
+  FREUD_REQUIRE(numel % 4 == 0, "split_operand needs numel % 4 == 0");
+  const int grid = grid_for(numel / 4, 256, sm_count() * 8);
+  if (precision == FREUD_BF16)
+    split_operand_kernel<0><<<grid, 256, 0, STREAM>>>(w, hi, lo, numel / 4);
+  else
+    split_operand_kernel<1><<<grid, 256, 0, STREAM>>>(w, hi, lo, numel / 4);
+  FREUD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+namespace {
+template <typename WT, typename RT>
+int launch_decode(const float* tv, const int32_t* ti, const void* W, const float* b_dec, const float* target,
+                  float* sae_out, void* resid, double* sse, float* colsum, int64_t N, int d, int k, cudaStream_t s) {
+  const int grid = grid_for(N, 8, sm_count() * 8);
+  const size_t sm = d * sizeof(float);
+#define LD(CH)                                                                                                   \
+  decode_kernel<WT, RT, CH><<<grid, 256, sm, s>>>(tv, ti, static_cast<const WT*>(W), b_dec, target, sae_out,     \
+                                                   static_cast<RT*>(resid), sse, colsum, N, d, k)
+  if (d <= 384) LD(3);
+  else if (d <= 768) LD(6);
+  else if (d <= 1280) LD(10);
+  else LD(16);
+#undef LD
+  return 0;
+}
+template <typename GT, typename WT>
+int launch_dacts(const void* g, const int32_t* ti, const void* W, float* dacts, int64_t N, int d, int k,
+                 cudaStream_t s) {
+  const int grid = grid_for(N, 8, sm_count() * 8);
+#define LD(CH) \
+  dacts_kernel<GT, WT, CH><<<grid, 256, 0, s>>>(static_cast<const GT*>(g), ti, static_cast<const WT*>(W), dacts, N, d, k)
+  if (d <= 384) LD(3);
+  else if (d <= 768) LD(6);
+  else if (d <= 1280) LD(10);
+  else LD(16);
+#undef LD
+  return 0;
+}
+}  // namespace
+
+extern "C" int freud_topk_decode(const float* top_vals, const int32_t* top_idx, const void* W_dec, int w_is_bf16,
+                                 const float* b_dec, const float* target, float* sae_out, void* resid,
+                                 int resid_is_bf16, double* sse, float* colsum, int64_t N, int64_t d, int64_t k,
+                                 void* stream) {
+  FREUD_REQUIRE(N > 0 && k > 0 && d % 4 == 0 && d <= 2048, "decode needs d % 4 == 0 and d <= 2048");
+  FREUD_REQUIRE(target != nullptr || (resid == nullptr && sse == nullptr && colsum == nullptr),
+                "residual outputs need a target");
+  if (w_is_bf16) {
+    if (resid_is_bf16)
+      launch_decode<__nv_bfloat16, __nv_bfloat16>(top_vals, top_idx, W_dec, b_dec, target, sae_out, resid, sse, colsum, N, (int)d, (int)k, STREAM);
+    else
+      launch_decode<__nv_bfloat16, float>(top_vals, top_idx, W_dec, b_dec, target, sae_out, resid, sse, colsum, N, (int)d, (int)k, STREAM);
+  } else {
+    if (resid_is_bf16)
+      launch_decode<float, __nv_bfloat16>(top_vals, top_idx, W_dec, b_dec, target, sae_out, resid, sse, colsum, N, (int)d, (int)k, STREAM);
+    else
+      launch_decode<float, float>(top_vals, top_idx, W_dec, b_dec, target, sae_out, resid, sse, colsum, N, (int)d, (int)k, STREAM);
+  }
+  FREUD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int freud_topk_dacts(const void* g, int g_is_bf16, const int32_t* top_idx, const void* W_dec,
+                                int w_is_bf16, float* dacts, int64_t N, int64_t d, int64_t k, void* stream) {
+  FREUD_REQUIRE(N > 0 && k > 0 && d % 4 == 0 && d <= 2048, "dacts needs d % 4 == 0 and d <= 2048");
+  if (g_is_bf16) {
+    if (w_is_bf16) launch_dacts<__nv_bfloat16, __nv_bfloat16>(g, top_idx, W_dec, dacts, N, (int)d, (int)k, STREAM);
+    else launch_dacts<__nv_bfloat16, float>(g, top_idx, W_dec, dacts, N, (int)d, (int)k, STREAM);
+  } else {
+    if (w_is_bf16) launch_dacts<float, __nv_bfloat16>(g, top_idx, W_dec, dacts, N, (int)d, (int)k, STREAM);
+    else launch_dacts<float, float>(g, top_idx, W_dec, dacts, N, (int)d, (int)k, STREAM);
+  }
+  FREUD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int freud_axpby(const float* a, const float* b, const float* coef, void* out, int out_is_bf16,
+                           int64_t numel, void* stream) {
+  FREUD_REQUIRE(numel % 4 == 0, "axpby needs numel % 4 == 0");
+  const int grid = grid_for(numel / 4, 256, sm_count() * 8);
+  if (out_is_bf16)
+    axpby_kernel<__nv_bfloat16><<<grid, 256, 0, STREAM>>>(a, b, coef, static_cast<__nv_bfloat16*>(out), numel / 4);
+  else
+    axpby_kernel<float><<<grid, 256, 0, STREAM>>>(a, b, coef, static_cast<float*>(out), numel / 4);
+  FREUD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int freud_csc_build(const int32_t* top_idx, int64_t N, int64_t k, int64_t n, int32_t* offsets,
+                               int32_t* entries, int32_t* cursor, void* stream) {
+  const int64_t total = N * k;
+  FREUD_REQUIRE(total > 0 && total < (1ll << 31) && n > 0 && n < (1ll << 31), "csc sizes out of range");
+  FREUD_CHECK_CUDA(cudaMemsetAsync(offsets, 0, (n + 1) * sizeof(int32_t), STREAM));
+  const int grid = grid_for(total, 256, sm_count() * 8);
+  csc_hist_kernel<<<grid, 256, 0, STREAM>>>(top_idx, total, offsets);
+  csc_scan_kernel<<<1, 1024, 0, STREAM>>>(offsets, cursor, (int)n);
+  csc_fill_kernel<<<grid, 256, 0, STREAM>>>(top_idx, total, cursor, entries);
+  csc_sort_kernel<<<(int)n, 256, 0, STREAM>>>(offsets, entries);
+  FREUD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int freud_topk_sparse_grads(const int32_t* offsets, const int32_t* entries, const float* top_vals,
+                                       const float* dacts, const void* g, int g_is_bf16, const void* xc,
+                                       int xc_is_bf16, const float* b_dec, const float* scales, float* dW_dec,
+                                       float* dW_enc, float* db_enc, int64_t n, int64_t d, int64_t k, int accumulate,
+                                       void* stream) {
+  FREUD_REQUIRE(n > 0 && d % 4 == 0, "sparse_grads needs d % 4 == 0");
+  FREUD_REQUIRE(g_is_bf16 == xc_is_bf16, "g and xc must share a storage type");
+  FREUD_REQUIRE(xc_is_bf16 || b_dec != nullptr, "fp32 path recomputes x - b_dec and needs b_dec");
+  int threads = (int)((d / 4 + 31) / 32) * 32;
+  if (threads > 256) threads = 256;
+  if (g_is_bf16)
+    sparse_grads_kernel<__nv_bfloat16, __nv_bfloat16><<<(int)n, threads, 0, STREAM>>>(
+        offsets, entries, top_vals, dacts, static_cast<const __nv_bfloat16*>(g),
+        static_cast<const __nv_bfloat16*>(xc), b_dec, scales, dW_dec, dW_enc, db_enc, (int)d, (int)k, accumulate);
+  else
+    sparse_grads_kernel<float, float><<<(int)n, threads, 0, STREAM>>>(
+        offsets, entries, top_vals, dacts, static_cast<const float*>(g), static_cast<const float*>(xc), b_dec, scales,
+        dW_dec, dW_enc, db_enc, (int)d, (int)k, accumulate);
+  FREUD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int freud_topk_bdec_grad(const float* colsum, const float* scales, const float* db_enc, const float* W_enc,
+                                    float* db_dec, int64_t n, int64_t d, int accumulate, void* stream) {
+  FREUD_REQUIRE(d > 0, "bdec_grad needs d > 0");
+  FREUD_REQUIRE(db_enc == nullptr || W_enc != nullptr, "db_enc term needs W_enc");
+  FREUD_REQUIRE(colsum == nullptr || scales != nullptr, "colsum term needs scales");
+  if (!accumulate) FREUD_CHECK_CUDA(cudaMemsetAsync(db_dec, 0, d * sizeof(float), STREAM));
+  const int slab = 256;
+  dim3 grid((unsigned)((d + 255) / 256), (unsigned)(db_enc ? (n + slab - 1) / slab : 1));
+  bdec_grad_kernel<<<grid, 256, 0, STREAM>>>(colsum, scales, db_enc, W_enc, db_dec, (int)n, (int)d, slab);
+  FREUD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int freud_topk_loss_scalars(const double* sse, const double* tv, float* out, int64_t numel, void* stream) {
+  loss_scalars_kernel<<<1, 1, 0, STREAM>>>(sse, tv, out, 1.0 / (double)numel);
+  FREUD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int freud_dead_latent_update(const int32_t* offsets, int64_t* frames, int64_t n, int64_t n_tokens,
+                                        void* stream) {
+  dead_update_kernel<<<(int)((n + 255) / 256), 256, 0, STREAM>>>(offsets, frames, (int)n, n_tokens);
+  FREUD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int freud_rownorm_project(float* W, int64_t rows, int64_t cols, float eps, void* stream) {
+  rownorm_kernel<<<(int)((rows + 7) / 8), 256, 0, STREAM>>>(W, rows, (int)cols, eps);
+  FREUD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int freud_remove_parallel_grad(float* G, const float* W, int64_t rows, int64_t cols, void* stream) {
+  remove_parallel_kernel<<<(int)((rows + 7) / 8), 256, 0, STREAM>>>(G, W, rows, (int)cols);
+  FREUD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

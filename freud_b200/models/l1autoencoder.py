@@ -1,0 +1,150 @@
+"""Drop-in mirror of src/models/l1autoencoder.py (reference :15-95) on the freud_b200 CUDA kernels.
+
+Tied-weight L1 SAE: state_dict keys `encoder_bias` [n] and `decoder.weight` [d, n]; `encode` renormalises the
+decoder columns IN PLACE on every call (reference :71-73), forward returns L1ForwardOutput.  CUDA only.
+"""
+from typing import NamedTuple
+
+import torch
+from torch import Tensor, nn
+
+from .. import ops
+from .._lib import BF16, FP32
+from ..utils.models import get_n_dict_components
+from .config import L1AutoEncoderConfig
+from .topkautoencoder import _precision
+
+
+class L1EncoderOutput(NamedTuple):
+    latent: Tensor
+
+
+class L1ForwardOutput(NamedTuple):
+    sae_out: Tensor
+
+    encoded: L1EncoderOutput
+
+    l1_loss: Tensor
+
+    reconstruction_loss: Tensor
+
+
+def mse_loss(input, target, ignored_index, reduction):
+    """mse_loss with ignored_index (reference :29-36), as one masked reduction kernel."""
+    if reduction != "mean":
+        raise NotImplementedError("freud_b200 mse_loss implements reduction='mean' (the only one the SAE uses)")
+    if ignored_index != -1:
+        raise NotImplementedError("freud_b200 mse_loss implements ignored_index=-1 (the only one the SAE uses)")
+    x = target.contiguous().float()
+    xh = input.contiguous().float()
+    d = x.shape[-1]
+    dummy = torch.zeros((x.numel() // d, 1), dtype=torch.float32, device=x.device)
+    acc, _ = ops.l1_loss_reduce(dummy, xh.view(-1, d), x.view(-1, d), False)
+    return (acc[1] / acc[2]).float()
+
+
+def _gemm_operands(t: Tensor, precision: int):
+    return ops.split_operand(t, precision)
+
+
+class _L1ForwardFn(torch.autograd.Function):
+    """(x, W, b) -> (x_hat, latent, l1_loss, reconstruction_loss, mse); losses carry gradient to W and b."""
+
+    @staticmethod
+    def forward(ctx, x2, W, b, recon_alpha, precision):
+        N, d = x2.shape
+        n = W.shape[1]
+        Wt = ops.l1_colnorm(W.data)  # in place on decoder.weight.data + K-major transposed copy
+        x_ops = _gemm_operands(x2, precision)
+        wt_ops = _gemm_operands(Wt, precision)
+        w_ops = _gemm_operands(W.data, precision)
+        latent = ops.gemm_nt(x_ops[0], x_ops[1], wt_ops[0], wt_ops[1], b, True, precision)       # relu(x @ W + b)
+        c_ops = _gemm_operands(latent, precision)
+        x_hat = ops.gemm_nt(c_ops[0], c_ops[1], w_ops[0], w_ops[1], None, False, precision)      # c @ W.T
+        need_grad = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        acc, dxhat = ops.l1_loss_reduce(latent, x_hat, x2, need_grad)
+        l1 = (acc[0] / N).float()
+        recon = (recon_alpha * acc[1] / acc[2]).float()
+        mse = (acc[3] / (N * d)).float()
+        ctx.saved = (x2, latent, dxhat, acc, wt_ops, Wt, precision, recon_alpha)
+        ctx.mark_non_differentiable(x_hat, latent, mse)
+        return x_hat, latent, l1, recon, mse
+
+    @staticmethod
+    def backward(ctx, g_xhat, g_latent, g_l1, g_recon, g_mse):
+        x2, latent, dxhat, acc, wt_ops, Wt, precision, recon_alpha = ctx.saved
+        N, d = x2.shape
+        dev = x2.device
+        zero = torch.zeros((), dtype=torch.float32, device=dev)
+        g_l1 = zero if g_l1 is None else g_l1.float()
+        g_recon = zero if g_recon is None else g_recon.float()
+        s_recon = (g_recon.double() * (2.0 * recon_alpha) / acc[2]).float()   # d recon / d x_hat = 2*alpha*(x_hat-x)/N_unmasked
+        s_l1 = g_l1 / N                                                       # d l1 / d c = 1[c>0]/N
+        # dc (unscaled) = dxhat_raw @ W  as  A = dxhat [N, K=d], B = W^T [n, K=d]
+        dx_ops = _gemm_operands(dxhat, precision)
+        dc = ops.gemm_nt(dx_ops[0], dx_ops[1], wt_ops[0], wt_ops[1], None, False, precision)
+        db = ops.l1_dz(dc, latent, torch.stack((s_recon, s_l1)))              # dc becomes dz in place
+        dW = ops.l1_weight_grad(x2, dc, dxhat, latent, torch.stack((torch.ones_like(s_recon), s_recon)))
+        ctx.saved = None
+        return None, dW, db, None, None
+
+
+class L1AutoEncoder(nn.Module):
+    def __init__(self, activation_size: int, cfg: L1AutoEncoderConfig):
+        """Same construction order as the reference (:40-67): decoder Linear, zero bias, orthogonal init."""
+        super(L1AutoEncoder, self).__init__()
+        self.cfg = cfg
+        self.tied = True  # tie encoder and decoder weights
+        self.activation_size = activation_size
+        self.n_dict_components = get_n_dict_components(activation_size, cfg.expansion_factor, cfg.n_dict_components)
+        self.recon_alpha = cfg.recon_alpha
+
+        self.decoder = nn.Linear(self.n_dict_components, self.activation_size, bias=False)
+        self.encoder_bias = nn.Parameter(torch.zeros(self.n_dict_components))
+        nn.init.orthogonal_(self.decoder.weight)
+        self.encoder = nn.Sequential(nn.ReLU())
+        self.precision = "auto"
+
+    def _check(self, x: Tensor):
+        if not x.is_cuda:
+            raise RuntimeError("freud_b200 L1AutoEncoder runs on CUDA only (no CPU fallback); move the model and "
+                               "the activations to a CUDA device")
+        return x.float().contiguous()
+
+    def encode(self, x: Tensor):
+        x = self._check(x)
+        d = x.shape[-1]
+        prec = _precision(self.precision)
+        with torch.no_grad():
+            Wt = ops.l1_colnorm(self.decoder.weight.data)  # unit-norm constraint, in place (reference :71-73)
+            x_ops = _gemm_operands(x.view(-1, d), prec)
+            wt_ops = _gemm_operands(Wt, prec)
+            c = ops.gemm_nt(x_ops[0], x_ops[1], wt_ops[0], wt_ops[1], self.encoder_bias, True, prec)
+        return L1EncoderOutput(latent=c.view(*x.shape[:-1], self.n_dict_components))
+
+    def decode(self, c: Tensor):
+        c = self._check(c)
+        n = c.shape[-1]
+        prec = _precision(self.precision)
+        with torch.no_grad():
+            c_ops = _gemm_operands(c.view(-1, n), prec)
+            w_ops = _gemm_operands(self.decoder.weight.data, prec)
+            out = ops.gemm_nt(c_ops[0], c_ops[1], w_ops[0], w_ops[1], None, False, prec)
+        return out.view(*c.shape[:-1], self.activation_size)
+
+    def forward(self, x: Tensor, return_mse: bool = False):
+        x = self._check(x)
+        d = x.shape[-1]
+        x_hat, latent, l1, recon, mse = _L1ForwardFn.apply(x.view(-1, d), self.decoder.weight, self.encoder_bias,
+                                                           float(self.recon_alpha), _precision(self.precision))
+        lead = x.shape[:-1]
+        c = latent.view(*lead, self.n_dict_components)
+        forward_output = L1ForwardOutput(
+            sae_out=x_hat.view(*lead, d),
+            encoded=L1EncoderOutput(c),
+            l1_loss=l1,
+            reconstruction_loss=recon,
+        )
+        if return_mse:
+            return forward_output, mse
+        return forward_output

@@ -1,0 +1,284 @@
+"""Torch-tensor front end of the C ABI: allocates outputs / workspaces with torch (the caller owns all memory)
+and enqueues the CUDA kernels on torch's current stream.  No CPU path: every op requires CUDA tensors."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import BF16, FP32, TensorList, call
+
+K_FUSED = 32  # selection width of the fused encoder epilogue
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("freud_b200 ops need CUDA tensors (there is no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError("freud_b200 ops need contiguous tensors")
+    return C.c_void_p(t.data_ptr())
+
+
+def _f32(t, name):
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    return t
+
+
+# ------------------------------------------------------------------------------------------------ TopK forward
+def split_operand(w: torch.Tensor, precision: int):
+    """W -> GEMM operand(s): bf16 copy, or (hi, lo) tf32 split."""
+    _f32(w, "w")
+    if precision == BF16:
+        hi = torch.empty_like(w, dtype=torch.bfloat16)
+        call("freud_split_operand", _ptr(w), _ptr(hi), None, w.numel(), precision, _stream())
+        return hi, None
+    hi, lo = torch.empty_like(w), torch.empty_like(w)
+    call("freud_split_operand", _ptr(w), _ptr(hi), _ptr(lo), w.numel(), precision, _stream())
+    return hi, lo
+
+
+def topk_prep_x(x: torch.Tensor, b_dec: torch.Tensor, precision: int):
+    """x [B,T,d] -> ((xc_hi, xc_lo) operand(s) of x - b_dec as [N,d], tv double[1])."""
+    _f32(x, "x")
+    B, T, d = x.shape
+    tv = torch.empty(1, dtype=torch.float64, device=x.device)
+    if precision == BF16:
+        hi = torch.empty((B * T, d), dtype=torch.bfloat16, device=x.device)
+        lo = None
+    else:
+        hi = torch.empty((B * T, d), dtype=torch.float32, device=x.device)
+        lo = torch.empty_like(hi)
+    call("freud_topk_prep_x", _ptr(x), _ptr(b_dec), _ptr(hi), _ptr(lo), _ptr(tv), B, T, d, precision, _stream())
+    return hi, lo, tv
+
+
+def topk_encode(xc_hi, xc_lo, w_hi, w_lo, b_enc, precision: int):
+    """Fused GEMM + bias + ReLU + top-32.  Returns (top_vals fp32 [N,32], top_idx int32 [N,32])."""
+    N, d = xc_hi.shape
+    n = w_hi.shape[0]
+    vals = torch.empty((N, K_FUSED), dtype=torch.float32, device=xc_hi.device)
+    idx = torch.empty((N, K_FUSED), dtype=torch.int32, device=xc_hi.device)
+    call("freud_topk_encode", _ptr(xc_hi), _ptr(xc_lo), _ptr(w_hi), _ptr(w_lo), _ptr(b_enc), _ptr(vals), _ptr(idx),
+         N, d, n, precision, _stream())
+    return vals, idx
+
+
+def gemm_nt(a_hi, a_lo, b_hi, b_lo, bias, relu: bool, precision: int, out=None):
+    """out[M,N] = act(A @ B^T + bias) on the tensor cores (operands as from split_operand / topk_prep_x)."""
+    M, K = a_hi.shape
+    Nn = b_hi.shape[0]
+    if out is None:
+        out = torch.empty((M, Nn), dtype=torch.float32, device=a_hi.device)
+    call("freud_gemm_nt", _ptr(a_hi), _ptr(a_lo), _ptr(b_hi), _ptr(b_lo), _ptr(bias), _ptr(out), M, Nn, K,
+         out.stride(0), int(relu), precision, _stream())
+    return out
+
+
+def row_topk(latents: torch.Tensor, k: int, col_mask: torch.Tensor | None = None):
+    _f32(latents, "latents")
+    rows, n = latents.shape
+    vals = torch.empty((rows, k), dtype=torch.float32, device=latents.device)
+    idx = torch.empty((rows, k), dtype=torch.int32, device=latents.device)
+    m = None
+    if col_mask is not None:
+        m = col_mask.to(torch.uint8).contiguous()
+    call("freud_row_topk", _ptr(latents), _ptr(m), _ptr(vals), _ptr(idx), rows, n, k, _stream())
+    return vals, idx
+
+
+def topk_decode(top_vals, top_idx, W_dec, b_dec, target=None, *, resid_dtype=None, want_sse=False,
+                want_colsum=False):
+    """sae_out = sum_j a_j W_dec[i_j] + b_dec; optional residual / sse / column sums against `target`."""
+    N, k = top_vals.shape
+    d = W_dec.shape[1]
+    dev = top_vals.device
+    sae_out = torch.empty((N, d), dtype=torch.float32, device=dev)
+    resid = torch.empty((N, d), dtype=resid_dtype, device=dev) if resid_dtype is not None else None
+    sse = torch.zeros(1, dtype=torch.float64, device=dev) if want_sse else None
+    colsum = torch.zeros(d, dtype=torch.float32, device=dev) if want_colsum else None
+    call("freud_topk_decode", _ptr(top_vals), _ptr(top_idx), _ptr(W_dec), int(W_dec.dtype == torch.bfloat16),
+         _ptr(b_dec), _ptr(target), _ptr(sae_out), _ptr(resid),
+         int(resid is not None and resid.dtype == torch.bfloat16), _ptr(sse), _ptr(colsum), N, d, k, _stream())
+    return sae_out, resid, sse, colsum
+
+
+def topk_dacts(g, top_idx, W_dec):
+    N, k = top_idx.shape
+    d = W_dec.shape[1]
+    out = torch.empty((N, k), dtype=torch.float32, device=g.device)
+    call("freud_topk_dacts", _ptr(g), int(g.dtype == torch.bfloat16), _ptr(top_idx), _ptr(W_dec),
+         int(W_dec.dtype == torch.bfloat16), _ptr(out), N, d, k, _stream())
+    return out
+
+
+def axpby(a, b, coef, out_dtype):
+    out = torch.empty(a.shape, dtype=out_dtype, device=a.device)
+    call("freud_axpby", _ptr(a), _ptr(b), _ptr(coef), _ptr(out), int(out_dtype == torch.bfloat16), a.numel(),
+         _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ TopK backward
+def csc_build(top_idx: torch.Tensor, n: int):
+    N, k = top_idx.shape
+    dev = top_idx.device
+    offsets = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    entries = torch.empty(N * k, dtype=torch.int32, device=dev)
+    cursor = torch.empty(n, dtype=torch.int32, device=dev)
+    call("freud_csc_build", _ptr(top_idx), N, k, n, _ptr(offsets), _ptr(entries), _ptr(cursor), _stream())
+    return offsets, entries
+
+
+def topk_sparse_grads(offsets, entries, top_vals, dacts, g, xc, b_dec, scales, dW_dec, dW_enc, db_enc, k,
+                      accumulate: bool):
+    n, d = dW_dec.shape
+    call("freud_topk_sparse_grads", _ptr(offsets), _ptr(entries), _ptr(top_vals), _ptr(dacts), _ptr(g),
+         int(g.dtype == torch.bfloat16), _ptr(xc), int(xc.dtype == torch.bfloat16), _ptr(b_dec), _ptr(scales),
+         _ptr(dW_dec), _ptr(dW_enc), _ptr(db_enc), n, d, k, int(accumulate), _stream())
+
+
+def topk_bdec_grad(colsum, scales, db_enc, W_enc, db_dec, accumulate: bool):
+    d = db_dec.numel()
+    n = db_enc.numel() if db_enc is not None else 0
+    call("freud_topk_bdec_grad", _ptr(colsum), _ptr(scales), _ptr(db_enc), _ptr(W_enc), _ptr(db_dec), n, d,
+         int(accumulate), _stream())
+
+
+def topk_loss_scalars(sse, tv, numel: int):
+    out = torch.empty(5, dtype=torch.float32, device=sse.device)
+    call("freud_topk_loss_scalars", _ptr(sse), _ptr(tv), _ptr(out), numel, _stream())
+    return out
+
+
+def dead_latent_update(offsets, frames, n_tokens: int):
+    if frames.dtype != torch.int64:
+        raise TypeError("num_frames_since_fired must be int64")
+    call("freud_dead_latent_update", _ptr(offsets), _ptr(frames), frames.numel(), n_tokens, _stream())
+
+
+def rownorm_project(W, eps: float):
+    call("freud_rownorm_project", _ptr(_f32(W, "W")), W.shape[0], W.shape[1], eps, _stream())
+
+
+def remove_parallel_grad(G, W):
+    call("freud_remove_parallel_grad", _ptr(_f32(G, "G")), _ptr(_f32(W, "W")), W.shape[0], W.shape[1], _stream())
+
+
+# ------------------------------------------------------------------------------------------------ L1
+def l1_colnorm(W):
+    d, n = W.shape
+    Wt = torch.empty((n, d), dtype=torch.float32, device=W.device)
+    call("freud_l1_colnorm", _ptr(_f32(W, "W")), _ptr(Wt), d, n, _stream())
+    return Wt
+
+
+def l1_loss_reduce(latent, x_hat, x, want_dxhat: bool):
+    N, n = latent.shape
+    d = x.shape[-1]
+    acc = torch.zeros(4, dtype=torch.float64, device=x.device)
+    dxhat = torch.empty((N, d), dtype=torch.float32, device=x.device) if want_dxhat else None
+    call("freud_l1_loss_reduce", _ptr(latent), _ptr(x_hat), _ptr(x), _ptr(dxhat), _ptr(acc), N, d, n, _stream())
+    return acc, dxhat
+
+
+def l1_dz(dc, latent, scales):
+    N, n = latent.shape
+    db = torch.zeros(n, dtype=torch.float32, device=dc.device)
+    call("freud_l1_dz", _ptr(dc), _ptr(latent), _ptr(scales), _ptr(db), N, n, _stream())
+    return db
+
+
+def l1_weight_grad(x, dz, dxhat, latent, scales):
+    N, d = x.shape
+    n = latent.shape[1]
+    dW = torch.empty((d, n), dtype=torch.float32, device=x.device)
+    call("freud_l1_weight_grad", _ptr(x), _ptr(dz), _ptr(dxhat), _ptr(latent), _ptr(scales), _ptr(dW), N, d, n,
+         _stream())
+    return dW
+
+
+# ------------------------------------------------------------------------------------------------ optimiser
+def make_tensor_list(params, grads, exp_avgs=None, exp_avg_sqs=None, shadows=None) -> TensorList:
+    if len(params) > _lib.MAX_TENSORS:
+        raise ValueError(f"at most {_lib.MAX_TENSORS} tensors per list")
+    tl = TensorList()
+    tl.count = len(params)
+    for i, p in enumerate(params):
+        for t in (p, grads[i]):
+            if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+                raise RuntimeError("optimizer tensors must be contiguous float32 CUDA tensors")
+        tl.param[i] = p.data_ptr()
+        tl.grad[i] = grads[i].data_ptr()
+        tl.exp_avg[i] = exp_avgs[i].data_ptr() if exp_avgs is not None else None
+        tl.exp_avg_sq[i] = exp_avg_sqs[i].data_ptr() if exp_avg_sqs is not None else None
+        tl.bf16_shadow[i] = shadows[i].data_ptr() if shadows is not None and shadows[i] is not None else None
+        tl.numel[i] = p.numel()
+    return tl
+
+
+def grad_sumsq(tl: TensorList, device):
+    out = torch.empty(1, dtype=torch.float64, device=device)
+    call("freud_grad_sumsq", C.byref(tl), _ptr(out), _stream())
+    return out
+
+
+def clip_grads(tl: TensorList, sumsq, max_norm: float):
+    norm = torch.empty((), dtype=torch.float32, device=sumsq.device)
+    call("freud_clip_grads", C.byref(tl), _ptr(sumsq), max_norm, _ptr(norm), _stream())
+    return norm
+
+
+def adam_step(tl: TensorList, lr, beta1, beta2, eps, step: int, sumsq=None, max_norm: float = 0.0):
+    call("freud_adam_step", C.byref(tl), lr, beta1, beta2, eps, step, _ptr(sumsq), max_norm, _stream())
+
+
+def radam_step(tl: TensorList, lr, beta1, beta2, eps, weight_decay, step: int, sumsq=None, max_norm: float = 0.0):
+    call("freud_radam_step", C.byref(tl), lr, beta1, beta2, eps, weight_decay, step, _ptr(sumsq), max_norm,
+         _stream())
+
+
+# ------------------------------------------------------------------------------------------------ search
+def search_dense(acts, n_frames, feature: int, want_trace: bool):
+    n_files, T, F = acts.shape
+    dev = acts.device
+    vmax = torch.empty(n_files, dtype=torch.float32, device=dev)
+    amax = torch.empty(n_files, dtype=torch.int32, device=dev)
+    vabs = torch.empty(n_files, dtype=torch.float32, device=dev)
+    trace = torch.empty((n_files, T), dtype=torch.float32, device=dev) if want_trace else None
+    if acts.dtype not in (torch.float32, torch.float16):
+        raise TypeError("dense activations must be float32 or float16")
+    call("freud_search_dense", _ptr(acts), int(acts.dtype == torch.float16), _ptr(n_frames), n_files, T, F, feature,
+         _ptr(vmax), _ptr(amax), _ptr(vabs), _ptr(trace), _stream())
+    return vmax, amax, vabs, trace
+
+
+def search_indexed(vals, idx, n_frames, feature: int, want_trace: bool):
+    n_files, T, k = vals.shape
+    dev = vals.device
+    vmax = torch.empty(n_files, dtype=torch.float32, device=dev)
+    amax = torch.empty(n_files, dtype=torch.int32, device=dev)
+    vabs = torch.empty(n_files, dtype=torch.float32, device=dev)
+    trace = torch.empty((n_files, T), dtype=torch.float32, device=dev) if want_trace else None
+    if idx.dtype not in (torch.int64, torch.int32):
+        raise TypeError("feature indices must be int64 or int32")
+    call("freud_search_indexed", _ptr(_f32(vals, "vals")), _ptr(idx), int(idx.dtype == torch.int64), _ptr(n_frames),
+         n_files, T, k, feature, _ptr(vmax), _ptr(amax), _ptr(vabs), _ptr(trace), _stream())
+    return vmax, amax, vabs, trace
+
+
+def search_topn(vmax, vabs, absolute: bool, min_val, max_val, n_top: int):
+    dev = vmax.device
+    out = torch.empty(n_top, dtype=torch.int32, device=dev)
+    cnt = torch.empty(1, dtype=torch.int32, device=dev)
+    call("freud_search_topn", _ptr(vmax), _ptr(vabs), vmax.numel(), int(absolute), int(min_val is not None),
+         float(min_val if min_val is not None else 0.0), int(max_val is not None),
+         float(max_val if max_val is not None else 0.0), n_top, _ptr(out), _ptr(cnt), _stream())
+    return out, cnt

@@ -1,0 +1,186 @@
+"""Kernel orchestration of the TopK SAE forward / backward (reference: TopKAutoEncoder.forward,
+src/models/topkautoencoder.py:93-151, and its autograd; formulas in SURVEY.md M5-M8').
+
+Two routes through the same C ABI:
+  fast    : k == 32, no live dead mask, no multi-TopK -- fused tcgen05 GEMM + top-k epilogue, the [N,n]
+            pre-activations never exist.
+  generic : AuxK and/or multi-TopK and/or k != 32 -- pre-activations materialised by the store-epilogue GEMM,
+            selections by the radix row top-k kernel, one sparse backward per decode.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Optional
+
+import torch
+
+from . import ops
+from ._lib import BF16, FP32
+
+
+@dataclass
+class TopKState:
+    """Everything the backward needs (all device tensors)."""
+    precision: int
+    x2: torch.Tensor            # [N,d] fp32 view of the input
+    xc_hi: torch.Tensor         # encoder A operand (bf16, or tf32-hi)
+    wd: torch.Tensor            # decoder weight as gathered (bf16 copy or the fp32 parameter)
+    W_enc: torch.Tensor
+    b_dec: torch.Tensor
+    k: int
+    n: int
+    scal: torch.Tensor          # [fvu, mse, 2/tv, 2/tv, tv] fp32
+    generic: bool
+    vals: torch.Tensor = None   # k-selection behind fvu
+    idx: torch.Tensor = None
+    e: torch.Tensor = None      # residual sae_out - x (bf16 in the bf16 fast path, else fp32)
+    colsum_e: torch.Tensor = None
+    aux: Optional[tuple] = None     # (a_vals, a_idx, resid_aux fp32, scale)
+    multi: Optional[tuple] = None   # (m_vals, m_idx, resid_m fp32, colsum_m)
+    auxk_alpha: float = 0.0
+    offsets: Optional[torch.Tensor] = None  # CSC offsets of the returned encoding (did_fire bookkeeping)
+    extra: dict = field(default_factory=dict)
+
+
+@dataclass
+class TopKResult:
+    sae_out: torch.Tensor       # [N,d] fp32 (of the 4k selection when multi_topk, as the reference rebinds it)
+    top_acts: torch.Tensor      # [N,k'] fp32
+    top_idx: torch.Tensor       # [N,k'] int32
+    fvu: torch.Tensor           # 0-d fp32
+    auxk_loss: torch.Tensor     # 0-d fp32, already times auxk_alpha
+    multi_topk_fvu: torch.Tensor
+    mse: torch.Tensor
+
+
+def encode_operands(x, W_enc, b_dec, precision):
+    xc_hi, xc_lo, tv = ops.topk_prep_x(x, b_dec, precision)
+    we_hi, we_lo = ops.split_operand(W_enc, precision)
+    return xc_hi, xc_lo, we_hi, we_lo, tv
+
+
+def topk_forward(x, W_enc, b_enc, W_dec, b_dec, k, *, precision, dead_mask=None, auxk_alpha=0.0, multi_topk=False,
+                 need_grad=True):
+    if x.dim() != 3:
+        raise ValueError("x must be [B, T, d]")
+    x = x.contiguous()
+    B, T, d = x.shape
+    N, n = B * T, W_enc.shape[0]
+    x2 = x.view(N, d)
+    xc_hi, xc_lo, we_hi, we_lo, tv = encode_operands(x, W_enc, b_dec, precision)
+    wd = ops.split_operand(W_dec, BF16)[0] if precision == BF16 else W_dec
+    # reference: `int(dead_mask.sum())` (topkautoencoder.py:109) -- one 8-byte device->host read, as upstream
+    num_dead = int(dead_mask.sum()) if dead_mask is not None else 0
+    generic = bool(multi_topk or num_dead > 0 or k != ops.K_FUSED)
+    zero = torch.zeros((), dtype=torch.float32, device=x.device)
+
+    pre = None
+    if not generic:
+        vals, idx = ops.topk_encode(xc_hi, xc_lo, we_hi, we_lo, b_enc, precision)
+    else:
+        pre = ops.gemm_nt(xc_hi, xc_lo, we_hi, we_lo, b_enc, True, precision)
+        vals, idx = ops.row_topk(pre, k)
+
+    fast_bwd = need_grad and not generic
+    resid_dtype = None
+    if fast_bwd:
+        resid_dtype = torch.bfloat16 if precision == BF16 else torch.float32
+    elif generic:
+        resid_dtype = torch.float32
+    sae_out, e, sse, colsum_e = ops.topk_decode(vals, idx, wd, b_dec, x2, resid_dtype=resid_dtype, want_sse=True,
+                                                want_colsum=need_grad)
+    scal = ops.topk_loss_scalars(sse, tv, N * d)
+    st = TopKState(precision, x2, xc_hi, wd, W_enc, b_dec, k, n, scal, generic, vals, idx, e, colsum_e,
+                   auxk_alpha=auxk_alpha)
+
+    auxk = zero
+    if num_dead > 0:
+        k_aux = d // 2
+        scale = min(num_dead / k_aux, 1.0)
+        k_aux = min(k_aux, num_dead)
+        a_vals, a_idx = ops.row_topk(pre, k_aux, col_mask=dead_mask)
+        _, r_aux, sse_aux, _ = ops.topk_decode(a_vals, a_idx, wd, b_dec, e, resid_dtype=torch.float32,
+                                               want_sse=True)
+        auxk = (scale * sse_aux[0] / scal[4].double()).float() * auxk_alpha
+        st.aux = (a_vals, a_idx, r_aux, scale)
+
+    mfvu = zero
+    ret_out, ret_vals, ret_idx = sae_out, vals, idx
+    if multi_topk:
+        m_vals, m_idx = ops.row_topk(pre, 4 * k)
+        m_out, r_m, sse_m, colsum_m = ops.topk_decode(m_vals, m_idx, wd, b_dec, x2, resid_dtype=torch.float32,
+                                                      want_sse=True, want_colsum=need_grad)
+        mfvu = (sse_m[0] / scal[4].double()).float()
+        st.multi = (m_vals, m_idx, r_m, colsum_m)
+        ret_out, ret_vals, ret_idx = m_out, m_vals, m_idx
+    res = TopKResult(ret_out, ret_vals, ret_idx, scal[0], auxk, mfvu, scal[1])
+    return res, st
+
+
+def topk_backward(st: TopKState, g_fvu, g_aux=None, g_multi=None, *, out=None):
+    """Parameter gradients of g_fvu*fvu + g_aux*auxk_loss + g_multi*multi_topk_fvu.
+    g_* are 0-d device tensors (or python floats).  Returns dict name -> gradient tensor.
+    `out` may supply preallocated gradient buffers {name: tensor}."""
+    dev = st.x2.device
+    n, d, k = st.n, st.x2.shape[1], st.k
+    out = out or {}
+    dW_enc = out.get("encoder.weight") if "encoder.weight" in out else torch.empty((n, d), dtype=torch.float32, device=dev)
+    dW_dec = out.get("W_dec") if "W_dec" in out else torch.empty((n, d), dtype=torch.float32, device=dev)
+    db_enc = out.get("encoder.bias") if "encoder.bias" in out else torch.empty(n, dtype=torch.float32, device=dev)
+    db_dec = out.get("b_dec") if "b_dec" in out else torch.empty(d, dtype=torch.float32, device=dev)
+    bf16 = st.precision == BF16
+    xc = st.xc_hi if bf16 else st.x2
+    two_over_tv = st.scal[2]
+
+    if not st.generic:
+        if isinstance(g_fvu, torch.Tensor):
+            scales = st.scal[2:4] * g_fvu.to(torch.float32)
+        elif g_fvu == 1.0:
+            scales = st.scal[2:4]  # (2/tv, 2/tv) straight from the loss-scalar kernel, no extra launch
+        else:
+            scales = st.scal[2:4] * float(g_fvu)
+        dacts = ops.topk_dacts(st.e, st.idx, st.wd)
+        offsets, entries = ops.csc_build(st.idx, n)
+        st.offsets = offsets
+        ops.topk_sparse_grads(offsets, entries, st.vals, dacts, st.e, xc, st.b_dec, scales, dW_dec, dW_enc, db_enc,
+                              k, False)
+        ops.topk_bdec_grad(st.colsum_e, scales, db_enc, st.W_enc, db_dec, False)
+    else:
+        def as_t(g):
+            if g is None:
+                return torch.zeros((), dtype=torch.float32, device=dev)
+            return g.to(torch.float32) if isinstance(g, torch.Tensor) else torch.tensor(float(g), device=dev)
+
+        gdt = torch.bfloat16 if bf16 else torch.float32
+        c_main = as_t(g_fvu) * two_over_tv
+        zero = torch.zeros((), dtype=torch.float32, device=dev)
+        decodes = []  # (tag, vals, idx, G)
+        db_direct = c_main * st.colsum_e
+        if st.aux is not None:
+            a_vals, a_idx, r_aux, scale = st.aux
+            # auxk_loss already carries auxk_alpha, so d auxk_loss / d e_hat = alpha*scale*2(e_hat - e)/tv
+            c_aux = as_t(g_aux) * (st.auxk_alpha * scale) * two_over_tv
+            G_main = ops.axpby(st.e, r_aux, torch.stack((c_main, -c_aux)), gdt)  # e is not detached (:126)
+            decodes.append(("aux", a_vals, a_idx, ops.axpby(r_aux, None, torch.stack((c_aux, zero)), gdt)))
+        else:
+            G_main = ops.axpby(st.e, None, torch.stack((c_main, zero)), gdt)
+        decodes.insert(0, ("main", st.vals, st.idx, G_main))
+        if st.multi is not None:
+            m_vals, m_idx, r_m, colsum_m = st.multi
+            c_m = as_t(g_multi) * two_over_tv
+            decodes.append(("multi", m_vals, m_idx, ops.axpby(r_m, None, torch.stack((c_m, zero)), gdt)))
+            db_direct = db_direct + c_m * colsum_m
+        ones = torch.ones(2, dtype=torch.float32, device=dev)
+        first = True
+        returned = "multi" if st.multi is not None else "main"
+        for tag, vals, idx, G in decodes:
+            dacts = ops.topk_dacts(G, idx, st.wd)
+            offsets, entries = ops.csc_build(idx, n)
+            ops.topk_sparse_grads(offsets, entries, vals, dacts, G, xc, st.b_dec, ones, dW_dec, dW_enc, db_enc,
+                                  idx.shape[1], not first)
+            first = False
+            if tag == returned:
+                st.offsets = offsets  # did_fire is taken from the RETURNED encoding (train_sae.py:442)
+        db_dec.copy_(db_direct)
+        ops.topk_bdec_grad(None, None, db_enc, st.W_enc, db_dec, True)
+    return {"encoder.weight": dW_enc, "encoder.bias": db_enc, "W_dec": dW_dec, "b_dec": db_dec}

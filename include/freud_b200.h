@@ -1,0 +1,201 @@
+/* freud_b200 -- C ABI of the B200-native SAE training / feature-search hot path.
+ *
+ * Drop-in boundary for ksadov/FREUD.  The reference has no FFI: its hot path is torch ATen ops called
+ * from Python (src/models/*.py, src/utils/activations.py, src/scripts/train_sae.py:421-453).  Each entry
+ * point below replaces the ATen sequence cited next to it; the Python host mirror in freud_b200/ binds
+ * them with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless named host_*; the caller (PyTorch) owns every buffer,
+ *     including workspaces; the library never frees or keeps a pointer after the call returns
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); calls are asynchronous
+ *   - return 0 on success; non-zero -> freud_last_error() (thread-local) describes the failure;
+ *     no exceptions cross the ABI
+ *   - row-major, innermost dimension contiguous; N = B*T tokens, d = activation size, n = dictionary size
+ *   - precision: FREUD_BF16 = bf16 tensor-core operands, fp32 accumulate (reference under autocast);
+ *                FREUD_FP32 = fp32 results (encoder GEMM as 3-pass split-TF32 on the tensor cores)
+ */
+#ifndef FREUD_B200_H_
+#define FREUD_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { FREUD_BF16 = 0, FREUD_FP32 = 1 };
+
+const char* freud_last_error(void);
+int freud_version(void);
+
+/* ------------------------------------------------------------------ TopK SAE forward */
+
+/* x - b_dec (topkautoencoder.py:74) written as the encoder GEMM's A operand, fused with the batch-axis
+ * total variance sum((x - x.mean(0))^2) of topkautoencoder.py:104 (accumulated into *tv, which the call
+ * zeroes first).  x is [B,T,d] fp32.  FREUD_BF16: xc_hi = bf16 [N,d], xc_lo unused.
+ * FREUD_FP32: xc_hi / xc_lo = fp32 [N,d] holding the tf32 high / low parts. */
+int freud_topk_prep_x(const float* x, const float* b_dec, void* xc_hi, void* xc_lo, double* tv,
+                      int64_t B, int64_t T, int64_t d, int precision, void* stream);
+
+/* Weight operand preparation (the implicit autocast cast of nn.Linear / matmul operands):
+ * FREUD_BF16: hi = bf16 copy; FREUD_FP32: hi / lo = tf32 split (fp32 storage). */
+int freud_split_operand(const float* w, void* hi, void* lo, int64_t numel, int precision, void* stream);
+
+/* Fused encoder: relu((x - b_dec) @ W_enc.T + b_enc) followed by top-32 per token, without materialising
+ * the [N,n] pre-activations (TopKAutoEncoder.pre_acts + select_topk, topkautoencoder.py:72-85, k == 32).
+ * tcgen05/TMEM GEMM fed by TMA; selection order: value descending, index ascending (set semantics of
+ * torch.topk(sorted=False)).  top_vals fp32 [N,32], top_idx int32 [N,32].  Requires n >= 64, d % 8 == 0. */
+int freud_topk_encode(const void* xc_hi, const void* xc_lo, const void* w_hi, const void* w_lo,
+                      const float* b_enc, float* top_vals, int32_t* top_idx,
+                      int64_t N, int64_t d, int64_t n, int precision, void* stream);
+
+/* out[M,N] = act(A[M,K] @ B[N,K]^T + bias[N]) on the tensor cores; act = relu if relu != 0.
+ * (pre_acts materialised for the AuxK / multi-TopK branches, topkautoencoder.py:72-77,121,135; and the
+ * L1 SAE's x @ W + b and c @ W.T, l1autoencoder.py:74,84.)  Operands prepared as for freud_topk_encode. */
+int freud_gemm_nt(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, const float* bias,
+                  float* out, int64_t M, int64_t N, int64_t K, int64_t ldo, int relu, int precision,
+                  void* stream);
+
+/* Exact per-row top-k of a materialised fp32 matrix (torch.topk(k, sorted=False), topkautoencoder.py:81,
+ * 121,135).  If col_mask != NULL, columns with col_mask[j] == 0 are treated as -inf (the
+ * torch.where(dead_mask[None], pre_acts, -inf) of :118).  Output order: value desc, index asc. */
+int freud_row_topk(const float* latents, const uint8_t* col_mask, float* vals, int32_t* idx,
+                   int64_t rows, int64_t n, int64_t k, void* stream);
+
+/* Sparse decode + residual (eager_decode + decode, topkautoencoder.py:15-18,87-91,101):
+ *   sae_out[t,:] = sum_j top_vals[t,j] * W_dec[top_idx[t,j],:] + b_dec
+ * W_dec is fp32 (w_is_bf16 == 0) or a bf16 copy.  Optional outputs (NULL to skip):
+ *   resid      [N,d]  = sae_out - target  (bf16 if resid_is_bf16 else fp32)
+ *   sse        double += sum resid^2      (caller zeroes)
+ *   colsum     [d] fp32 += sum_t resid    (caller zeroes)                                        */
+int freud_topk_decode(const float* top_vals, const int32_t* top_idx, const void* W_dec, int w_is_bf16,
+                      const float* b_dec, const float* target, float* sae_out, void* resid,
+                      int resid_is_bf16, double* sse, float* colsum,
+                      int64_t N, int64_t d, int64_t k, void* stream);
+
+/* dacts[t,j] = sum_c g[t,c] * W_dec[top_idx[t,j], c]   (gradient of decode w.r.t. the selected
+ * activations, autograd of topkautoencoder.py:17-18).  g is bf16 or fp32 [N,d]. */
+int freud_topk_dacts(const void* g, int g_is_bf16, const int32_t* top_idx, const void* W_dec, int w_is_bf16,
+                     float* dacts, int64_t N, int64_t d, int64_t k, void* stream);
+
+/* Elementwise AuxK / multi-TopK gradient seeds (autograd of topkautoencoder.py:126-138):
+ *   out = alpha * a + beta * b   (b may be NULL), alpha/beta read from device scalars coef[0], coef[1];
+ * written as bf16 or fp32. */
+int freud_axpby(const float* a, const float* b, const float* coef, void* out, int out_is_bf16,
+                int64_t numel, void* stream);
+
+/* ------------------------------------------------------------------ TopK SAE backward */
+
+/* Feature-major (CSC) index of the selected entries: offsets[f]..offsets[f+1] lists the flat positions
+ * p = t*k + j with top_idx[p] == f.  offsets is int32 [n+1]; entries int32 [N*k]; cursor int32 [n]
+ * workspace.  Also the did_fire bookkeeping of train_sae.py:442 (offsets[f+1] > offsets[f]). */
+int freud_csc_build(const int32_t* top_idx, int64_t N, int64_t k, int64_t n, int32_t* offsets,
+                    int32_t* entries, int32_t* cursor, void* stream);
+
+/* Row-sparse weight gradients of one decode (autograd of :17-18 and of nn.Linear, :75):
+ *   dW_dec[f,:] (+)= s_dec * sum_{p in list(f)} top_vals[p] * g[t(p),:]
+ *   dpre[p]       = top_vals[p] > 0 ? s_enc * dacts[p] : 0
+ *   dW_enc[f,:] (+)= sum_p dpre[p] * xc[t(p),:]        db_enc[f] (+)= sum_p dpre[p]
+ * s_dec = scales[0], s_enc = scales[1] (device floats).  g / xc: bf16 [N,d], or fp32 with xc = x - b_dec
+ * recomputed from x and b_dec when xc_is_bf16 == 0.  accumulate != 0 adds to the existing gradients. */
+int freud_topk_sparse_grads(const int32_t* offsets, const int32_t* entries, const float* top_vals,
+                            const float* dacts, const void* g, int g_is_bf16, const void* xc,
+                            int xc_is_bf16, const float* b_dec, const float* scales,
+                            float* dW_dec, float* dW_enc, float* db_enc,
+                            int64_t n, int64_t d, int64_t k, int accumulate, void* stream);
+
+/* db_dec[c] (+)= s * colsum[c] - sum_f db_enc_part[f] * W_enc[f,c]   (s = scales[0]; either term may be
+ * skipped with a NULL pointer).  Autograd of `x - b_dec` (:74) and `+ b_dec` (:91). */
+int freud_topk_bdec_grad(const float* colsum, const float* scales, const float* db_enc, const float* W_enc,
+                         float* db_dec, int64_t n, int64_t d, int accumulate, void* stream);
+
+/* Loss scalars (topkautoencoder.py:104-106,126-132,138,150), all on device:
+ *   tv' = tv == 0 ? 1 : tv;  out[0] = fvu = sse/tv';  out[1] = mse = sse/numel;
+ *   out[2] = out[3] = 2/tv' (the (s_dec, s_enc) pair freud_topk_sparse_grads reads);  out[4] = tv' */
+int freud_topk_loss_scalars(const double* sse, const double* tv, float* out, int64_t numel, void* stream);
+
+/* Dead-latent bookkeeping (train_sae.py:442-446): frames[f] = fired(f) ? 0 : frames[f] + n_tokens,
+ * fired(f) = offsets[f+1] > offsets[f]. */
+int freud_dead_latent_update(const int32_t* offsets, int64_t* frames, int64_t n, int64_t n_tokens, void* stream);
+
+/* W_dec /= ||W_dec[i,:]|| + eps   (set_decoder_norm_to_unit_norm, topkautoencoder.py:153-159) */
+int freud_rownorm_project(float* W, int64_t rows, int64_t cols, float eps, void* stream);
+/* G -= (G . W)_row * W           (remove_gradient_parallel_to_decoder_directions, :161-175) */
+int freud_remove_parallel_grad(float* G, const float* W, int64_t rows, int64_t cols, void* stream);
+
+/* ------------------------------------------------------------------ L1 SAE */
+
+/* W[:,j] /= max(||W[:,j]||, 1e-12) in place (F.normalize(dim=0), l1autoencoder.py:71-73); also writes the
+ * transposed copy Wt [n,d] used as the K-major GEMM operand.  W is decoder.weight [d,n]. */
+int freud_l1_colnorm(float* W, float* Wt, int64_t d, int64_t n, void* stream);
+
+/* Loss pieces of L1AutoEncoder.forward (l1autoencoder.py:85-86,94, mse_loss :29-36):
+ *   acc[0] += sum |c|,  acc[1] += sum_{x != -1} (x_hat-x)^2,  acc[2] += #{x != -1},  acc[3] += sum (x_hat-x)^2
+ * and, if dxhat != NULL, dxhat = (x != -1) * (x_hat - x)  (scaled later).  acc: 4 doubles, caller zeroes. */
+int freud_l1_loss_reduce(const float* latent, const float* x_hat, const float* x, float* dxhat, double* acc,
+                         int64_t N, int64_t d, int64_t n, void* stream);
+
+/* dz = (c > 0) * (s_recon * dc_recon + s_l1) in place on dc_recon [N,n]; db[j] += sum_t dz (caller zeroes). */
+int freud_l1_dz(float* dc, const float* latent, const float* scales, float* db, int64_t N, int64_t n,
+                void* stream);
+
+/* dW[d,n] = scales[0] * X^T dz + scales[1] * dxhat^T c: the two tied-weight accumulating GEMMs of SURVEY.md M3'
+ * (autograd of l1autoencoder.py:74,84) as one split-K kernel over the token axis. */
+int freud_l1_weight_grad(const float* x, const float* dz, const float* dxhat, const float* latent,
+                         const float* scales, float* dW, int64_t N, int64_t d, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------ optimiser (train_sae.py:449-450) */
+
+#define FREUD_MAX_TENSORS 8
+typedef struct {
+  int32_t count;
+  float* param[FREUD_MAX_TENSORS];
+  float* grad[FREUD_MAX_TENSORS];
+  float* exp_avg[FREUD_MAX_TENSORS];
+  float* exp_avg_sq[FREUD_MAX_TENSORS];
+  void* bf16_shadow[FREUD_MAX_TENSORS]; /* optional bf16 copy refreshed with the new parameter, or NULL */
+  int64_t numel[FREUD_MAX_TENSORS];
+} freud_tensor_list;
+
+/* sumsq[0] = sum over all tensors of grad^2 (zeroed first): the inner norms of clip_grad_norm_
+ * (torch/nn/utils/clip_grad.py:50). */
+int freud_grad_sumsq(const freud_tensor_list* host_list, double* sumsq, void* stream);
+/* grad *= clamp(max_norm / (sqrt(sumsq) + 1e-6), max=1)  (clip_grad.py:121,165-169); total norm -> *norm_out */
+int freud_clip_grads(const freud_tensor_list* host_list, const double* sumsq, float max_norm, float* norm_out,
+                     void* stream);
+/* Adam (torch/optim/adam.py:347; betas (0.9,0.999) defaults passed explicitly).  `step` is the 1-based
+ * step count.  If sumsq != NULL the clip coefficient is applied to the gradient on the fly (fused
+ * clip + Adam; the stored gradients are left unscaled). */
+int freud_adam_step(const freud_tensor_list* host_list, double lr, double beta1, double beta2, double eps,
+                    int64_t step, const double* sumsq, float max_norm, void* stream);
+/* RAdam with non-decoupled weight decay (torch/optim/radam.py:256-361). */
+int freud_radam_step(const freud_tensor_list* host_list, double lr, double beta1, double beta2, double eps,
+                     double weight_decay, int64_t step, const double* sumsq, float max_norm, void* stream);
+
+/* ------------------------------------------------------------------ feature search (utils/activations.py) */
+
+/* Per-file statistics of one feature over dense activations acts[N_files, T, F] (fp32 or fp16):
+ * for the first n_frames[i] frames (trim_activation, utils/activations.py:19-29) of column `feature`:
+ *   vmax[i] = max, amax[i] = first argmax, vabs[i] = signed value at the first argmax of |a|  (:104-119).
+ * n_frames[i] == 0 -> vmax = -inf, amax = -1.  If trace != NULL it receives the column [N_files, T] fp32. */
+int freud_search_dense(const void* acts, int acts_is_fp16, const int32_t* n_frames, int64_t n_files, int64_t T,
+                       int64_t F, int64_t feature, float* vmax, int32_t* amax, float* vabs, float* trace,
+                       void* stream);
+/* Same statistics for indexed (top-k) activations vals/idx [N_files, T, k] (activation_tensor_from_indexed,
+ * utils/activations.py:41-57: value of the first slot whose index == feature, else 0).  idx is int64 or int32. */
+int freud_search_indexed(const float* vals, const void* idx, int idx_is_int64, const int32_t* n_frames,
+                         int64_t n_files, int64_t T, int64_t k, int64_t feature, float* vmax, int32_t* amax,
+                         float* vabs, float* trace, void* stream);
+/* Ranking of utils/activations.py:88-93,121-130: among files passing the min/max filter (applied to the
+ * signed statistic), the n_top largest keys (vmax, or |vabs| when absolute != 0), ties broken by lower file
+ * index (stable sort).  use_min/use_max select the optional bounds.  out_files int32 [n_top] (-1 padded),
+ * out_count int32 [1]. */
+int freud_search_topn(const float* vmax, const float* vabs, int64_t n_files, int absolute, int use_min,
+                      double min_val, int use_max, double max_val, int64_t n_top, int32_t* out_files,
+                      int32_t* out_count, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FREUD_B200_H_ */
