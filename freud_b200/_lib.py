@@ -29,7 +29,7 @@ _p, _i64, _i, _f, _d = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_double
 
 # name -> argtypes, exactly the prototypes of include/freud_b200.h
 SIGNATURES = {
-    "freud_topk_prep_x": [_p, _p, _p, _p, _p, _i64, _i64, _i64, _i, _p],
+    "freud_topk_prep_x": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i, _p],
     "freud_split_operand": [_p, _p, _p, _i64, _i, _p],
     "freud_topk_encode": [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i, _p],
     "freud_gemm_nt": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i, _i, _p],

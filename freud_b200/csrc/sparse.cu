@@ -14,7 +14,8 @@ namespace freud {
 template <int MODE>  // 0: bf16 out, 1: tf32 hi/lo out
 __global__ void __launch_bounds__(256) prep_x_kernel(const float* __restrict__ x, const float* __restrict__ b_dec,
                                                      void* __restrict__ out_hi, void* __restrict__ out_lo,
-                                                     double* __restrict__ tv, int B, int64_t T, int d) {
+                                                     double* __restrict__ tv, float* __restrict__ colmean, int B,
+                                                     int64_t T, int d) {
   __shared__ double scratch[32];
   const int d4 = d >> 2;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -46,6 +47,10 @@ __global__ void __launch_bounds__(256) prep_x_kernel(const float* __restrict__ x
       s2.x += dv.x * dv.x; s2.y += dv.y * dv.y; s2.z += dv.z * dv.z; s2.w += dv.w * dv.w;
     }
     const double inv = 1.0 / B;
+    if (colmean) {
+      const float fi = 1.f / B;  // mean over the batch axis = shift + s1 / B
+      store4(colmean + t * d + c, make_float4(sh.x + s1.x * fi, sh.y + s1.y * fi, sh.z + s1.z * fi, sh.w + s1.w * fi));
+    }
     part = (double)s2.x - (double)s1.x * s1.x * inv + (double)s2.y - (double)s1.y * s1.y * inv +
            (double)s2.z - (double)s1.z * s1.z * inv + (double)s2.w - (double)s1.w * s1.w * inv;
   }
@@ -478,16 +483,16 @@ static inline int grid_for(int64_t work, int block, int max_blocks) {
 using namespace freud;
 #define STREAM static_cast<cudaStream_t>(stream)
 
-extern "C" int freud_topk_prep_x(const float* x, const float* b_dec, void* xc_hi, void* xc_lo, double* tv, int64_t B,
-                                 int64_t T, int64_t d, int precision, void* stream) {
+extern "C" int freud_topk_prep_x(const float* x, const float* b_dec, void* xc_hi, void* xc_lo, double* tv,
+                                 float* colmean, int64_t B, int64_t T, int64_t d, int precision, void* stream) {
   FREUD_REQUIRE(B > 0 && T > 0 && d > 0 && d % 4 == 0, "prep_x needs d % 4 == 0");
   FREUD_CHECK_CUDA(cudaMemsetAsync(tv, 0, sizeof(double), STREAM));
   const int64_t work = T * (d / 4);
   const int grid = static_cast<int>((work + 255) / 256);
   if (precision == FREUD_BF16)
-    prep_x_kernel<0><<<grid, 256, 0, STREAM>>>(x, b_dec, xc_hi, xc_lo, tv, (int)B, T, (int)d);
+    prep_x_kernel<0><<<grid, 256, 0, STREAM>>>(x, b_dec, xc_hi, xc_lo, tv, colmean, (int)B, T, (int)d);
   else
-    prep_x_kernel<1><<<grid, 256, 0, STREAM>>>(x, b_dec, xc_hi, xc_lo, tv, (int)B, T, (int)d);
+    prep_x_kernel<1><<<grid, 256, 0, STREAM>>>(x, b_dec, xc_hi, xc_lo, tv, colmean, (int)B, T, (int)d);
   FREUD_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

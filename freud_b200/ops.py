@@ -45,18 +45,22 @@ def split_operand(w: torch.Tensor, precision: int):
     return hi, lo
 
 
-def topk_prep_x(x: torch.Tensor, b_dec: torch.Tensor, precision: int):
-    """x [B,T,d] -> ((xc_hi, xc_lo) operand(s) of x - b_dec as [N,d], tv double[1])."""
+def topk_prep_x(x: torch.Tensor, b_dec: torch.Tensor, precision: int, want_colmean: bool = False):
+    """x [B,T,d] -> (xc_hi, xc_lo operand(s) of x - b_dec as [N,d], tv double[1][, x.mean(0) [T,d]])."""
     _f32(x, "x")
     B, T, d = x.shape
     tv = torch.empty(1, dtype=torch.float64, device=x.device)
+    colmean = torch.empty((T, d), dtype=torch.float32, device=x.device) if want_colmean else None
     if precision == BF16:
         hi = torch.empty((B * T, d), dtype=torch.bfloat16, device=x.device)
         lo = None
     else:
         hi = torch.empty((B * T, d), dtype=torch.float32, device=x.device)
         lo = torch.empty_like(hi)
-    call("freud_topk_prep_x", _ptr(x), _ptr(b_dec), _ptr(hi), _ptr(lo), _ptr(tv), B, T, d, precision, _stream())
+    call("freud_topk_prep_x", _ptr(x), _ptr(b_dec), _ptr(hi), _ptr(lo), _ptr(tv), _ptr(colmean), B, T, d, precision,
+         _stream())
+    if want_colmean:
+        return hi, lo, tv, colmean
     return hi, lo, tv
 
 

@@ -53,21 +53,28 @@ class TopKResult:
     mse: torch.Tensor
 
 
-def encode_operands(x, W_enc, b_dec, precision):
-    xc_hi, xc_lo, tv = ops.topk_prep_x(x, b_dec, precision)
+def encode_operands(x, W_enc, b_dec, precision, dp=None):
+    if dp is None:
+        xc_hi, xc_lo, tv = ops.topk_prep_x(x, b_dec, precision)
+    else:
+        # data parallel: variance of the CONCATENATED batch = sum_r tv_r + sum_r B_r * sum (mean_r - mean)^2
+        xc_hi, xc_lo, tv, colmean = ops.topk_prep_x(x, b_dec, precision, want_colmean=True)
+        tv = dp.global_total_variance(tv, colmean, x.shape[0])
     we_hi, we_lo = ops.split_operand(W_enc, precision)
     return xc_hi, xc_lo, we_hi, we_lo, tv
 
 
 def topk_forward(x, W_enc, b_enc, W_dec, b_dec, k, *, precision, dead_mask=None, auxk_alpha=0.0, multi_topk=False,
-                 need_grad=True):
+                 need_grad=True, dp=None):
+    """dp: optional freud_b200.parallel.DataParallel -- makes tv / sse (and with them every loss and gradient
+    scale) those of the batch concatenated over ranks; gradients stay rank-local sums for the caller to allreduce."""
     if x.dim() != 3:
         raise ValueError("x must be [B, T, d]")
     x = x.contiguous()
     B, T, d = x.shape
     N, n = B * T, W_enc.shape[0]
     x2 = x.view(N, d)
-    xc_hi, xc_lo, we_hi, we_lo, tv = encode_operands(x, W_enc, b_dec, precision)
+    xc_hi, xc_lo, we_hi, we_lo, tv = encode_operands(x, W_enc, b_dec, precision, dp)
     wd = ops.split_operand(W_dec, BF16)[0] if precision == BF16 else W_dec
     # reference: `int(dead_mask.sum())` (topkautoencoder.py:109) -- one 8-byte device->host read, as upstream
     num_dead = int(dead_mask.sum()) if dead_mask is not None else 0
@@ -89,7 +96,11 @@ def topk_forward(x, W_enc, b_enc, W_dec, b_dec, k, *, precision, dead_mask=None,
         resid_dtype = torch.float32
     sae_out, e, sse, colsum_e = ops.topk_decode(vals, idx, wd, b_dec, x2, resid_dtype=resid_dtype, want_sse=True,
                                                 want_colsum=need_grad)
-    scal = ops.topk_loss_scalars(sse, tv, N * d)
+    numel = N * d
+    if dp is not None:
+        sse = dp.all_reduce_sum(sse)
+        numel *= dp.world_size
+    scal = ops.topk_loss_scalars(sse, tv, numel)
     st = TopKState(precision, x2, xc_hi, wd, W_enc, b_dec, k, n, scal, generic, vals, idx, e, colsum_e,
                    auxk_alpha=auxk_alpha)
 
@@ -101,6 +112,8 @@ def topk_forward(x, W_enc, b_enc, W_dec, b_dec, k, *, precision, dead_mask=None,
         a_vals, a_idx = ops.row_topk(pre, k_aux, col_mask=dead_mask)
         _, r_aux, sse_aux, _ = ops.topk_decode(a_vals, a_idx, wd, b_dec, e, resid_dtype=torch.float32,
                                                want_sse=True)
+        if dp is not None:
+            sse_aux = dp.all_reduce_sum(sse_aux)
         auxk = (scale * sse_aux[0] / scal[4].double()).float() * auxk_alpha
         st.aux = (a_vals, a_idx, r_aux, scale)
 
@@ -110,6 +123,8 @@ def topk_forward(x, W_enc, b_enc, W_dec, b_dec, k, *, precision, dead_mask=None,
         m_vals, m_idx = ops.row_topk(pre, 4 * k)
         m_out, r_m, sse_m, colsum_m = ops.topk_decode(m_vals, m_idx, wd, b_dec, x2, resid_dtype=torch.float32,
                                                       want_sse=True, want_colsum=need_grad)
+        if dp is not None:
+            sse_m = dp.all_reduce_sum(sse_m)
         mfvu = (sse_m[0] / scal[4].double()).float()
         st.multi = (m_vals, m_idx, r_m, colsum_m)
         ret_out, ret_vals, ret_idx = m_out, m_vals, m_idx

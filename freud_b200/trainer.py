@@ -1,0 +1,144 @@
+"""The SAE train step -- body of the reference loop, src/scripts/train_sae.py:421-453 -- on the CUDA kernels.
+
+`SAETrainer.step(activations)` = dead-mask, forward, loss, backward, global-norm clip, Adam/RAdam update,
+LR-scheduler step and dead-latent bookkeeping, with the same hyper-parameter schema as `train(**config)`
+(configs/train/*.json).  The TopK path drives the kernels directly (no autograd graph); the L1 path goes
+through the module's autograd.Function.  With `dp` (freud_b200.parallel.DataParallel) the step equals the
+single-GPU step on the batch concatenated over ranks.
+"""
+from __future__ import annotations
+
+import torch
+from torch.optim.lr_scheduler import CosineAnnealingLR, LambdaLR
+
+from . import ops, topk_engine
+from ._lib import BF16, FP32
+from .models.l1autoencoder import L1AutoEncoder
+from .models.topkautoencoder import TopKAutoEncoder
+from .optim import FusedAdam, FusedRAdam
+
+_TOPK_KEYS = ("encoder.weight", "encoder.bias", "W_dec", "b_dec")
+
+
+def linear_schedule_with_warmup(optimizer, num_warmup_steps, num_training_steps):
+    """Same lambda as transformers.get_linear_schedule_with_warmup (transformers/optimization.py:101-131),
+    which train_sae.py:386-390 uses; restated to avoid importing transformers on the hot path."""
+
+    def lr_lambda(current_step: int):
+        if current_step < num_warmup_steps:
+            return float(current_step) / float(max(1, num_warmup_steps))
+        return max(0.0, float(num_training_steps - current_step) / float(max(1, num_training_steps - num_warmup_steps)))
+
+    return LambdaLR(optimizer, lr_lambda)
+
+
+def build_optimizer(model, optimizer: str, lr: float, weight_decay: float, clip_thresh):
+    if optimizer == "radam":
+        return FusedRAdam(model.parameters(), eps=1e-5, lr=lr, weight_decay=weight_decay, max_grad_norm=clip_thresh)
+    if optimizer == "adam":
+        return FusedAdam(model.parameters(), lr=lr, max_grad_norm=clip_thresh)
+    raise ValueError(f"Invalid optimizer: {optimizer}, must be 'radam' or 'adam'")
+
+
+def build_scheduler(opt, scheduler: str, scheduler_params: dict, steps: int):
+    if scheduler == "cosine":
+        return CosineAnnealingLR(opt, T_max=steps, eta_min=0)
+    if scheduler == "linear":
+        return linear_schedule_with_warmup(opt, scheduler_params["num_warmup_steps"], steps)
+    raise ValueError(f"Invalid scheduler: {scheduler}, must be 'cosine' or 'linear'")
+
+
+class SAETrainer:
+    def __init__(self, model, *, lr, steps, clip_thresh=1.0, weight_decay=0.0, optimizer="adam", scheduler="linear",
+                 scheduler_params=None, dead_feature_threshold=None, precision="bf16", dp=None):
+        if not next(model.parameters()).is_cuda:
+            raise RuntimeError("SAETrainer needs the model on a CUDA device (no CPU fallback)")
+        self.model = model
+        self.is_topk = isinstance(model, TopKAutoEncoder)
+        self.precision = {"bf16": BF16, "fp32": FP32}[precision]
+        model.precision = precision
+        self.clip_thresh = clip_thresh
+        self.optimizer = build_optimizer(model, optimizer, lr, weight_decay, clip_thresh)
+        self.scheduler = build_scheduler(self.optimizer, scheduler, scheduler_params or {}, steps)
+        self.dp = dp
+        self.step_count = 0
+        self.tokens_seen = 0
+        self.dead_feature_threshold = dead_feature_threshold
+        dev = next(model.parameters()).device
+        if self.is_topk:
+            # train_sae.py:412-415 (recreated as zeros on resume, as upstream)
+            self.num_frames_since_fired = torch.zeros(model.n_dict_components, device=dev, dtype=torch.long)
+            self.params = {"encoder.weight": model.encoder.weight, "encoder.bias": model.encoder.bias,
+                           "W_dec": model.W_dec, "b_dec": model.b_dec}
+            for p in self.params.values():
+                p.grad = torch.zeros_like(p)
+        self.last_state = None
+
+    # ------------------------------------------------------------------------------------------ TopK
+    def _topk_step(self, x):
+        m = self.model
+        cfg = m.cfg
+        B, T, _ = x.shape
+        n_tokens = B * T * (self.dp.world_size if self.dp else 1)
+        dead_mask = None
+        thr = self.dead_feature_threshold
+        # a latent can only be dead once more than `thr` frames have been seen in total; before that the mask
+        # is provably empty and the reference's per-step `dead_mask.sum()` read-back is skipped
+        if thr is not None and self.tokens_seen > thr:
+            dead_mask = self.num_frames_since_fired > thr
+        res, st = topk_engine.topk_forward(x, m.encoder.weight.data, m.encoder.bias.data, m.W_dec.data,
+                                           m.b_dec.data, cfg.k, precision=self.precision, dead_mask=dead_mask,
+                                           auxk_alpha=float(cfg.auxk_alpha), multi_topk=bool(cfg.multi_topk),
+                                           need_grad=True, dp=self.dp)
+        # loss = fvu + auxk_loss + multi_topk_fvu / 8   (train_sae.py:441)
+        grads = {k: p.grad for k, p in self.params.items()}
+        topk_engine.topk_backward(st, 1.0, 1.0, 1.0 / 8.0, out=grads)
+        glist = [self.params[k].grad for k in _TOPK_KEYS]
+        if self.dp is not None:
+            self.dp.all_reduce_grads(glist)
+        tl = ops.make_tensor_list([self.params[k].data for k in _TOPK_KEYS], glist)
+        sumsq = ops.grad_sumsq(tl, x.device)
+        self.optimizer.step(grad_sumsq=sumsq)  # clip_grad_norm_ + optimizer.step (train_sae.py:449-450), fused
+        self.scheduler.step()
+        # did_fire / num_frames_since_fired (train_sae.py:442-446), from the CSC index of the returned encoding
+        offsets = st.offsets
+        if offsets is None:
+            offsets, _ = ops.csc_build(res.top_idx, m.n_dict_components)
+        if self.dp is None:
+            ops.dead_latent_update(offsets, self.num_frames_since_fired, n_tokens)
+        else:
+            counts = (offsets[1:] - offsets[:-1]).contiguous()
+            self.dp.all_reduce_sum(counts)
+            f = self.num_frames_since_fired
+            f.add_(n_tokens)
+            f.masked_fill_(counts > 0, 0)
+        self.tokens_seen += n_tokens
+        self.last_state = st
+        if st.generic:
+            loss = res.fvu + res.auxk_loss + res.multi_topk_fvu / 8
+        else:
+            loss = res.fvu
+        return {"loss": loss, "fvu": res.fvu, "auxk_loss": res.auxk_loss, "multi_topk_fvu": res.multi_topk_fvu,
+                "grad_sumsq": sumsq, "top_idx": res.top_idx, "top_acts": res.top_acts, "sae_out": res.sae_out}
+
+    # ------------------------------------------------------------------------------------------ L1
+    def _l1_step(self, x):
+        if self.dp is not None:
+            raise NotImplementedError("data-parallel L1 training is not implemented in this round")
+        self.optimizer.zero_grad(set_to_none=True)
+        out = self.model(x)
+        loss = out.reconstruction_loss + out.l1_loss  # train_sae.py:433-434
+        loss.backward()
+        self.optimizer.step()
+        self.scheduler.step()
+        return {"loss": loss.detach(), "loss_recon": out.reconstruction_loss.detach(), "loss_l1": out.l1_loss.detach(),
+                "sae_out": out.sae_out, "latent": out.encoded.latent}
+
+    def step(self, activations: torch.Tensor):
+        """One optimisation step on a [B, T, d] fp32 CUDA batch.  Returns device tensors (no host sync)."""
+        if not activations.is_cuda:
+            raise RuntimeError("activations must already be on the CUDA device")
+        x = activations.float().contiguous()
+        out = self._topk_step(x) if self.is_topk else self._l1_step(x)
+        self.step_count += 1
+        return out

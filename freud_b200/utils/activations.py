@@ -1,0 +1,68 @@
+"""Mirror of the search entry point of src/utils/activations.py:61-132 on the CUDA search kernels.
+
+`top_activations(dataloader, feature_idx, n_files, max_val, min_val, absolute_magnitude, return_max_per_file)`
+keeps the reference's seven positional arguments (it is the `top_fn` lambda of gui_server.py:91-99) and its return
+value `(pq, max_per_file)` with pq[i] = (filename, trimmed_activation, value, time).  Instead of re-reading every
+file through the DataLoader (and re-decoding its audio) on every query, the first call uploads the whole store to
+HBM once (DeviceActivationStore) and each query is one streaming kernel + one ranking kernel.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from .. import ops
+from ..dataset.activations import DeviceActivationStore
+from .constants import TIMESTEP_S
+
+_STORE_ATTR = "_freud_b200_store"
+
+
+def attach_store(dataloader, store: DeviceActivationStore):
+    setattr(dataloader, _STORE_ATTR, store)
+    return store
+
+
+def get_store(dataloader, **store_kwargs) -> DeviceActivationStore:
+    store = getattr(dataloader, _STORE_ATTR, None)
+    if store is None:
+        if not hasattr(dataloader, "dataset") or not hasattr(dataloader.dataset, "metadata"):
+            raise RuntimeError("freud_b200.top_activations needs a MemoryMappedActivationDataLoader (--from_disk)")
+        store = attach_store(dataloader, DeviceActivationStore(dataloader.dataset, **store_kwargs))
+    return store
+
+
+@torch.no_grad()
+def top_activations(dataloader, feature_idx: int, n_files: int, max_val: Optional[float], min_val: Optional[float],
+                    absolute_magnitude: bool, return_max_per_file: bool):
+    store = get_store(dataloader)
+    if store.activation_type == "tensor":
+        vmax, amax, vabs, _ = ops.search_dense(store.acts, store.n_frames, int(feature_idx), False)
+    else:
+        vmax, amax, vabs, _ = ops.search_indexed(store.vals, store.idx, store.n_frames, int(feature_idx), False)
+    files, count = ops.search_topn(vmax, vabs, bool(absolute_magnitude), min_val, max_val, int(n_files))
+    stat = vabs if absolute_magnitude else vmax
+    n_found = int(count.item())
+    files_h = files[:n_found].tolist()
+    pq = []
+    if n_found:
+        sel = files[:n_found].long()
+        stat_h = stat[sel].tolist()
+        amax_h = amax[sel].tolist()
+        if store.activation_type == "tensor":
+            traces = store.acts[sel, :, int(feature_idx)].float().cpu()
+        else:
+            _, _, _, tr = ops.search_indexed(store.vals[sel].contiguous(), store.idx[sel].contiguous(),
+                                             store.n_frames[sel].contiguous(), int(feature_idx), True)
+            traces = tr.cpu()
+        for r, fi in enumerate(files_h):
+            nf = store.n_frames_host[fi]
+            signed = stat_h[r]
+            value = abs(signed) if absolute_magnitude else signed
+            pq.append((store.filenames[fi], traces[r, :nf].clone(), value, amax_h[r] * TIMESTEP_S))
+    max_per_file = None
+    if return_max_per_file:
+        # the reference appends one entry per file (utils/activations.py:110-117)
+        max_per_file = stat.tolist()
+    return pq, max_per_file

@@ -34,8 +34,10 @@ int freud_version(void);
 /* x - b_dec (topkautoencoder.py:74) written as the encoder GEMM's A operand, fused with the batch-axis
  * total variance sum((x - x.mean(0))^2) of topkautoencoder.py:104 (accumulated into *tv, which the call
  * zeroes first).  x is [B,T,d] fp32.  FREUD_BF16: xc_hi = bf16 [N,d], xc_lo unused.
- * FREUD_FP32: xc_hi / xc_lo = fp32 [N,d] holding the tf32 high / low parts. */
-int freud_topk_prep_x(const float* x, const float* b_dec, void* xc_hi, void* xc_lo, double* tv,
+ * FREUD_FP32: xc_hi / xc_lo = fp32 [N,d] holding the tf32 high / low parts.
+ * colmean (optional, [T,d] fp32) receives x.mean(0); data-parallel ranks exchange it to form the variance of
+ * the concatenated batch. */
+int freud_topk_prep_x(const float* x, const float* b_dec, void* xc_hi, void* xc_lo, double* tv, float* colmean,
                       int64_t B, int64_t T, int64_t d, int precision, void* stream);
 
 /* Weight operand preparation (the implicit autocast cast of nn.Linear / matmul operands):

@@ -1,0 +1,84 @@
+"""GPU parity of the feature search against the reference's top_activations goldens (exact rankings)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.util import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _write_sets(tmp, z, filenames):
+    dense, idx, vals = z["dense"], z["idx"], z["vals"]
+    n_files, T, F = dense.shape
+    k = idx.shape[-1]
+    os.makedirs(f"{tmp}/dense")
+    np.save(f"{tmp}/dense/layer_tensors.npy", dense.reshape(n_files, -1))
+    json.dump({"tensor_shape": [T, F], "activation_shape": [T, F], "filenames": filenames},
+              open(f"{tmp}/dense/layer_metadata.json", "w"))
+    os.makedirs(f"{tmp}/indexed")
+    np.save(f"{tmp}/indexed/layer_activation_values.npy", vals.reshape(n_files, -1))
+    np.save(f"{tmp}/indexed/layer_feature_indices.npy", idx.reshape(n_files, -1))
+    json.dump({"tensor_shape": [T, k], "activation_shape": [T, 64], "filenames": filenames},
+              open(f"{tmp}/indexed/layer_metadata.json", "w"))
+
+
+def test_top_activations_matches_reference(tmp_path):
+    from freud_b200.dataset.activations import DeviceActivationStore, MemoryMappedActivationDataLoader
+    from freud_b200.utils.activations import attach_store, top_activations
+
+    z, meta = load_golden("search")
+    filenames = meta["filenames"]
+    num_samples = {f: int(s) for f, s in zip(filenames, z["num_samples"])}
+    _write_sets(str(tmp_path), z, filenames)
+    loaders = {}
+    for kind in ("dense", "indexed"):
+        dl = MemoryMappedActivationDataLoader(f"{tmp_path}/{kind}", "layer", batch_size=8, dl_max_workers=0)
+        attach_store(dl, DeviceActivationStore(dl.dataset, num_samples=num_samples))
+        loaders[kind] = dl
+    for q, query in enumerate(meta["queries"]):
+        pq, mpf = top_activations(loaders[query["kind"]], query["feature"], query["n_files"], query["max_val"],
+                                  query["min_val"], query["abs"], True)
+        assert [filenames.index(p[0]) for p in pq] == z[f"q{q}.files"].tolist(), query
+        assert np.array_equal(np.array([p[2] for p in pq], dtype=np.float64), z[f"q{q}.values"]), query
+        assert np.array_equal(np.array([p[3] for p in pq], dtype=np.float64), z[f"q{q}.times"]), query
+        assert [len(p[1]) for p in pq] == z[f"q{q}.lens"].tolist()
+        assert np.array_equal(np.array(mpf, dtype=np.float64), z[f"q{q}.max_per_file"]), query
+        if pq:
+            assert np.array_equal(pq[0][1].numpy(), z[f"q{q}.trace0"])
+
+
+def test_search_large_against_oracle():
+    """2000 files x 1500 frames, dense and indexed, 8 seeded queries x {plain, abs, filtered}: exact rankings."""
+    from freud_b200 import ops
+    from oracle import search as osearch
+
+    rng = np.random.default_rng(1)
+    n_files, T, F, k, n = 2000, 1500, 48, 32, 6144
+    dense = rng.standard_normal((n_files, T, F)).astype(np.float32)
+    n_frames = np.array([osearch.n_frames_from_samples(int(s)) for s in rng.integers(16000, 480001, n_files)])
+    idx = rng.integers(0, n, (n_files, T, k)).astype(np.int64)
+    vals = np.abs(rng.standard_normal((n_files, T, k))).astype(np.float32)
+    names = [str(i) for i in range(n_files)]
+    nf_dev = torch.tensor(n_frames, dtype=torch.int32, device="cuda")
+    d_dev, v_dev, i_dev = torch.from_numpy(dense).cuda(), torch.from_numpy(vals).cuda(), torch.from_numpy(idx).cuda()
+    for feature in rng.integers(0, F, 4):
+        for kind in ("dense", "indexed"):
+            if kind == "dense":
+                acts = dense[:, :, feature]
+                vmax, amax, vabs, _ = ops.search_dense(d_dev, nf_dev, int(feature), False)
+            else:
+                f2 = int(idx[0, 0, feature % k])
+                acts = osearch.dense_from_indexed(vals, idx, f2)
+                vmax, amax, vabs, _ = ops.search_indexed(v_dev, i_dev, nf_dev, f2, False)
+            for (mx, mn, ab) in ((None, None, False), (None, None, True), (3.2, 0.5, False)):
+                pq, mpf = osearch.top_activations(acts, names, n_frames, 20, mx, mn, ab, True)
+                files, cnt = ops.search_topn(vmax, vabs, ab, mn, mx, 20)
+                assert files[: int(cnt)].tolist() == [int(p[0]) for p in pq]
+                stat = (vabs if ab else vmax).cpu().numpy().astype(np.float64)
+                assert np.array_equal(stat, np.array(mpf))
+                sel = files[: int(cnt)].long()
+                assert np.array_equal(amax[sel].cpu().numpy() * osearch.TIMESTEP_S, np.array([p[3] for p in pq]))

@@ -1,0 +1,191 @@
+"""GPU parity of the TopK SAE path: CUDA kernels (through the C ABI) vs the reference goldens and the oracle."""
+import pytest
+import torch
+
+from oracle import sae as osae
+from tests.util import load_golden, rel_err, sets_equal_rows, t
+
+pytestmark = pytest.mark.gpu
+
+TOPK_KEYS = ["encoder.weight", "encoder.bias", "W_dec", "b_dec"]
+
+
+def _model_from_golden(z, meta, prefix="init"):
+    from freud_b200.models.config import TopKAutoEncoderConfig
+    from freud_b200.models.topkautoencoder import TopKAutoEncoder
+
+    cfg = TopKAutoEncoderConfig.from_dict({"n_dict_components": meta["n"], "k": meta["k"],
+                                           "multi_topk": meta["multi_topk"], "auxk_alpha": meta["auxk_alpha"]})
+    model = TopKAutoEncoder(meta["d"], cfg)
+    model.load_state_dict({k: t(z[f"{prefix}.{k}"]) for k in TOPK_KEYS})
+    return model.cuda()
+
+
+@pytest.mark.parametrize("name", ["topk_fp32", "topk_fp32_auxk", "topk_fp32_auxk_few", "topk_fp32_multi",
+                                  "topk_fp32_b1"])
+def test_trainer_follows_reference_trajectory_fp32(name):
+    """SAETrainer.step == body of train_sae.py:421-453 run by the reference (fp32, 1e-5 relative)."""
+    from freud_b200.trainer import SAETrainer
+
+    z, meta = load_golden(name)
+    model = _model_from_golden(z, meta)
+    tr = SAETrainer(model, lr=meta["lr"], steps=meta["total_steps"], clip_thresh=meta["clip"], optimizer="adam",
+                    scheduler="linear", scheduler_params={"num_warmup_steps": meta["warmup"]},
+                    dead_feature_threshold=meta["dead_thresh"], precision="fp32")
+    tr.tokens_seen = 10 ** 12  # the goldens start with pre-aged counters
+    for s in range(meta["steps"]):
+        x = t(z[f"s{s}.x"]).cuda()
+        tr.num_frames_since_fired.copy_(t(z[f"s{s}.frames_in"]))
+        assert abs(tr.optimizer.param_groups[0]["lr"] - float(z[f"s{s}.lr"])) < 1e-12
+        out = tr.step(x)
+        torch.cuda.synchronize()
+        for key in ("fvu", "auxk_loss", "multi_topk_fvu"):
+            assert rel_err(out[key].cpu(), z[f"s{s}.{key}"]) < 1e-5 or abs(float(out[key]) - float(z[f"s{s}.{key}"])) < 1e-9, key
+        assert rel_err(out["sae_out"].cpu().view(z[f"s{s}.sae_out"].shape), z[f"s{s}.sae_out"]) < 1e-5
+        for k in TOPK_KEYS:
+            assert rel_err(tr.params[k].grad.cpu(), z[f"s{s}.grad.{k}"]) < 1e-5, f"grad {k} step {s}"
+        assert rel_err(out["grad_sumsq"].sqrt().cpu(), z[f"s{s}.grad_norm"]) < 1e-5
+        for k in TOPK_KEYS:
+            assert rel_err(tr.params[k].data.cpu(), z[f"s{s}.param.{k}"]) < 1e-5, f"param {k} step {s}"
+        assert torch.equal(tr.num_frames_since_fired.cpu(), t(z[f"s{s}.frames_out"])), "dead-latent counters"
+
+
+def test_module_autograd_dropin_fp32():
+    """model(x, dead_mask) -> loss.backward() -> clip_grad_norm_ -> FusedAdam.step, as train_sae.py calls them."""
+    from freud_b200.optim import FusedAdam, clip_grad_norm_
+
+    z, meta = load_golden("topk_fp32_auxk")
+    model = _model_from_golden(z, meta)
+    opt = FusedAdam(model.parameters(), lr=float(z["s0.lr"]))
+    x = t(z["s0.x"]).cuda()
+    dead = (t(z["s0.frames_in"]) > meta["dead_thresh"]).cuda()
+    out, mse = model(x, dead_mask=dead, return_mse=True)
+    loss = out.fvu + out.auxk_loss + out.multi_topk_fvu / 8
+    loss.backward()
+    assert out.encoded.top_indices.dtype == torch.int64
+    assert rel_err(loss.detach().cpu(), z["s0.loss"]) < 1e-5
+    assert rel_err(mse.cpu(), z["s0.mse"]) < 1e-5
+    free = osae.tie_free_rows(t(z["s0.pre_acts"]), meta["k"]).reshape(-1)
+    same = sets_equal_rows(out.encoded.top_indices.cpu(), z["s0.top_indices"])
+    assert bool(same[free].all())
+    named = dict(model.named_parameters())
+    for k in TOPK_KEYS:
+        assert rel_err(named[k].grad.cpu(), z[f"s0.grad.{k}"]) < 1e-5, k
+    total = clip_grad_norm_(model.parameters(), meta["clip"])
+    assert rel_err(total.cpu(), z["s0.grad_norm"]) < 1e-5
+    opt.step()
+    for k in TOPK_KEYS:
+        assert rel_err(named[k].data.cpu(), z[f"s0.param.{k}"]) < 1e-5, k
+
+
+def test_bf16_mode_vs_reference_autocast():
+    """bf16 tensor-core mode vs the reference under autocast('cpu'): 2e-2 (north_star), same selected sets."""
+    z, meta = load_golden("topk_bf16")
+    model = _model_from_golden(z, meta)
+    model.precision = "bf16"
+    x = t(z["s0.x"]).cuda()
+    out = model(x)
+    loss = out.fvu + out.auxk_loss + out.multi_topk_fvu / 8
+    loss.backward()
+    assert bool(sets_equal_rows(out.encoded.top_indices.cpu(), z["s0.top_indices"]).all())
+    assert rel_err(out.fvu.detach().cpu(), z["s0.fvu"]) < 2e-2
+    assert rel_err(out.sae_out.cpu(), z["s0.sae_out"]) < 2e-2
+    named = dict(model.named_parameters())
+    for k in TOPK_KEYS:
+        assert rel_err(named[k].grad.cpu(), z[f"s0.grad.{k}"]) < 2e-2, k
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 4e-3)])
+@pytest.mark.parametrize("shape", [(3, 200, 64, 512), (2, 129, 384, 6144)])
+def test_fused_fast_path_vs_oracle(precision, tol, shape):
+    """k == 32 fused tcgen05 GEMM + top-k epilogue, sparse decode and CSC backward vs the oracle in the same
+    precision mode; index sets exact on rows whose k-th gap exceeds the GEMM rounding."""
+    from freud_b200 import topk_engine
+    from freud_b200._lib import BF16, FP32
+
+    B, T, d, n = shape
+    k = 32
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, T, d, generator=g) * (0.5 + torch.rand(T, 1, generator=g)) + torch.randn(d, generator=g)
+    W_enc = torch.randn(n, d, generator=g) / d ** 0.5
+    W_dec = osae.set_decoder_norm_to_unit_norm(W_enc.clone() + 0.1 * torch.randn(n, d, generator=g))
+    b_enc = 0.05 * torch.randn(n, generator=g)
+    b_dec = 0.1 * torch.randn(d, generator=g)
+    ref = osae.topk_forward(x, W_enc, b_enc, W_dec, b_dec, k, mode=precision)
+    rg = osae.topk_backward(x, W_enc, b_enc, W_dec, b_dec, ref, k, mode=precision)
+    prec = BF16 if precision == "bf16" else FP32
+    cu = [v.cuda() for v in (x, W_enc, b_enc, W_dec, b_dec)]
+    res, st = topk_engine.topk_forward(*cu, k, precision=prec)
+    assert not st.generic
+    grads = topk_engine.topk_backward(st, 1.0)
+    torch.cuda.synchronize()
+    pre = ref.pre_acts.reshape(-1, n)
+    srt = torch.sort(pre, -1, descending=True).values
+    clear = (srt[:, k - 1] - srt[:, k]) > 1e-4 * srt[:, k - 1].abs().clamp_min(1e-3)
+    same = sets_equal_rows(res.top_idx.cpu(), ref.top_indices.reshape(-1, k))
+    assert bool(same[clear].all()) and clear.float().mean() > 0.9
+    assert rel_err(res.fvu.cpu(), ref.fvu) < max(tol, 1e-5)
+    if bool(same.all()):
+        assert rel_err(res.sae_out.cpu(), ref.sae_out.reshape(-1, d)) < tol
+        for key in TOPK_KEYS:
+            assert rel_err(grads[key].cpu(), rg[key]) < tol, key
+
+
+def test_short_rows_and_ragged_sizes():
+    """Rows with fewer than 32 positive pre-activations are completed with zeros at the lowest free indices
+    (oracle order); N not a multiple of 128 and n not a multiple of 256 exercise the TMA out-of-bounds fill."""
+    from freud_b200 import ops
+    from freud_b200._lib import FP32
+
+    g = torch.Generator().manual_seed(11)
+    N, d, n = 77, 40, 600
+    x = torch.randn(1, N, d, generator=g)
+    W = torch.randn(n, d, generator=g) / d ** 0.5
+    b_enc = torch.full((n,), -2.5)  # strongly negative bias -> only a handful of positives per row
+    b_dec = torch.zeros(d)
+    ref = osae.topk_pre_acts(x, W, b_enc, b_dec)[0]
+    rv, ri = osae.select_topk(ref, 32)
+    assert int((rv > 0).sum(-1).min()) < 32
+    xc_hi, xc_lo, tv = ops.topk_prep_x(x.cuda(), b_dec.cuda(), FP32)
+    w_hi, w_lo = ops.split_operand(W.cuda(), FP32)
+    vals, idx = ops.topk_encode(xc_hi, xc_lo, w_hi, w_lo, b_enc.cuda(), FP32)
+    assert torch.equal(torch.sort(idx.cpu().long(), -1).values, torch.sort(ri, -1).values)
+    assert rel_err(torch.sort(vals.cpu(), -1, descending=True).values, rv) < 1e-5
+
+
+def test_row_topk_masked_exact():
+    from freud_b200 import ops
+
+    g = torch.Generator().manual_seed(3)
+    lat = torch.relu(torch.randn(50, 1000, generator=g))
+    mask = torch.rand(1000, generator=g) < 0.3
+    for k, m in ((8, None), (128, None), (192, mask)):
+        src = lat if m is None else torch.where(m[None], lat, torch.full_like(lat, -torch.inf))
+        rv, ri = osae.select_topk(src, k)
+        vals, idx = ops.row_topk(lat.cuda(), k, None if m is None else m.cuda())
+        assert torch.equal(idx.cpu().long(), ri), (k, m is not None)  # identical order: value desc, index asc
+        assert torch.equal(vals.cpu(), rv)
+
+
+def test_decoder_norm_helpers():
+    from freud_b200.models.config import TopKAutoEncoderConfig
+    from freud_b200.models.topkautoencoder import TopKAutoEncoder
+
+    z, _ = load_golden("topk_decoder_norm")
+    cfg = TopKAutoEncoderConfig.from_dict({"n_dict_components": 96, "k": 4, "normalize_decoder": False})
+    model = TopKAutoEncoder(24, cfg).cuda()
+    model.W_dec.data.copy_(t(z["W_dec_in"]))
+    model.set_decoder_norm_to_unit_norm()
+    assert rel_err(model.W_dec.data.cpu(), z["W_dec_unit"]) < 1e-6
+    model.W_dec.grad = t(z["grad_in"]).cuda()
+    model.remove_gradient_parallel_to_decoder_directions()
+    assert rel_err(model.W_dec.grad.cpu(), z["grad_out"]) < 1e-5
+
+
+def test_cpu_input_fails_loudly():
+    from freud_b200.models.config import TopKAutoEncoderConfig
+    from freud_b200.models.topkautoencoder import TopKAutoEncoder
+
+    model = TopKAutoEncoder(32, TopKAutoEncoderConfig.from_dict({"n_dict_components": 256}))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model(torch.randn(2, 3, 32))
