@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path BASELINE.json names: SAE train activation-tokens/s.
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--workload c3|c2] [--precision bf16|fp32]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the train-step body (src/scripts/train_sae.py:421-453: dead mask, TopK SAE forward, loss,
+backward, global-norm clip, Adam, LR schedule, dead-latent bookkeeping) over one synthetic batch.
+
+Workload (config.workload):
+  c3 (default): Whisper-small residual, d=768, n=24576 (32x), k=32, B=32 files x 1500 frames per GPU, data parallel
+                (weak scaling; the configuration BASELINE.json quotes "at 1/2/4/8 B200")
+  c2          : Whisper-tiny block 2, d=384, n=6144 (16x), k=32, B=50 (configs/train/tiny_topk.json)
+Prints ONE JSON line (rank 0).  `value` = device-timed throughput with inputs resident in HBM; `e2e` = the same
+metric through the public API with host (pinned) inputs copied in and the loss read back every step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "c3": dict(d=768, n=24576, k=32, B=32, T=1500, lr=1e-4, warmup_steps=1000, auxk_alpha=1 / 32,
+               dead_feature_threshold=1e6, desc="TopK SAE d=768 n=24576 (32x) k=32, B=32x1500 tokens per GPU"),
+    "c2": dict(d=384, n=6144, k=32, B=50, T=1500, lr=1e-4, warmup_steps=1000, auxk_alpha=1 / 32,
+               dead_feature_threshold=1e6, desc="TopK SAE d=384 n=6144 (16x) k=32, B=50x1500 tokens"),
+}
+METRIC = "sae_train_activation_tokens_per_sec"
+
+
+def synth_batch(B, T, d, seed, device="cpu", pin=False):
+    """x = randn * sigma_t + mu_d so the b_dec / total_variance paths are non-trivial."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, T, d, generator=g) * (0.5 + torch.rand(T, 1, generator=g)) + torch.randn(d, generator=g)
+    if pin:
+        x = x.pin_memory()
+    return x.to(device) if device != "cpu" else x
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [c.strip() for c in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- reference arm / CPU
+def oracle_cpu_step_factory(w, B):
+    """One train step of the oracle port (oracle/sae.py + oracle/optim.py) on the host cores -- the CPU restatement
+    of the reference's own step, same workload shape with a bounded batch."""
+    from oracle import optim as ooptim
+    from oracle import sae as osae
+
+    osae.FAST_TOPK = True  # time torch.topk, as the reference does
+    torch.manual_seed(0)
+    d, n, k = w["d"], w["n"], w["k"]
+    enc = torch.nn.Linear(d, n)
+    W_enc = enc.weight.data.clone()
+    b_enc = torch.zeros(n)
+    W_dec = osae.set_decoder_norm_to_unit_norm(W_enc.clone())
+    b_dec = torch.zeros(d)
+    state = dict(p=[W_enc, b_enc, W_dec, b_dec], m=[torch.zeros_like(t) for t in (W_enc, b_enc, W_dec, b_dec)],
+                 v=[torch.zeros_like(t) for t in (W_enc, b_enc, W_dec, b_dec)], step=0)
+    keys = ["encoder.weight", "encoder.bias", "W_dec", "b_dec"]
+    x = synth_batch(B, w["T"], d, 100)
+
+    def step():
+        W_enc, b_enc, W_dec, b_dec = state["p"]
+        out = osae.topk_forward(x, W_enc, b_enc, W_dec, b_dec, k, auxk_alpha=w["auxk_alpha"], mode="bf16")
+        grads = osae.topk_backward(x, W_enc, b_enc, W_dec, b_dec, out, k, auxk_alpha=w["auxk_alpha"], mode="bf16")
+        clipped, _ = ooptim.clip_grad_norm([grads[k_] for k_ in keys], 1.0)
+        state["step"] += 1
+        lr = ooptim.linear_warmup_lr(w["lr"], state["step"] - 1, w["warmup_steps"], 100000)
+        for i, g in enumerate(clipped):
+            state["p"][i], state["m"][i], state["v"][i] = ooptim.adam_step(state["p"][i], g, state["m"][i],
+                                                                           state["v"][i], state["step"], lr)
+        return float(out.fvu)
+
+    return step, B * w["T"]
+
+
+def run_cpu_port(w, steps, warmup, B):
+    torch.set_num_threads(os.cpu_count() or 1)
+    step, tokens = oracle_cpu_step_factory(w, B)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return tokens * steps / dt, dt / steps * 1e3, torch.get_num_threads()
+
+
+def reference_arm(args, w, rank, world):
+    if rank != 0:
+        return
+    B = 1 if args.workload == "c3" else 2
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
+    val, ms, cores = run_cpu_port(w, steps, warmup, B)
+    sample = f"{B}x{w['T']} tokens per step of the same shape (d={w['d']}, n={w['n']}, k={w['k']}), {steps} steps"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "tokens/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {w['desc']}", "note": "CPU port of the reference step (oracle/), "
+                       "bf16-operand mode as under the reference's autocast('cpu')"},
+            "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------- our arm
+def build_trainer(w, precision, dp, device):
+    from freud_b200.models.config import TopKAutoEncoderConfig
+    from freud_b200.models.topkautoencoder import TopKAutoEncoder
+    from freud_b200.trainer import SAETrainer
+
+    torch.manual_seed(0)
+    cfg = TopKAutoEncoderConfig.from_dict({"n_dict_components": w["n"], "k": w["k"], "auxk_alpha": w["auxk_alpha"],
+                                           "multi_topk": False, "normalize_decoder": True})
+    model = TopKAutoEncoder(w["d"], cfg).to(device)
+    return SAETrainer(model, lr=w["lr"], steps=100000, clip_thresh=1.0, optimizer="adam", scheduler="linear",
+                      scheduler_params={"num_warmup_steps": w["warmup_steps"]},
+                      dead_feature_threshold=w["dead_feature_threshold"], precision=precision, dp=dp)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-out", default=None, help="write the per-kernel share table (json) here")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        reference_arm(args, w, rank, world)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    import torch.distributed as dist
+
+    from freud_b200 import _lib
+
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dp = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+        from freud_b200.parallel import DataParallel
+
+        dp = DataParallel()
+    tr = build_trainer(w, args.precision, dp, device)
+    B, T, d = w["B"], w["T"], w["d"]
+    tokens_per_step = B * T * world
+    n_bufs = 3  # 3 x 147 MB (c3) of distinct inputs, each larger than the 126 MB L2
+    host = [synth_batch(B, T, d, 1000 + 17 * rank + i, pin=True) for i in range(n_bufs)]
+    dev_x = [h.to(device) for h in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- device-resident throughput (`value`) + live per-kernel timing
+    for i in range(args.warmup):
+        tr.step(dev_x[i % n_bufs])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    _lib.profile = {}
+    k0 = _lib.kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        out = tr.step(dev_x[i % n_bufs])
+    ev1.record()
+    barrier()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    gpu_launches = _lib.kernel_launches - k0
+    prof = _lib.profile_summary()
+    _lib.profile = None
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms_total / args.steps
+    value = tokens_per_step * args.steps / (ms_total / 1e3)
+    last_loss = float(out["loss"].item())
+
+    # ---------------- end to end: pinned host batch -> H2D -> step -> loss read back, every step
+    copy_stream = torch.cuda.Stream(device)
+    stage = [torch.empty_like(dev_x[0]) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(i):
+        s = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[s])
+            stage[s].copy_(host[i % n_bufs], non_blocking=True)
+            ready[s].record(copy_stream)
+
+    def e2e_loop(n):
+        for s in range(2):
+            freed[s].record()
+        prefetch(0)
+        loss_sum = 0.0
+        for i in range(n):
+            if i + 1 < n:
+                prefetch(i + 1)  # overlaps the next batch's H2D with this step's compute
+            torch.cuda.current_stream().wait_event(ready[i % 2])
+            o = tr.step(stage[i % 2])
+            freed[i % 2].record()
+            loss_sum += float(o["loss"].item())  # 4-byte D2H read of the step's loss (blocks, as train_sae.py:455)
+        return loss_sum
+
+    e2e_loop(2)
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record()
+    e2e_loop(args.steps)
+    ev1.record()
+    barrier()
+    e2e_ms = max_over_ranks(max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3))
+    e2e_value = tokens_per_step * args.steps / (e2e_ms / 1e3)
+
+    # ---------------- roofline of the dominant kernel (fused encoder GEMM + top-k), from the live events
+    peaks = measured_peaks()
+    enc_calls, enc_ms = prof.get("freud_topk_encode", (0, 0.0))
+    step_kernel_ms = sum(v[1] for v in prof.values())
+    roofline = None
+    if enc_calls:
+        flops = 2.0 * B * T * d * w["n"]  # 2*d*n per token (algorithmic, one bf16 pass)
+        achieved = flops / (enc_ms / enc_calls * 1e-3) / 1e12
+        roofline = {"kernel": "sm100_gemm_kernel<EPI_TOPK> (freud_topk_encode)", "bound": "tensor",
+                    "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                    "frac": achieved / peaks["tf_sustained"], "traffic": None, "peak_source": peaks["src"] +
+                    " bf16 sustained (kernel timed inside a long step)",
+                    "share_of_step": enc_ms / step_kernel_ms if step_kernel_ms else None}
+    shares = {k_: {"calls": c, "ms_per_step": ms / args.steps, "share": ms / step_kernel_ms}
+              for k_, (c, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+    if args.profile_out and rank == 0:
+        with open(args.profile_out, "w") as f:
+            json.dump({"workload": args.workload, "precision": args.precision, "n_gpus": world,
+                       "ms_per_step": ms_per_step, "kernels": shares}, f, indent=1)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        Bc = 1 if args.workload == "c3" else 2
+        v, ms, cores = run_cpu_port(w, 3, 1, Bc)
+        cpu_baseline = {"value": v, "unit": "tokens/s", "cores": cores, "kind": "port",
+                        "sample": f"{Bc}x{T} tokens/step of the same shape, 3 timed steps after 1 warm-up, "
+                                  f"{ms:.0f} ms/step (oracle/ CPU port of the reference step)"}
+    line = {
+        "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {w['desc']}", "global_batch_tokens": tokens_per_step,
+                   "parallelism": f"dp{world}", "optimizer": "adam+clip(1.0)+linear-warmup",
+                   "l2": f"{n_bufs} rotating input batches of {B * T * d * 4 / 1e6:.0f} MB (> 126 MB L2)"
+                   if B * T * d * 4 > 126e6 else f"{n_bufs} rotating input batches ({B * T * d * 4 / 1e6:.0f} MB each, "
+                   f"{n_bufs * B * T * d * 4 / 1e6:.0f} MB total > 126 MB L2)"},
+        "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": B * T * d * 4 * world,
+                "d2h_bytes_per_step": 4 * world, "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "loss": last_loss, "kernel_shares": {k_: round(v["share"], 4) for k_, v in shares.items()},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

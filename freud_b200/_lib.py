@@ -57,8 +57,22 @@ SIGNATURES = {
     "freud_search_topn": [_p, _p, _i64, _i, _i, _d, _i, _d, _i64, _p, _p, _p],
 }
 
+# CUDA kernels each entry point enqueues (memsets not counted); bench.py sums these into `gpu_launches`
+KERNELS_PER_CALL = {
+    "freud_topk_prep_x": 1, "freud_split_operand": 1, "freud_topk_encode": 1, "freud_gemm_nt": 1,
+    "freud_row_topk": 1, "freud_topk_decode": 1, "freud_topk_dacts": 1, "freud_axpby": 1, "freud_csc_build": 4,
+    "freud_topk_sparse_grads": 1, "freud_topk_bdec_grad": 1, "freud_topk_loss_scalars": 1,
+    "freud_dead_latent_update": 1, "freud_rownorm_project": 1, "freud_remove_parallel_grad": 1,
+    "freud_l1_colnorm": 1, "freud_l1_loss_reduce": 1, "freud_l1_dz": 1, "freud_l1_weight_grad": 1,
+    "freud_grad_sumsq": 1, "freud_clip_grads": 1, "freud_adam_step": 1, "freud_radam_step": 1,
+    "freud_search_dense": 1, "freud_search_indexed": 1, "freud_search_topn": 1,
+}
+
 _lib = None
-launch_count = 0  # number of C-ABI calls that enqueued kernels (bench.py reports it as gpu_launches evidence)
+call_count = 0      # C-ABI calls made
+kernel_launches = 0  # CUDA kernels those calls enqueued
+# when set to a dict, every call is bracketed by CUDA events on the current stream: name -> [(start, end), ...]
+profile = None
 
 
 def lib():
@@ -82,9 +96,27 @@ def lib():
 
 def call(name, *args):
     """Invoke a C-ABI entry point; raise RuntimeError(freud_last_error()) on a non-zero status."""
-    global launch_count
+    global call_count, kernel_launches
     handle = lib()
-    rc = getattr(handle, name)(*args)
+    if profile is not None:
+        import torch
+
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        rc = getattr(handle, name)(*args)
+        end.record()
+        profile.setdefault(name, []).append((start, end))
+    else:
+        rc = getattr(handle, name)(*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {handle.freud_last_error().decode()}")
-    launch_count += 1
+    call_count += 1
+    kernel_launches += KERNELS_PER_CALL[name]
+
+
+def profile_summary():
+    """{name: (calls, total_ms)} from the recorded events (call after torch.cuda.synchronize())."""
+    out = {}
+    for name, evs in (profile or {}).items():
+        out[name] = (len(evs), sum(s.elapsed_time(e) for s, e in evs))
+    return out

@@ -30,6 +30,9 @@ def _r(t: torch.Tensor, mode: str) -> torch.Tensor:
 # --------------------------------------------------------------------------- #
 # selection
 # --------------------------------------------------------------------------- #
+FAST_TOPK = False  # bench.py's cpu_baseline sets this: time torch.topk (what the reference calls), not a full sort
+
+
 def select_topk(latents: torch.Tensor, k: int):
     """topkautoencoder.py:79-81 ``latents.topk(k, sorted=False)``.
 
@@ -37,6 +40,8 @@ def select_topk(latents: torch.Tensor, k: int):
     the CUDA kernels) define it: value descending, then index ascending.
     Returned sorted that way; compare with the reference as per-row *sets*.
     """
+    if FAST_TOPK:
+        return latents.topk(k, sorted=False)
     vals, idx = torch.sort(latents, dim=-1, descending=True, stable=True)
     return vals[..., :k].contiguous(), idx[..., :k].contiguous()
 
