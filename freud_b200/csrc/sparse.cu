@@ -318,96 +318,202 @@ __global__ void __launch_bounds__(256) csc_sort_kernel(const int32_t* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------ weight grads
-// One CTA per feature f.  Thread c4 owns 4 channels; the CTA walks list(f) and accumulates
-//   dW_dec[f,:] += a_p * g[t_p,:]      dW_enc[f,:] += dpre_p * xc[t_p,:]
-// with 4 list entries in flight.  Gathers are whole contiguous rows (coalesced across the CTA).
-template <typename GT, typename XT>
-__global__ void __launch_bounds__(256) sparse_grads_kernel(
-    const int32_t* __restrict__ offsets, const int32_t* __restrict__ entries, const float* __restrict__ top_vals,
-    const float* __restrict__ dacts, const GT* __restrict__ g, const XT* __restrict__ xc,
-    const float* __restrict__ b_dec, const float* __restrict__ scales, float* __restrict__ dW_dec,
-    float* __restrict__ dW_enc, float* __restrict__ db_enc, int d, int k, int accumulate) {
-  const int f = blockIdx.x;
-  const int beg = offsets[f], end = offsets[f + 1];
-  const float s_dec = scales[0], s_enc = scales[1];
-  constexpr bool kRecenter = sizeof(XT) == 4;  // fp32 path: xc = x - b_dec recomputed on the fly
-  __shared__ int32_t tok_s[256];
-  __shared__ float a_s[256];
-  __shared__ float dp_s[256];
-  float dpsum = 0.f;
-  const int chunk = blockDim.x;
-  const int num_pass = (d + chunk * 4 - 1) / (chunk * 4);  // 1 for d <= 1024 (block sized to d/4 threads)
-  for (int pass = 0; pass < num_pass; ++pass) {
-    const int c = (pass * chunk + threadIdx.x) * 4;
-    const bool active = c < d;
-    float4 accd = make_float4(0, 0, 0, 0), acce = make_float4(0, 0, 0, 0);
-    float4 bd = make_float4(0, 0, 0, 0);
-    if (kRecenter && active) bd = load4(b_dec + c);
-    for (int base = beg; base < end; base += chunk) {
-      const int cnt = min(chunk, end - base);
-      __syncthreads();
-      if (threadIdx.x < cnt) {
-        const int p = entries[base + threadIdx.x];
-        const float a = top_vals[p];
-        tok_s[threadIdx.x] = p / k;
-        a_s[threadIdx.x] = a * s_dec;
-        const float dp = a > 0.f ? dacts[p] * s_enc : 0.f;
-        dp_s[threadIdx.x] = dp;
-        if (pass == 0) dpsum += dp;
-      }
-      __syncthreads();
-      if (active) {
-        int i = 0;
-        for (; i + 4 <= cnt; i += 4) {
-          float4 gv[4], xv[4];
+// Work item = (feature f, chunk of <= kChunk list entries); real activations make the lists wildly uneven (a few
+// dense features fire on most tokens), so long lists are split over many CTAs.  Each CTA stages its chunk's
+// (token, a*s_dec, dpre) triples in shared memory, then `groups` row-teams walk the entries, every thread owning
+// one 16-byte column slice of the gathered g / xc rows (whole contiguous rows: coalesced), 4 entries in flight:
+//   dW_dec[f,:] += a_p * g[t_p,:]      dW_enc[f,:] += dpre_p * xc[t_p,:]      db_enc[f] += dpre_p
+// Single-chunk features store their rows; multi-chunk features accumulate with vector atomics into zeroed rows.
+constexpr int kChunk = 1024;
+
+__global__ void __launch_bounds__(1024) chunk_scan_kernel(const int32_t* __restrict__ offsets,
+                                                          int32_t* __restrict__ chunk_off, int n) {
+  __shared__ int32_t warp_tot[32];
+  __shared__ int32_t carry_s;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int32_t v = i < n ? (offsets[i + 1] - offsets[i] + kChunk - 1) / kChunk : 0;
+    int32_t incl = v;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int64_t t = tok_s[i + u];
-            gv[u] = load4(g + t * d + c);
-            xv[u] = load4(xc + t * d + c);
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float a = a_s[i + u], dp = dp_s[i + u];
-            accd.x = fmaf(a, gv[u].x, accd.x); accd.y = fmaf(a, gv[u].y, accd.y);
-            accd.z = fmaf(a, gv[u].z, accd.z); accd.w = fmaf(a, gv[u].w, accd.w);
-            acce.x = fmaf(dp, xv[u].x - bd.x, acce.x); acce.y = fmaf(dp, xv[u].y - bd.y, acce.y);
-            acce.z = fmaf(dp, xv[u].z - bd.z, acce.z); acce.w = fmaf(dp, xv[u].w - bd.w, acce.w);
-          }
-        }
-        for (; i < cnt; ++i) {
-          const int64_t t = tok_s[i];
-          const float4 gv = load4(g + t * d + c);
-          const float4 xv = load4(xc + t * d + c);
-          const float a = a_s[i], dp = dp_s[i];
-          accd.x = fmaf(a, gv.x, accd.x); accd.y = fmaf(a, gv.y, accd.y);
-          accd.z = fmaf(a, gv.z, accd.z); accd.w = fmaf(a, gv.w, accd.w);
-          acce.x = fmaf(dp, xv.x - bd.x, acce.x); acce.y = fmaf(dp, xv.y - bd.y, acce.y);
-          acce.z = fmaf(dp, xv.z - bd.z, acce.z); acce.w = fmaf(dp, xv.w - bd.w, acce.w);
-        }
-      }
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += u;
     }
-    if (active) {
-      float* pd = dW_dec + static_cast<int64_t>(f) * d + c;
-      float* pe = dW_enc + static_cast<int64_t>(f) * d + c;
-      if (accumulate) {
-        const float4 od = *reinterpret_cast<const float4*>(pd), oe = *reinterpret_cast<const float4*>(pe);
-        accd.x += od.x; accd.y += od.y; accd.z += od.z; accd.w += od.w;
-        acce.x += oe.x; acce.y += oe.y; acce.z += oe.z; acce.w += oe.w;
+    if (lane == 31) warp_tot[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+      int32_t t = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int32_t u = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += u;
       }
-      store4(pd, accd);
-      store4(pe, acce);
+      warp_tot[lane] = t;
+    }
+    __syncthreads();
+    const int32_t carry = carry_s;
+    if (i < n) chunk_off[i] = carry + (w > 0 ? warp_tot[w - 1] : 0) + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + warp_tot[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) chunk_off[n] = carry_s;
+}
+
+template <typename T> struct RowVec;
+template <> struct RowVec<__nv_bfloat16> {
+  static constexpr int kVec = 8;
+  __device__ static __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
     }
   }
-  // db_enc[f] = sum of dpre over the list (each entry was loaded by exactly one thread in the first pass)
-  __shared__ float red[8];
+};
+template <> struct RowVec<float> {
+  static constexpr int kVec = 4;
+  __device__ static __forceinline__ void load(const float* p, float (&v)[4]) {
+    const float4 f = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+  }
+};
+
+template <typename GT, typename XT>
+__global__ void __launch_bounds__(256) sparse_grads_kernel(
+    const int32_t* __restrict__ offsets, const int32_t* __restrict__ chunk_off, const int32_t* __restrict__ entries,
+    const float* __restrict__ top_vals, const float* __restrict__ dacts, const GT* __restrict__ g,
+    const XT* __restrict__ xc, const float* __restrict__ b_dec, const float* __restrict__ scales,
+    float* __restrict__ dW_dec, float* __restrict__ dW_enc, float* __restrict__ db_enc, int n, int d, int k) {
+  constexpr int V = RowVec<GT>::kVec;
+  static_assert(RowVec<XT>::kVec == V, "g and xc share a storage type");
+  constexpr bool kRecenter = sizeof(XT) == 4;  // fp32 path: xc = x - b_dec recomputed on the fly
+  extern __shared__ float red_s[];             // [groups][2][d] cross-team reduction
+  __shared__ int32_t tok_s[kChunk];
+  __shared__ float a_s[kChunk];
+  __shared__ float dp_s[kChunk];
+  __shared__ int f_s;
+  __shared__ float wsum[8];
+  const int item = blockIdx.x;
+  if (item >= chunk_off[n]) return;
+  if (threadIdx.x == 0) {  // binary search: last f with chunk_off[f] <= item
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (chunk_off[mid] <= item) lo = mid; else hi = mid - 1;
+    }
+    f_s = lo;
+  }
+  __syncthreads();
+  const int f = f_s;
+  const int nchunks = chunk_off[f + 1] - chunk_off[f];
+  const int beg = offsets[f] + (item - chunk_off[f]) * kChunk;
+  const int cnt = min(kChunk, offsets[f + 1] - beg);
+  const float s_dec = scales[0], s_enc = scales[1];
+  float dpsum = 0.f;
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const int p = entries[beg + i];
+    const float a = top_vals[p];
+    const float dp = a > 0.f ? dacts[p] * s_enc : 0.f;  // ReLU mask of pre_acts at the selected entries
+    tok_s[i] = p / k;
+    a_s[i] = a * s_dec;
+    dp_s[i] = dp;
+    dpsum += dp;
+  }
+  __syncthreads();
+  const int tpr = (d + V - 1) / V;              // threads per row
+  const int col_passes = (tpr + 255) / 256;     // > 1 only for very wide rows
+  const int tpr_eff = col_passes > 1 ? 256 : tpr;
+  const int groups = col_passes > 1 ? 1 : max(1, 256 / tpr);
+  const int team = threadIdx.x / tpr_eff;
+  const int lane_c = threadIdx.x - team * tpr_eff;
+  const bool multi = nchunks > 1;
+  for (int cp = 0; cp < col_passes; ++cp) {
+    const int c = (cp * 256 + lane_c) * V;
+    const bool active = team < groups && c < d;
+    float accd[V], acce[V], bd[V];
+#pragma unroll
+    for (int u = 0; u < V; ++u) { accd[u] = 0.f; acce[u] = 0.f; bd[u] = 0.f; }
+    if (active) {
+      if (kRecenter) {
+#pragma unroll
+        for (int u = 0; u < V; ++u) bd[u] = b_dec[c + u];
+      }
+      int i = team;
+      for (; i + 3 * groups < cnt; i += 4 * groups) {
+        float gv[4][V], xv[4][V];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int64_t t = tok_s[i + u * groups];
+          RowVec<GT>::load(g + t * d + c, gv[u]);
+          RowVec<XT>::load(xc + t * d + c, xv[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float a = a_s[i + u * groups], dp = dp_s[i + u * groups];
+#pragma unroll
+          for (int e = 0; e < V; ++e) {
+            accd[e] = fmaf(a, gv[u][e], accd[e]);
+            acce[e] = fmaf(dp, xv[u][e] - bd[e], acce[e]);
+          }
+        }
+      }
+      for (; i < cnt; i += groups) {
+        const int64_t t = tok_s[i];
+        float gv[V], xv[V];
+        RowVec<GT>::load(g + t * d + c, gv);
+        RowVec<XT>::load(xc + t * d + c, xv);
+        const float a = a_s[i], dp = dp_s[i];
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          accd[e] = fmaf(a, gv[e], accd[e]);
+          acce[e] = fmaf(dp, xv[e] - bd[e], acce[e]);
+        }
+      }
+    }
+    // cross-team reduction through shared memory, then one store / vector-atomic per 4 columns
+    __syncthreads();
+    if (active) {
+      float* r = red_s + static_cast<size_t>(team) * 2 * d;
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        r[c + e] = accd[e];
+        r[d + c + e] = acce[e];
+      }
+    }
+    __syncthreads();
+    const int c_lo = cp * 256 * V, c_hi = min(d, c_lo + 256 * V);
+    const int span4 = (c_hi - c_lo) / 4;  // d % 4 == 0
+    for (int q = threadIdx.x; q < 2 * span4; q += blockDim.x) {
+      const int m = q / span4;
+      const int cc = c_lo + (q - m * span4) * 4;
+      float4 sum = make_float4(0, 0, 0, 0);
+      for (int t = 0; t < groups; ++t) {
+        const float4 v = *reinterpret_cast<const float4*>(red_s + (static_cast<size_t>(t) * 2 + m) * d + cc);
+        sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+      }
+      float* dst = (m == 0 ? dW_dec : dW_enc) + static_cast<int64_t>(f) * d + cc;
+      if (multi) {
+        atomicAdd(reinterpret_cast<float4*>(dst), sum);
+      } else {
+        const float4 old = *reinterpret_cast<const float4*>(dst);  // zero, or earlier decodes when accumulating
+        *reinterpret_cast<float4*>(dst) = make_float4(old.x + sum.x, old.y + sum.y, old.z + sum.z, old.w + sum.w);
+      }
+    }
+  }
   dpsum = warp_sum(dpsum);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dpsum;
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = dpsum;
   __syncthreads();
   if (threadIdx.x == 0) {
     float tot = 0.f;
-    for (int w = 0; w < (blockDim.x >> 5); ++w) tot += red[w];
-    db_enc[f] = accumulate ? db_enc[f] + tot : tot;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) tot += wsum[w];
+    if (multi) atomicAdd(db_enc + f, tot); else db_enc[f] += tot;
   }
 }
 
@@ -604,21 +710,37 @@ extern "C" int freud_csc_build(const int32_t* top_idx, int64_t N, int64_t k, int
 extern "C" int freud_topk_sparse_grads(const int32_t* offsets, const int32_t* entries, const float* top_vals,
                                        const float* dacts, const void* g, int g_is_bf16, const void* xc,
                                        int xc_is_bf16, const float* b_dec, const float* scales, float* dW_dec,
-                                       float* dW_enc, float* db_enc, int64_t n, int64_t d, int64_t k, int accumulate,
-                                       void* stream) {
+                                       float* dW_enc, float* db_enc, int32_t* chunk_off, int64_t n_entries,
+                                       int64_t n, int64_t d, int64_t k, int accumulate, void* stream) {
   FREUD_REQUIRE(n > 0 && d % 4 == 0, "sparse_grads needs d % 4 == 0");
   FREUD_REQUIRE(g_is_bf16 == xc_is_bf16, "g and xc must share a storage type");
+  FREUD_REQUIRE(!g_is_bf16 || d % 8 == 0, "bf16 rows need d % 8 == 0");
   FREUD_REQUIRE(xc_is_bf16 || b_dec != nullptr, "fp32 path recomputes x - b_dec and needs b_dec");
-  int threads = (int)((d / 4 + 31) / 32) * 32;
-  if (threads > 256) threads = 256;
-  if (g_is_bf16)
-    sparse_grads_kernel<__nv_bfloat16, __nv_bfloat16><<<(int)n, threads, 0, STREAM>>>(
-        offsets, entries, top_vals, dacts, static_cast<const __nv_bfloat16*>(g),
-        static_cast<const __nv_bfloat16*>(xc), b_dec, scales, dW_dec, dW_enc, db_enc, (int)d, (int)k, accumulate);
-  else
-    sparse_grads_kernel<float, float><<<(int)n, threads, 0, STREAM>>>(
-        offsets, entries, top_vals, dacts, static_cast<const float*>(g), static_cast<const float*>(xc), b_dec, scales,
-        dW_dec, dW_enc, db_enc, (int)d, (int)k, accumulate);
+  if (!accumulate) {
+    FREUD_CHECK_CUDA(cudaMemsetAsync(dW_dec, 0, n * d * sizeof(float), STREAM));
+    FREUD_CHECK_CUDA(cudaMemsetAsync(dW_enc, 0, n * d * sizeof(float), STREAM));
+    FREUD_CHECK_CUDA(cudaMemsetAsync(db_enc, 0, n * sizeof(float), STREAM));
+  }
+  chunk_scan_kernel<<<1, 1024, 0, STREAM>>>(offsets, chunk_off, (int)n);
+  const int64_t max_items = n_entries / kChunk + n;  // ceil(len/kChunk) summed over features, upper bound
+  const int V = g_is_bf16 ? 8 : 4;
+  const int tpr = (int)((d + V - 1) / V);
+  const int groups = tpr > 256 ? 1 : (256 / tpr > 0 ? 256 / tpr : 1);
+  const size_t smem = static_cast<size_t>(groups) * 2 * d * sizeof(float);
+  FREUD_REQUIRE(smem + 3 * kChunk * 4 + 64 <= 227 * 1024, "activation size too wide for sparse_grads");
+  if (g_is_bf16) {
+    auto kern = sparse_grads_kernel<__nv_bfloat16, __nv_bfloat16>;
+    if (smem > 32 * 1024) FREUD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)max_items, 256, smem, STREAM>>>(
+        offsets, chunk_off, entries, top_vals, dacts, static_cast<const __nv_bfloat16*>(g),
+        static_cast<const __nv_bfloat16*>(xc), b_dec, scales, dW_dec, dW_enc, db_enc, (int)n, (int)d, (int)k);
+  } else {
+    auto kern = sparse_grads_kernel<float, float>;
+    if (smem > 32 * 1024) FREUD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)max_items, 256, smem, STREAM>>>(
+        offsets, chunk_off, entries, top_vals, dacts, static_cast<const float*>(g), static_cast<const float*>(xc),
+        b_dec, scales, dW_dec, dW_enc, db_enc, (int)n, (int)d, (int)k);
+  }
   FREUD_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
