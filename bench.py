@@ -40,9 +40,11 @@ METRIC = "sae_train_activation_tokens_per_sec"
 
 
 def synth_batch(B, T, d, seed, device="cpu", pin=False):
-    """x = randn * sigma_t + mu_d so the b_dec / total_variance paths are non-trivial."""
+    """x = randn([B,1500,d]) with a per-frame scale sigma_t so total_variance is non-trivial.
+    (Zero mean: a large shared mean makes a handful of latents win every token and most others die, which turns
+    the step into the AuxK-live variant; that variant is measured separately, see `auxk_live`.)"""
     g = torch.Generator().manual_seed(seed)
-    x = torch.randn(B, T, d, generator=g) * (0.5 + torch.rand(T, 1, generator=g)) + torch.randn(d, generator=g)
+    x = torch.randn(B, T, d, generator=g) * (0.5 + torch.rand(T, 1, generator=g))
     if pin:
         x = x.pin_memory()
     return x.to(device) if device != "cpu" else x

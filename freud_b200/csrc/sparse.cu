@@ -577,6 +577,26 @@ __global__ void __launch_bounds__(256) remove_parallel_kernel(float* __restrict_
   for (int c = lane; c < cols; c += 32) gr[c] = fmaf(-s, w[c], gr[c]);
 }
 
+// dst[r, :] = src[rows[r], :] in 4-byte words (row_words per row); used to compact the dead-latent encoder rows.
+__global__ void __launch_bounds__(256) gather_rows_kernel(const uint32_t* __restrict__ src,
+                                                          const int32_t* __restrict__ rows,
+                                                          uint32_t* __restrict__ dst, int64_t n_rows, int row_words) {
+  const int64_t total = n_rows * row_words;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / row_words;
+    const int w = static_cast<int>(i - r * row_words);
+    dst[i] = __ldg(src + static_cast<int64_t>(rows[r]) * row_words + w);
+  }
+}
+__global__ void __launch_bounds__(256) index_map_kernel(const int32_t* __restrict__ table,
+                                                        const int32_t* __restrict__ in, int32_t* __restrict__ out,
+                                                        int64_t count) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < count;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    out[i] = table[in[i]];
+}
+
 static inline int grid_for(int64_t work, int block, int max_blocks) {
   int64_t g = (work + block - 1) / block;
   if (g > max_blocks) g = max_blocks;
@@ -689,6 +709,23 @@ extern "C" int freud_axpby(const float* a, const float* b, const float* coef, vo
     axpby_kernel<__nv_bfloat16><<<grid, 256, 0, STREAM>>>(a, b, coef, static_cast<__nv_bfloat16*>(out), numel / 4);
   else
     axpby_kernel<float><<<grid, 256, 0, STREAM>>>(a, b, coef, static_cast<float*>(out), numel / 4);
+  FREUD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int freud_gather_rows(const void* src, const int32_t* rows, void* dst, int64_t n_rows, int64_t row_bytes,
+                                 void* stream) {
+  FREUD_REQUIRE(n_rows > 0 && row_bytes > 0 && row_bytes % 4 == 0, "gather_rows needs row_bytes % 4 == 0");
+  const int grid = grid_for(n_rows * (row_bytes / 4), 256, sm_count() * 8);
+  gather_rows_kernel<<<grid, 256, 0, STREAM>>>(static_cast<const uint32_t*>(src), rows, static_cast<uint32_t*>(dst),
+                                              n_rows, (int)(row_bytes / 4));
+  FREUD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int freud_index_map(const int32_t* table, const int32_t* in, int32_t* out, int64_t count, void* stream) {
+  FREUD_REQUIRE(count > 0, "index_map needs count > 0");
+  index_map_kernel<<<grid_for(count, 256, sm_count() * 8), 256, 0, STREAM>>>(table, in, out, count);
   FREUD_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

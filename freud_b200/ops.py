@@ -98,6 +98,21 @@ def row_topk(latents: torch.Tensor, k: int, col_mask: torch.Tensor | None = None
     return vals, idx
 
 
+def gather_rows(src: torch.Tensor, rows: torch.Tensor):
+    """dst[r] = src[rows[r]] for a 1-D or 2-D source (rows int32)."""
+    row_elems = 1 if src.dim() == 1 else src.shape[1]
+    out = torch.empty((rows.numel(),) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    call("freud_gather_rows", _ptr(src), _ptr(rows), _ptr(out), rows.numel(), row_elems * src.element_size(),
+         _stream())
+    return out
+
+
+def index_map(table: torch.Tensor, idx: torch.Tensor):
+    out = torch.empty_like(idx)
+    call("freud_index_map", _ptr(table), _ptr(idx), _ptr(out), idx.numel(), _stream())
+    return out
+
+
 def topk_decode(top_vals, top_idx, W_dec, b_dec, target=None, *, resid_dtype=None, want_sse=False,
                 want_colsum=False):
     """sae_out = sum_j a_j W_dec[i_j] + b_dec; optional residual / sse / column sums against `target`."""

@@ -78,22 +78,22 @@ def topk_forward(x, W_enc, b_enc, W_dec, b_dec, k, *, precision, dead_mask=None,
     wd = ops.split_operand(W_dec, BF16)[0] if precision == BF16 else W_dec
     # reference: `int(dead_mask.sum())` (topkautoencoder.py:109) -- one 8-byte device->host read, as upstream
     num_dead = int(dead_mask.sum()) if dead_mask is not None else 0
-    generic = bool(multi_topk or num_dead > 0 or k != ops.K_FUSED)
+    fused_main = (k == ops.K_FUSED) and not multi_topk
+    generic = not fused_main or num_dead > 0  # backward needs materialised gradient seeds (AuxK couples e_hat and e)
     zero = torch.zeros((), dtype=torch.float32, device=x.device)
 
     pre = None
-    if not generic:
+    if fused_main:
         vals, idx = ops.topk_encode(xc_hi, xc_lo, we_hi, we_lo, b_enc, precision)
     else:
         pre = ops.gemm_nt(xc_hi, xc_lo, we_hi, we_lo, b_enc, True, precision)
         vals, idx = ops.row_topk(pre, k)
 
-    fast_bwd = need_grad and not generic
     resid_dtype = None
-    if fast_bwd:
-        resid_dtype = torch.bfloat16 if precision == BF16 else torch.float32
-    elif generic:
+    if generic:
         resid_dtype = torch.float32
+    elif need_grad:
+        resid_dtype = torch.bfloat16 if precision == BF16 else torch.float32
     sae_out, e, sse, colsum_e = ops.topk_decode(vals, idx, wd, b_dec, x2, resid_dtype=resid_dtype, want_sse=True,
                                                 want_colsum=need_grad)
     numel = N * d
@@ -109,7 +109,18 @@ def topk_forward(x, W_enc, b_enc, W_dec, b_dec, k, *, precision, dead_mask=None,
         k_aux = d // 2
         scale = min(num_dead / k_aux, 1.0)
         k_aux = min(k_aux, num_dead)
-        a_vals, a_idx = ops.row_topk(pre, k_aux, col_mask=dead_mask)
+        if pre is not None:
+            a_vals, a_idx = ops.row_topk(pre, k_aux, col_mask=dead_mask)
+        else:
+            # dead latents are a column subset: GEMM against their compacted encoder rows, select among them, map
+            # the subset-local indices back (same (value desc, index asc) order as the masked full-width top-k)
+            dead_idx = torch.nonzero(dead_mask).squeeze(1).to(torch.int32)
+            ws_hi = ops.gather_rows(we_hi, dead_idx)
+            ws_lo = ops.gather_rows(we_lo, dead_idx) if we_lo is not None else None
+            bs = ops.gather_rows(b_enc, dead_idx)
+            pre_dead = ops.gemm_nt(xc_hi, xc_lo, ws_hi, ws_lo, bs, True, precision)
+            a_vals, a_loc = ops.row_topk(pre_dead, k_aux)
+            a_idx = ops.index_map(dead_idx, a_loc)
         _, r_aux, sse_aux, _ = ops.topk_decode(a_vals, a_idx, wd, b_dec, e, resid_dtype=torch.float32,
                                                want_sse=True)
         if dp is not None:

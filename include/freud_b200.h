@@ -65,6 +65,14 @@ int freud_gemm_nt(const void* a_hi, const void* a_lo, const void* b_hi, const vo
 int freud_row_topk(const float* latents, const uint8_t* col_mask, float* vals, int32_t* idx,
                    int64_t rows, int64_t n, int64_t k, void* stream);
 
+/* AuxK support (topkautoencoder.py:118-121): the dead latents form a column subset, so their pre-activations
+ * come from a GEMM against the compacted encoder rows instead of a masked [N,n] matrix.
+ *   freud_gather_rows: dst[r,:] = src[rows[r],:]  (row_bytes % 4 == 0; weights, biases)
+ *   freud_index_map  : out[i] = table[in[i]]      (subset-local top-k indices -> dictionary indices) */
+int freud_gather_rows(const void* src, const int32_t* rows, void* dst, int64_t n_rows, int64_t row_bytes,
+                      void* stream);
+int freud_index_map(const int32_t* table, const int32_t* in, int32_t* out, int64_t count, void* stream);
+
 /* Sparse decode + residual (eager_decode + decode, topkautoencoder.py:15-18,87-91,101):
  *   sae_out[t,:] = sum_j top_vals[t,j] * W_dec[top_idx[t,j],:] + b_dec
  * W_dec is fp32 (w_is_bf16 == 0) or a bf16 copy.  Optional outputs (NULL to skip):

@@ -134,6 +134,42 @@ def test_fused_fast_path_vs_oracle(precision, tol, shape):
             assert rel_err(grads[key].cpu(), rg[key]) < tol, key
 
 
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 4e-3)])
+@pytest.mark.parametrize("n_dead", [7, 150])
+def test_fused_main_with_live_auxk_vs_oracle(precision, tol, n_dead):
+    """k == 32 with dead latents: fused encoder for the main selection, AuxK on the compacted dead-latent
+    subset (GEMM against gathered encoder rows), coupled backward (e not detached, topkautoencoder.py:126)."""
+    from freud_b200 import topk_engine
+    from freud_b200._lib import BF16, FP32
+
+    B, T, d, n, k = 2, 150, 64, 512, 32
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(B, T, d, generator=g) * (0.5 + torch.rand(T, 1, generator=g))
+    W_enc = torch.randn(n, d, generator=g) / d ** 0.5
+    W_dec = osae.set_decoder_norm_to_unit_norm(W_enc.clone() + 0.1 * torch.randn(n, d, generator=g))
+    b_enc = 0.05 * torch.randn(n, generator=g)
+    b_dec = 0.1 * torch.randn(d, generator=g)
+    dead = torch.zeros(n, dtype=torch.bool)
+    dead[torch.randperm(n, generator=g)[:n_dead]] = True
+    alpha = 1 / 32
+    ref = osae.topk_forward(x, W_enc, b_enc, W_dec, b_dec, k, dead_mask=dead, auxk_alpha=alpha, mode=precision)
+    rg = osae.topk_backward(x, W_enc, b_enc, W_dec, b_dec, ref, k, auxk_alpha=alpha, mode=precision)
+    prec = BF16 if precision == "bf16" else FP32
+    cu = [v.cuda() for v in (x, W_enc, b_enc, W_dec, b_dec)]
+    res, st = topk_engine.topk_forward(*cu, k, precision=prec, dead_mask=dead.cuda(), auxk_alpha=alpha)
+    assert st.aux is not None
+    grads = topk_engine.topk_backward(st, 1.0, 1.0, 0.125)
+    torch.cuda.synchronize()
+    same_main = sets_equal_rows(res.top_idx.cpu(), ref.top_indices.reshape(-1, k))
+    same_aux = sets_equal_rows(st.aux[1].cpu(), ref.aux[1].reshape(-1, ref.aux[1].shape[-1]))
+    assert same_main.float().mean() > 0.97 and same_aux.float().mean() > 0.97
+    assert rel_err(res.fvu.cpu(), ref.fvu) < max(tol, 1e-5)
+    if bool(same_main.all()) and bool(same_aux.all()):
+        assert rel_err(res.auxk_loss.cpu(), ref.auxk_loss) < tol
+        for key in TOPK_KEYS:
+            assert rel_err(grads[key].cpu(), rg[key]) < tol, key
+
+
 def test_short_rows_and_ragged_sizes():
     """Rows with fewer than 32 positive pre-activations are completed with zeros at the lowest free indices
     (oracle order); N not a multiple of 128 and n not a multiple of 256 exercise the TMA out-of-bounds fill."""
