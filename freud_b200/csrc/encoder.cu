@@ -3,34 +3,58 @@
 #include "host_common.h"
 #include "../../include/freud_b200.h"
 
+#include <cstdlib>
+
 namespace freud {
 
-template <int BN, int STAGES, int EPI, bool TF32>
+template <int BN, int STAGES, int EPI, bool TF32, int SETS, int CL>
 static int launch_gemm(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, GemmParams p,
                        int passes, cudaStream_t stream) {
-  using L = GemmSmem<BN, STAGES>;
+  using L = GemmSmem<BN, STAGES, EPI, SETS>;
   const int eb = TF32 ? 4 : 2;
   CUtensorMap mA0, mA1, mB0, mB1;
   if (make_tensor_map_2d(&mA0, a_hi, p.M, p.K, p.K, eb, kBM)) return 3;
-  if (make_tensor_map_2d(&mB0, b_hi, p.N, p.K, p.K, eb, BN)) return 3;
+  if (make_tensor_map_2d(&mB0, b_hi, p.N, p.K, p.K, eb, BN / CL)) return 3;
   if (passes > 1) {
     if (make_tensor_map_2d(&mA1, a_lo, p.M, p.K, p.K, eb, kBM)) return 3;
-    if (make_tensor_map_2d(&mB1, b_lo, p.N, p.K, p.K, eb, BN)) return 3;
+    if (make_tensor_map_2d(&mB1, b_lo, p.N, p.K, p.K, eb, BN / CL)) return 3;
   } else {
     mA1 = mA0;
     mB1 = mB0;
   }
   p.passes = passes;
-  auto kern = sm100_gemm_kernel<BN, STAGES, EPI, TF32>;
+  auto kern = sm100_gemm_kernel<BN, STAGES, EPI, TF32, SETS, CL>;
   static bool attr_set = false;
   if (!attr_set) {
     FREUD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     attr_set = true;
   }
-  const int grid = (p.M + kBM - 1) / kBM;
-  kern<<<grid, kGemmThreads, L::kTotal, stream>>>(mA0, mA1, mB0, mB1, p);
-  FREUD_CHECK_CUDA(cudaGetLastError());
+  int grid = (p.M + kBM - 1) / kBM;
+  grid = (grid + CL - 1) / CL * CL;  // whole clusters; surplus CTAs run the protocol on out-of-range rows
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(L::kThreads);
+  cfg.dynamicSmemBytes = L::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  FREUD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, mA0, mA1, mB0, mB1, p));
   return 0;
+}
+
+// Encoder variant (epilogue sets / smem stages / multicast cluster); FREUD_ENC_VARIANT overrides for experiments.
+static int encoder_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FREUD_ENC_VARIANT");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
 }
 
 }  // namespace freud
@@ -52,8 +76,21 @@ extern "C" int freud_topk_encode(const void* xc_hi, const void* xc_lo, const voi
   p.top_vals = top_vals;
   p.top_idx = top_idx;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (precision == FREUD_BF16) return launch_gemm<256, 3, EPI_TOPK, false>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
-  if (precision == FREUD_FP32) return launch_gemm<256, 3, EPI_TOPK, true>(xc_hi, xc_lo, w_hi, w_lo, p, 3, s);
+  if (precision == FREUD_BF16) {
+    switch (encoder_variant()) {
+      case 1: return launch_gemm<256, 3, EPI_TOPK, false, 1, 2>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
+      case 2: return launch_gemm<256, 3, EPI_TOPK, false, 1, 4>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
+      case 3: return launch_gemm<256, 2, EPI_TOPK, false, 2, 1>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
+      case 4: return launch_gemm<256, 2, EPI_TOPK, false, 2, 2>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
+      case 5: return launch_gemm<256, 2, EPI_TOPK, false, 2, 4>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
+      case 6: p.out = top_vals; return launch_gemm<256, 3, EPI_NONE, false, 1, 1>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
+      case 7: p.out = top_vals; return launch_gemm<256, 4, EPI_NONE, false, 1, 1>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
+      case 8: p.out = top_vals; return launch_gemm<256, 4, EPI_NONE, false, 1, 2>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
+      case 9: p.out = top_vals; return launch_gemm<256, 2, EPI_NONE, false, 1, 1>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
+      default: return launch_gemm<256, 3, EPI_TOPK, false, 1, 1>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
+    }
+  }
+  if (precision == FREUD_FP32) return launch_gemm<256, 3, EPI_TOPK, true, 1, 1>(xc_hi, xc_lo, w_hi, w_lo, p, 3, s);
   FREUD_REQUIRE(false, "unknown precision");
 }
 
@@ -74,11 +111,11 @@ extern "C" int freud_gemm_nt(const void* a_hi, const void* a_lo, const void* b_h
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (precision == FREUD_BF16) {
     FREUD_REQUIRE(K % 8 == 0, "K must be a multiple of 8 for bf16 operands");
-    return launch_gemm<256, 3, EPI_STORE, false>(a_hi, nullptr, b_hi, nullptr, p, 1, s);
+    return launch_gemm<256, 4, EPI_STORE, false, 2, 1>(a_hi, nullptr, b_hi, nullptr, p, 1, s);
   }
   if (precision == FREUD_FP32) {
     FREUD_REQUIRE(K % 4 == 0, "K must be a multiple of 4 for fp32 operands");
-    return launch_gemm<256, 3, EPI_STORE, true>(a_hi, a_lo, b_hi, b_lo, p, 3, s);
+    return launch_gemm<256, 4, EPI_STORE, true, 2, 1>(a_hi, a_lo, b_hi, b_lo, p, 3, s);
   }
   FREUD_REQUIRE(false, "unknown precision");
 }

@@ -11,8 +11,9 @@
 //              (reference: TopKAutoEncoder.pre_acts + select_topk, topkautoencoder.py:72-85)
 //   EPI_STORE: bias (+ReLU) and store fp32 [M, N]  (reference: pre_acts / L1 encode + decode GEMMs)
 //
-// Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warp 3 idle, warps 4-7 = epilogue (TMEM lane quarter == warp_idx % 4).
+// Roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warp 3 idle,
+// warps 4-11 = epilogue in two sets of four (TMEM lane quarter == warp_idx % 4); set s drains accumulator
+// buffer s (tiles s, s+2, ...), so two epilogue warps share every SM sub-partition and hide each other's latency.
 // Pipelines: smem ring full/empty (TMA <-> MMA), TMEM accumulator double buffer full/empty (MMA <-> epilogue).
 //
 // Precision: kind::f16 with bf16 operands (1 pass), or kind::tf32 with the 3-pass split
@@ -26,12 +27,12 @@ namespace freud {
 constexpr int kBM = 128;          // token rows per CTA (UMMA M)
 constexpr int kBKBytes = 128;     // one swizzle-128B row per k-block
 constexpr int kTopK = 32;         // fused selection width (one survivor per lane)
-constexpr int kNewSlots = 32;     // unsorted candidate slots per token between compactions
+constexpr int kNewSlots = 28;     // unsorted candidate slots per token between compactions
 constexpr int kCheckEvery = 8;    // columns between buffer-occupancy checks
-constexpr int kGemmThreads = 256;
-constexpr int kEpiWarps = 4;
+// epilogue warps come in SETS (1 or 2) of 4 (one warp per TMEM lane quarter); with 2 sets, set s drains
+// accumulator buffer s.  threads = 128 (producer / MMA / alloc / spare) + SETS * 128
 
-enum { EPI_TOPK = 0, EPI_STORE = 1 };
+enum { EPI_TOPK = 0, EPI_STORE = 1, EPI_NONE = 2 };  // EPI_NONE: mainloop-ceiling probe, discards the tile
 
 struct GemmParams {
   int M, N, K;          // K in elements
@@ -46,8 +47,10 @@ struct GemmParams {
   int64_t ldo;
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EPI, int SETS>
 struct GemmSmem {
+  static constexpr int kEpiWarps = 4 * SETS;
+  static constexpr int kThreads = 128 + kEpiWarps * 32;
   static constexpr int kABytes = kBM * kBKBytes;
   static constexpr int kBBytes = BN * kBKBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
@@ -55,10 +58,11 @@ struct GemmSmem {
   // candidate buffers: per epilogue warp, (32 sorted + kNewSlots new) slots x 33 lanes (padded) x 8 B
   static constexpr int kSlots = kTopK + kNewSlots;
   static constexpr int kBufPerWarp = kSlots * 33 * 8;
-  static constexpr int kBuf = kEpiWarps * kBufPerWarp;
-  static constexpr int kBias = 2 * BN * 4;
+  static constexpr int kBuf = EPI == 0 ? kEpiWarps * kBufPerWarp : 0;
+  static constexpr int kBias = 4 * BN * 4;             // [set][parity][BN]
+  static constexpr int kThr = 2 * kBM * 4;             // per-set published thresholds
   static constexpr int kBars = (2 * STAGES + 4) * 8 + 16;
-  static constexpr int kTotal = kRing + kBuf + kBias + kBars;
+  static constexpr int kTotal = kRing + kBuf + kBias + kThr + kBars;
 };
 
 // 64-bit candidate key: high word = fp32 bits of a strictly positive value, low word = ~index.
@@ -118,12 +122,15 @@ __device__ __noinline__ float compact_one(uint64_t* wbuf, int owner, int ncnt, i
   return __uint_as_float(kth_hi);
 }
 
-template <int BN, int STAGES, int EPI, bool TF32>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int BN, int STAGES, int EPI, bool TF32, int SETS, int CL>
+__global__ void __launch_bounds__(128 + SETS * 128, 1)
 sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                   const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
                   const GemmParams p) {
-  using L = GemmSmem<BN, STAGES>;
+  using L = GemmSmem<BN, STAGES, EPI, SETS>;
+  constexpr int kEpiWarps = L::kEpiWarps;
+  constexpr uint16_t kMcMask = static_cast<uint16_t>((1u << CL) - 1u);
+  const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0u;
   constexpr int kBKe = TF32 ? 32 : 64;  // elements per 128-byte k-block
   constexpr uint32_t kTmemCols = 2 * BN;
   static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns must be pow2 <= 512");
@@ -133,7 +140,8 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   uint8_t* ring = smem;
   uint64_t* cand = reinterpret_cast<uint64_t*>(smem + L::kRing);
   float* bias_s = reinterpret_cast<float*>(smem + L::kRing + L::kBuf);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kRing + L::kBuf + L::kBias);
+  float* thr_s = reinterpret_cast<float*>(smem + L::kRing + L::kBuf + L::kBias);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kRing + L::kBuf + L::kBias + L::kThr);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tfull_bar = bars + 2 * STAGES;
@@ -158,11 +166,11 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   if (warp_idx == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CL);  // every CTA of the cluster releases a slot its peers multicast into
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], kEpiWarps);
+      mbar_init(&tempty_bar[b], 4);
     }
     fence_barrier_init();
   }
@@ -170,8 +178,10 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
+  if (threadIdx.x < 2 * kBM) thr_s[threadIdx.x] = 0.f;  // published per-set thresholds start at the ReLU floor
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();  // peers' barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -192,7 +202,14 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           uint8_t* sb = sa + L::kABytes;
           mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
           tma_load_2d(sa, ma, &full_bar[stage], kb * kBKe, m0, kEvictNormal);
-          tma_load_2d(sb, mb, &full_bar[stage], kb * kBKe, nt * BN, kEvictLast);
+          if constexpr (CL == 1) {
+            tma_load_2d(sb, mb, &full_bar[stage], kb * kBKe, nt * BN, kEvictLast);
+          } else {
+            // every CTA of the cluster walks the same weight tiles: fetch 1/CL of the tile, multicast it to all
+            constexpr int kSlice = BN / CL;
+            tma_load_2d_mc(sb + cta_rank * kSlice * kBKBytes, mb, &full_bar[stage], kb * kBKe,
+                           nt * BN + static_cast<int>(cta_rank) * kSlice, kMcMask, kEvictLast);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -225,7 +242,10 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             else
               mma_f16_ss(d_tmem, adesc, bdesc, idesc, (vk | k4) != 0);
           }
-          tc_commit(&empty_bar[stage]);
+          if constexpr (CL == 1)
+            tc_commit(&empty_bar[stage]);
+          else
+            tc_commit_mc(&empty_bar[stage], kMcMask);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -236,9 +256,12 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     }
   } else if (warp_idx >= 4) {
     // ===================== epilogue =====================
-    const int q = warp_idx & 3;  // TMEM lane quarter this warp may read
+    // Two sets of four warps; set s owns accumulator buffer s, i.e. tiles nt = s, s+2, ...  Within a set, warp
+    // quarter q reads TMEM lanes [32q, 32q+32): one token row per thread.
+    const int q = warp_idx & 3;
     const int ew = warp_idx - 4;
-    const int etid = ew * 32 + lane;
+    const int set = SETS == 2 ? (ew >> 2) : 0;
+    const int stid = q * 32 + lane;  // thread index within the set
     const int row = m0 + q * 32 + lane;
     uint64_t* wbuf = cand + ew * (L::kSlots * 33);
     float thresh = 0.f;
@@ -252,11 +275,12 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       for (int s = 0; s < kTopK; ++s) wbuf[s * 33 + lane] = 0ull;
       __syncwarp();
     }
-    for (int nt = 0; nt < num_nt; ++nt) {
+    for (int nt = set; nt < num_nt; nt += SETS) {
       const int buf = nt & 1;
+      const int it = nt >> 1;  // per-buffer tile counter
       // stage this tile's bias (or -inf for out-of-range columns so they can never be selected)
-      float* bs = bias_s + buf * BN;
-      for (int c = etid; c < BN; c += kEpiWarps * 32) {
+      float* bs = bias_s + (buf * 2 + (it & 1)) * BN;
+      for (int c = stid; c < BN; c += 128) {
         const int gc = nt * BN + c;
         float b = 0.f;
         if (gc < p.N) {
@@ -266,8 +290,15 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         }
         bs[c] = b;
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-      mbar_wait(&tfull_bar[buf], (nt >> 1) & 1);
+      if (set == 0)
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      else
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+      if constexpr (EPI == EPI_TOPK && SETS == 2) {
+        // any lower bound of the row's 32nd largest value is a valid filter: adopt the other set's if tighter
+        thresh = fmaxf(thresh, thr_s[(set ^ 1) * kBM + stid]);
+      }
+      mbar_wait(&tfull_bar[buf], it & 1);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
       const uint32_t bs_addr = smem_u32(bs);
@@ -275,25 +306,27 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_addr + c0, r);
+        float bb[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {  // bias loads overlap the TMEM load
+          const float4 b4 = lds128(bs_addr + (c0 + j) * 4);
+          bb[j] = b4.x; bb[j + 1] = b4.y; bb[j + 2] = b4.z; bb[j + 3] = b4.w;
+        }
         tmem_ld_wait();
         if constexpr (EPI == EPI_TOPK) {
           const uint32_t nidx0 = ~static_cast<uint32_t>(nt * BN + c0);  // ~(col) == nidx0 - j
 #pragma unroll
           for (int g = 0; g < 32; g += kCheckEvery) {
+            float v[kCheckEvery];
 #pragma unroll
-            for (int j4 = 0; j4 < kCheckEvery; j4 += 4) {
-              const float4 b4 = lds128(bs_addr + (c0 + g + j4) * 4);
-              const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+            for (int jj = 0; jj < kCheckEvery; ++jj) v[jj] = __uint_as_float(r[g + jj]) + bb[g + jj];
 #pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                const int j = g + j4 + jj;
-                const float v = __uint_as_float(r[j]) + bb[jj];
-                if (v > thresh) {
-                  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(ptr), "r"(nidx0 - j),
-                               "r"(__float_as_uint(v))
-                               : "memory");
-                  ptr += 33 * 8;
-                }
+            for (int jj = 0; jj < kCheckEvery; ++jj) {
+              if (v[jj] > thresh) {
+                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(ptr), "r"(nidx0 - (g + jj)),
+                             "r"(__float_as_uint(v[jj]))
+                             : "memory");
+                ptr += 33 * 8;
               }
             }
             // compaction round for lanes that could overflow in the next kCheckEvery columns
@@ -306,13 +339,16 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                 const int ncnt = (__shfl_sync(0xffffffffu, ptr, owner) - (warp_new_base + owner * 8)) / (33 * 8);
                 const float t = compact_one(wbuf, owner, ncnt, lane);
                 if (lane == owner) {
-                  thresh = t;
+                  thresh = fmaxf(thresh, t);
                   ptr = my_new_base;
+                  thr_s[set * kBM + stid] = thresh;
                 }
               }
               __syncwarp();
             }
           }
+        } else if constexpr (EPI == EPI_NONE) {
+          if (__uint_as_float(r[0]) + bb[0] == 1.2345e38f) p.out[0] = 1.f;  // keep the loads alive
         } else {
           if (row < p.M) {
             float* orow = p.out + static_cast<int64_t>(row) * p.ldo + nt * BN + c0;
@@ -320,12 +356,11 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             if (full_chunk) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
-                const float4 b4 = lds128(bs_addr + (c0 + j) * 4);
                 float4 o;
-                o.x = __uint_as_float(r[j + 0]) + b4.x;
-                o.y = __uint_as_float(r[j + 1]) + b4.y;
-                o.z = __uint_as_float(r[j + 2]) + b4.z;
-                o.w = __uint_as_float(r[j + 3]) + b4.w;
+                o.x = __uint_as_float(r[j + 0]) + bb[j + 0];
+                o.y = __uint_as_float(r[j + 1]) + bb[j + 1];
+                o.z = __uint_as_float(r[j + 2]) + bb[j + 2];
+                o.w = __uint_as_float(r[j + 3]) + bb[j + 3];
                 if (p.relu) {
                   o.x = fmaxf(o.x, 0.f);
                   o.y = fmaxf(o.y, 0.f);
@@ -338,7 +373,7 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 if (nt * BN + c0 + j < p.N) {
-                  float o = __uint_as_float(r[j]) + bs[c0 + j];
+                  float o = __uint_as_float(r[j]) + bb[j];
                   if (p.relu) o = fmaxf(o, 0.f);
                   orow[j] = o;
                 }
@@ -352,19 +387,28 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       if (lane == 0) mbar_arrive(&tempty_bar[buf]);
     }
     if constexpr (EPI == EPI_TOPK) {
-      // final compaction of every token-lane, then emit (value, index) rows; short rows (fewer than 32
-      // positive pre-activations) are completed with zeros at the lowest indices not already chosen,
-      // which is the oracle's (value desc, index asc) order for the all-zero tail after ReLU.
+      // final compaction of every token-lane in both sets, then merge the two sets' sorted survivors and emit
+      // (value, index) rows; short rows (fewer than 32 positive pre-activations) are completed with zeros at the
+      // lowest indices not already chosen, which is the oracle's (value desc, index asc) order for the all-zero
+      // tail after ReLU.
       __syncwarp();
       for (int owner = 0; owner < 32; ++owner) {
         const int ncnt = (__shfl_sync(0xffffffffu, ptr, owner) - (warp_new_base + owner * 8)) / (33 * 8);
         if (ncnt > 0) compact_one(wbuf, owner, ncnt, lane);
       }
-      __syncwarp();
-      for (int owner = 0; owner < 32; ++owner) {
+      asm volatile("bar.sync 3, %0;" ::"n"(kEpiWarps * 32) : "memory");
+      const uint64_t* bufA = cand + q * (L::kSlots * 33);        // set 0, this lane quarter
+      const uint64_t* bufB = cand + (4 + q) * (L::kSlots * 33);  // set 1, this lane quarter
+      for (int o = 0; o < 32 / SETS; ++o) {
+        const int owner = set * (32 / SETS) + o;
         const int orow = m0 + q * 32 + owner;
         if (orow >= p.M) break;  // warp-uniform
-        const uint64_t key = wbuf[lane * 33 + owner];
+        uint64_t key = bufA[lane * 33 + owner];
+        if constexpr (SETS == 2) {
+          const uint64_t kb = bufB[(31 - lane) * 33 + owner];
+          // max(desc, reversed desc) = the 32 largest of the union as a bitonic sequence -> sort it
+          key = warp_bitonic_merge_desc(key > kb ? key : kb, lane);
+        }
         float val = __uint_as_float(static_cast<uint32_t>(key >> 32));
         uint32_t idx = ~static_cast<uint32_t>(key);
         const uint32_t valid = __ballot_sync(0xffffffffu, key != 0ull);
@@ -403,6 +447,7 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();  // no CTA exits while peers may still signal its barriers
   if (warp_idx == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
