@@ -80,15 +80,25 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def wait_first_sample(self, timeout=5.0):
+        """nvidia-smi's own start-up (NVML init) can stall the GPU for tens of ms: let it finish before timing."""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.lines and time.perf_counter() - t0 < timeout:
+            time.sleep(0.05)
+
+    def mark(self):
+        return time.perf_counter()
+
+    def stop(self, t_begin=None, t_end=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        inside = [ln for (ts, ln) in self.lines if t_begin is not None and t_begin <= ts <= t_end + 0.12]
+        for ln in (inside if inside else [ln for (_, ln) in self.lines]):
             f = [c.strip() for c in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -238,12 +248,14 @@ def main():
         return float(t.item())
 
     # ---------------- device-resident throughput (`value`) + live per-kernel timing
-    for i in range(args.warmup):
-        tr.step(dev_x[i % n_bufs])
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        sampler.wait_first_sample()
+    for i in range(args.warmup):
+        tr.step(dev_x[i % n_bufs])
+    barrier()
+    t_begin = sampler.mark()
     _lib.profile = {}
     k0 = _lib.kernel_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -256,7 +268,7 @@ def main():
     gpu_launches = _lib.kernel_launches - k0
     prof = _lib.profile_summary()
     _lib.profile = None
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, sampler.mark()) if rank == 0 else None
     ms_per_step = ms_total / args.steps
     value = tokens_per_step * args.steps / (ms_total / 1e3)
     last_loss = float(out["loss"].item())

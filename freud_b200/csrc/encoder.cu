@@ -78,19 +78,16 @@ extern "C" int freud_topk_encode(const void* xc_hi, const void* xc_lo, const voi
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (precision == FREUD_BF16) {
     switch (encoder_variant()) {
-      case 1: return launch_gemm<256, 3, EPI_TOPK, false, 1, 2>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
-      case 2: return launch_gemm<256, 3, EPI_TOPK, false, 1, 4>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
-      case 3: return launch_gemm<256, 2, EPI_TOPK, false, 2, 1>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
-      case 4: return launch_gemm<256, 2, EPI_TOPK, false, 2, 2>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
-      case 5: return launch_gemm<256, 2, EPI_TOPK, false, 2, 4>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
+      case 1: return launch_gemm<256, 4, EPI_TOPK, false, 1, 1>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
+      case 2: return launch_gemm<256, 3, EPI_TOPK, false, 2, 2>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
+      case 3: return launch_gemm<256, 3, EPI_TOPK, false, 1, 1>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
       case 6: p.out = top_vals; return launch_gemm<256, 3, EPI_NONE, false, 1, 1>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
       case 7: p.out = top_vals; return launch_gemm<256, 4, EPI_NONE, false, 1, 1>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
-      case 8: p.out = top_vals; return launch_gemm<256, 4, EPI_NONE, false, 1, 2>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
-      case 9: p.out = top_vals; return launch_gemm<256, 2, EPI_NONE, false, 1, 1>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
-      default: return launch_gemm<256, 3, EPI_TOPK, false, 1, 1>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
+      case 8: p.out = top_vals; return launch_gemm<256, 3, EPI_NONE, false, 2, 1>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
+      default: return launch_gemm<256, 3, EPI_TOPK, false, 2, 1>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
     }
   }
-  if (precision == FREUD_FP32) return launch_gemm<256, 3, EPI_TOPK, true, 1, 1>(xc_hi, xc_lo, w_hi, w_lo, p, 3, s);
+  if (precision == FREUD_FP32) return launch_gemm<256, 3, EPI_TOPK, true, 2, 1>(xc_hi, xc_lo, w_hi, w_lo, p, 3, s);
   FREUD_REQUIRE(false, "unknown precision");
 }
 
