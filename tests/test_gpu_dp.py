@@ -1,0 +1,72 @@
+"""2-GPU data-parallel parity: N-rank step == 1-rank step on the concatenated batch."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _build(device, precision):
+    from freud_b200.models.config import TopKAutoEncoderConfig
+    from freud_b200.models.topkautoencoder import TopKAutoEncoder
+    from freud_b200.trainer import SAETrainer
+
+    torch.manual_seed(0)
+    cfg = TopKAutoEncoderConfig.from_dict({"n_dict_components": 1024, "k": 32, "auxk_alpha": 1 / 32})
+    model = TopKAutoEncoder(64, cfg).to(device)
+    return model
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from freud_b200.parallel import DataParallel
+        from freud_b200.trainer import SAETrainer
+
+        g = torch.Generator().manual_seed(7)
+        B, T, d = 8, 96, 64
+        xs = [torch.randn(B, T, d, generator=g) * (0.5 + torch.rand(T, 1, generator=g)) + 0.2 * torch.randn(d, generator=g)
+              for _ in range(2)]
+        kw = dict(lr=1e-3, steps=100, clip_thresh=1.0, optimizer="adam", scheduler="linear",
+                  scheduler_params={"num_warmup_steps": 2}, dead_feature_threshold=1e9, precision="fp32")
+        tr = SAETrainer(_build(dev, "fp32"), dp=DataParallel(), **kw)
+        per = B // world
+        for x in xs:
+            o = tr.step(x[rank * per:(rank + 1) * per].to(dev))
+        torch.cuda.synchronize()
+        if rank == 0:
+            ref = SAETrainer(_build(dev, "fp32"), dp=None, **kw)
+            for x in xs:
+                r = ref.step(x.to(dev))
+            torch.cuda.synchronize()
+            errs = {k: float((tr.params[k].data - ref.params[k].data).abs().max() / ref.params[k].data.abs().max())
+                    for k in tr.params}
+            errs["fvu"] = abs(float(o["fvu"]) - float(r["fvu"])) / float(r["fvu"])
+            errs["frames"] = float((tr.num_frames_since_fired != ref.num_frames_since_fired).sum())
+            out.update(errs)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_rank_step_equals_single_rank_on_concatenated_batch():
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert out, "rank 0 reported nothing"
+    for k, v in out.items():
+        assert v < (1e-12 if k == "frames" else 2e-5), (k, v)
