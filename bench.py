@@ -60,59 +60,76 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region through NVML (the fields of the
+    B200_PROFILING.md nvidia-smi line: clocks.sm, clocks.max.sm, power.draw, clocks_event_reasons.*).  NVML is read
+    in-process every 20 ms: spawning `nvidia-smi -lms` next to a 100 ms timed region stalls the GPU for tens of
+    milliseconds per poll and distorts the measurement it is supposed to qualify."""
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, index):
         self.index = index
-        self.lines = []
-        self.proc = None
+        self.samples = []
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.handle = None
+        self.max_mhz = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except OSError:
-            self.proc = None
+            import pynvml
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append((time.perf_counter(), line.strip()))
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() \
+                else self.index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception as ex:  # noqa: BLE001
+            self.handle = None
+            self.error = repr(ex)
+            return
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
-    def wait_first_sample(self, timeout=5.0):
-        """nvidia-smi's own start-up (NVML init) can stall the GPU for tens of ms: let it finish before timing."""
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:  # noqa: BLE001
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                pw = nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                self.samples.append((time.perf_counter(), mhz, rs, pw))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.02)
+
+    def wait_first_sample(self, timeout=2.0):
         t0 = time.perf_counter()
-        while self.proc is not None and not self.lines and time.perf_counter() - t0 < timeout:
-            time.sleep(0.05)
+        while self.thread is not None and not self.samples and time.perf_counter() - t0 < timeout:
+            time.sleep(0.01)
 
     def mark(self):
         return time.perf_counter()
 
     def stop(self, t_begin=None, t_end=None):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        inside = [ln for (ts, ln) in self.lines if t_begin is not None and t_begin <= ts <= t_end + 0.12]
-        for ln in (inside if inside else [ln for (_, ln) in self.lines]):
-            f = [c.strip() for c in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if val.lower().startswith("active"):
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "error", "")]}
+        self.stop_flag.set()
+        self.thread.join(timeout=1.0)
+        inside = [s for s in self.samples if t_begin is not None and t_begin <= s[0] <= t_end]
+        use = inside if inside else self.samples
+        sm = sorted(s[1] for s in use)
+        reasons = set()
+        for s in use:
+            for name, bit in self.REASONS.items():
+                if s[2] & bit:
                     reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(reasons),
+                "samples": len(use), "power_w_max": max((s[3] for s in use), default=None), "source": "nvml"}
 
 
 # ---------------------------------------------------------------------------------------------- reference arm / CPU
@@ -228,6 +245,9 @@ def main():
         from freud_b200.parallel import DataParallel
 
         dp = DataParallel()
+    # all work runs on an explicit non-blocking stream: the legacy default stream serialises with copy streams
+    main_stream = torch.cuda.Stream(device)
+    torch.cuda.set_stream(main_stream)
     tr = build_trainer(w, args.precision, dp, device)
     B, T, d = w["B"], w["T"], w["d"]
     tokens_per_step = B * T * world
@@ -290,14 +310,19 @@ def main():
         for s in range(2):
             freed[s].record()
         prefetch(0)
-        loss_sum = 0.0
+        loss_sum, prev = 0.0, None
         for i in range(n):
             if i + 1 < n:
                 prefetch(i + 1)  # overlaps the next batch's H2D with this step's compute
             torch.cuda.current_stream().wait_event(ready[i % 2])
             o = tr.step(stage[i % 2])
             freed[i % 2].record()
-            loss_sum += float(o["loss"].item())  # 4-byte D2H read of the step's loss (blocks, as train_sae.py:455)
+            # every step's loss is read back (4-byte D2H, train_sae.py:455); reading step i-1's after enqueueing
+            # step i keeps the host one step ahead of the device instead of idling the GPU during the enqueue
+            if prev is not None:
+                loss_sum += float(prev["loss"].item())
+            prev = o
+        loss_sum += float(prev["loss"].item())
         return loss_sum
 
     e2e_loop(2)

@@ -71,10 +71,23 @@ __global__ void __launch_bounds__(256) search_dense_kernel(const T* __restrict__
   const T* col = acts + file * Tn * F + feature;
   Stat s = stat_init();
   const int limit = trace ? static_cast<int>(Tn) : nf;
-  for (int t = threadIdx.x; t < limit; t += blockDim.x) {
-    const float v = static_cast<float>(col[static_cast<int64_t>(t) * F]);
-    if (trace) trace[file * Tn + t] = v;
-    if (t < nf) stat_push(s, v, t);
+  const int bd = blockDim.x;
+  // 4 independent strided loads in flight per thread (each pulls one 32-byte sector)
+  for (int t0 = threadIdx.x; t0 < limit; t0 += 4 * bd) {
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = t0 + u * bd;
+      v[u] = t < limit ? static_cast<float>(col[static_cast<int64_t>(t) * F]) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = t0 + u * bd;
+      if (t < limit) {
+        if (trace) trace[file * Tn + t] = v[u];
+        if (t < nf) stat_push(s, v[u], t);
+      }
+    }
   }
   s = block_stat_reduce(s, scratch);
   if (threadIdx.x == 0) stat_store(s, file, vmax, amax, vabs);
@@ -94,24 +107,53 @@ __global__ void __launch_bounds__(256) search_indexed_kernel(const float* __rest
   const int nf = min(static_cast<int64_t>(n_frames[file]), Tn);
   const int limit = trace ? static_cast<int>(Tn) : nf;
   Stat s = stat_init();
-  for (int t = w; t < limit; t += nw) {
-    const int64_t base = (file * Tn + t) * k;
-    float v = 0.f;  // feature absent from the frame's top-k -> 0 (utils/activations.py:48-56)
-    for (int64_t j0 = 0; j0 < k; j0 += 32) {
-      const int64_t j = j0 + lane;
-      const bool hit = j < k && static_cast<int64_t>(idx[base + j]) == feature;
-      const uint32_t m = __ballot_sync(0xffffffffu, hit);
-      if (m) {
-        const int src = __ffs(m) - 1;
-        float mine = 0.f;
-        if (lane == src) mine = vals[base + j0 + src];
-        v = __shfl_sync(0xffffffffu, mine, src);
-        break;
+  if (k <= 32) {
+    // common case (k == 32): 4 frames per warp iteration, 4 independent coalesced index loads in flight per lane
+    for (int t0 = w; t0 < limit; t0 += 4 * nw) {
+      IT id[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int t = t0 + u * nw;
+        id[u] = (t < limit && lane < k) ? idx[(file * Tn + t) * k + lane] : static_cast<IT>(-1);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int t = t0 + u * nw;
+        if (t >= limit) break;  // warp-uniform
+        const uint32_t m = __ballot_sync(0xffffffffu, static_cast<int64_t>(id[u]) == feature);
+        float v = 0.f;  // feature absent from the frame's top-k -> 0 (utils/activations.py:48-56)
+        if (m) {
+          const int src = __ffs(m) - 1;  // first matching slot, as `.nonzero()` on a unique match
+          float mine = 0.f;
+          if (lane == src) mine = vals[(file * Tn + t) * k + src];
+          v = __shfl_sync(0xffffffffu, mine, src);
+        }
+        if (lane == 0) {
+          if (trace) trace[file * Tn + t] = v;
+          if (t < nf) stat_push(s, v, t);
+        }
       }
     }
-    if (lane == 0) {
-      if (trace) trace[file * Tn + t] = v;
-      if (t < nf) stat_push(s, v, t);
+  } else {
+    for (int t = w; t < limit; t += nw) {
+      const int64_t base = (file * Tn + t) * k;
+      float v = 0.f;
+      for (int64_t j0 = 0; j0 < k; j0 += 32) {
+        const int64_t j = j0 + lane;
+        const bool hit = j < k && static_cast<int64_t>(idx[base + j]) == feature;
+        const uint32_t m = __ballot_sync(0xffffffffu, hit);
+        if (m) {
+          const int src = __ffs(m) - 1;
+          float mine = 0.f;
+          if (lane == src) mine = vals[base + j0 + src];
+          v = __shfl_sync(0xffffffffu, mine, src);
+          break;
+        }
+      }
+      if (lane == 0) {
+        if (trace) trace[file * Tn + t] = v;
+        if (t < nf) stat_push(s, v, t);
+      }
     }
   }
   s = block_stat_reduce(s, scratch);
