@@ -39,6 +39,9 @@ SIGNATURES = {
     "freud_topk_decode": [_p, _p, _p, _i, _p, _p, _p, _p, _i, _p, _p, _i64, _i64, _i64, _p],
     "freud_topk_dacts": [_p, _i, _p, _p, _i, _p, _i64, _i64, _i64, _p],
     "freud_axpby": [_p, _p, _p, _p, _i, _i64, _p],
+    "freud_shard_merge": [_p, _p, _p, _p, _i64, _i64, _i64, _p],
+    "freud_shard_localize": [_p, _p, _p, _p, _i64, _i64, _i64, _p],
+    "freud_residual": [_p, _p, _p, _i, _p, _p, _i64, _i64, _p],
     "freud_csc_build": [_p, _i64, _i64, _i64, _p, _p, _p, _p],
     "freud_topk_sparse_grads": [_p, _p, _p, _p, _p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i, _p],
     "freud_topk_bdec_grad": [_p, _p, _p, _p, _p, _i64, _i64, _i, _p],
@@ -62,7 +65,7 @@ SIGNATURES = {
 # CUDA kernels each entry point enqueues (memsets not counted); bench.py sums these into `gpu_launches`
 KERNELS_PER_CALL = {
     "freud_topk_prep_x": 1, "freud_split_operand": 1, "freud_topk_encode": 1, "freud_gemm_nt": 1,
-    "freud_row_topk": 1, "freud_gather_rows": 1, "freud_index_map": 1, "freud_topk_decode": 1, "freud_topk_dacts": 1, "freud_axpby": 1, "freud_csc_build": 4,
+    "freud_row_topk": 1, "freud_gather_rows": 1, "freud_index_map": 1, "freud_topk_decode": 1, "freud_topk_dacts": 1, "freud_axpby": 1, "freud_shard_merge": 1, "freud_shard_localize": 1, "freud_residual": 1, "freud_csc_build": 4,
     "freud_topk_sparse_grads": 2, "freud_topk_bdec_grad": 1, "freud_topk_loss_scalars": 1,
     "freud_dead_latent_update": 1, "freud_rownorm_project": 1, "freud_remove_parallel_grad": 1,
     "freud_l1_colnorm": 1, "freud_l1_loss_reduce": 1, "freud_l1_dz": 1, "freud_l1_weight_grad": 1,

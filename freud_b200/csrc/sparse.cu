@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ t
       for (int j = 0; j < jn; ++j) {
         const float a = __shfl_sync(0xffffffffu, my_a, j);
         const int64_t f = __shfl_sync(0xffffffffu, my_i, j);
+        if (f < 0) continue;  // warp-uniform: entry owned by another feature shard
         const WT* wr = W + f * d;
 #pragma unroll
         for (int i = 0; i < CH; ++i) {
@@ -229,8 +230,10 @@ __global__ void __launch_bounds__(256) axpby_kernel(const float* __restrict__ a,
 __global__ void __launch_bounds__(256) csc_hist_kernel(const int32_t* __restrict__ top_idx, int64_t total,
                                                        int32_t* __restrict__ counts) {
   for (int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p < total;
-       p += static_cast<int64_t>(gridDim.x) * blockDim.x)
-    atomicAdd(counts + __ldg(top_idx + p), 1);
+       p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int32_t f = __ldg(top_idx + p);
+    if (f >= 0) atomicAdd(counts + f, 1);  // negative = entry owned by another feature shard
+  }
 }
 
 // Single-block exclusive scan of counts[0..n) -> offsets[0..n]; cursor[f] = offsets[f].
@@ -279,7 +282,9 @@ __global__ void __launch_bounds__(256) csc_fill_kernel(const int32_t* __restrict
                                                        int32_t* __restrict__ cursor, int32_t* __restrict__ entries) {
   for (int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p < total;
        p += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int32_t pos = atomicAdd(cursor + __ldg(top_idx + p), 1);
+    const int32_t f = __ldg(top_idx + p);
+    if (f < 0) continue;
+    const int32_t pos = atomicAdd(cursor + f, 1);
     entries[pos] = static_cast<int32_t>(p);
   }
 }
@@ -597,6 +602,89 @@ __global__ void __launch_bounds__(256) index_map_kernel(const int32_t* __restric
     out[i] = table[in[i]];
 }
 
+// ---------------------------------------------------------------------------------------------- feature sharding
+// Global top-32 of G per-shard top-32 lists (each sorted by (value desc, index asc), indices shard-local):
+// one warp per token, lane j holds element j; each further shard is folded in with max(cur, reversed other)
+// followed by a 5-stage bitonic merge.  Output indices are GLOBAL (local + shard * n_local).
+__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
+  const uint32_t lo = __shfl_sync(0xffffffffu, static_cast<uint32_t>(v), src);
+  const uint32_t hi = __shfl_sync(0xffffffffu, static_cast<uint32_t>(v >> 32), src);
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+__global__ void __launch_bounds__(256) shard_merge_kernel(const float* __restrict__ vals, const int32_t* __restrict__ idx,
+                                                          float* __restrict__ out_vals, int32_t* __restrict__ out_idx,
+                                                          int64_t N, int G, int n_local) {
+  const int lane = threadIdx.x & 31;
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= N) return;
+  uint64_t cur = 0;
+  for (int g = 0; g < G; ++g) {
+    const int64_t o = (static_cast<int64_t>(g) * N + t) * 32 + lane;
+    const uint32_t gi = static_cast<uint32_t>(idx[o] + g * n_local);
+    // zero-valued fillers keep value bits 0 but a real index, so they order by index among themselves
+    const uint64_t key = (static_cast<uint64_t>(__float_as_uint(vals[o])) << 32) | static_cast<uint32_t>(~gi);
+    if (g == 0) {
+      cur = key;
+    } else {
+      const uint64_t rev = shfl64(key, 31 - lane);
+      cur = cur > rev ? cur : rev;
+#pragma unroll
+      for (int j = 16; j > 0; j >>= 1) {
+        const uint64_t other = shfl64(cur, lane ^ j);
+        const bool lower = (lane & j) == 0;
+        const uint64_t mx = cur > other ? cur : other, mn = cur > other ? other : cur;
+        cur = lower ? mx : mn;
+      }
+    }
+  }
+  out_vals[t * 32 + lane] = __uint_as_float(static_cast<uint32_t>(cur >> 32));
+  out_idx[t * 32 + lane] = static_cast<int32_t>(~static_cast<uint32_t>(cur));
+}
+
+// Keep the winners this shard owns: local index in [0, n_local) or -1, value or 0.
+__global__ void __launch_bounds__(256) shard_localize_kernel(const float* __restrict__ vals,
+                                                             const int32_t* __restrict__ gidx,
+                                                             float* __restrict__ lvals, int32_t* __restrict__ lidx,
+                                                             int64_t count, int lo, int n_local) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < count;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int32_t l = gidx[i] - lo;
+    const bool own = l >= 0 && l < n_local;
+    lidx[i] = own ? l : -1;
+    lvals[i] = own ? vals[i] : 0.f;
+  }
+}
+
+// resid = sae_out - target (+ SSE, column sums) after the partial reconstructions have been reduced.
+template <typename RT>
+__global__ void __launch_bounds__(256) residual_kernel(const float* __restrict__ sae_out,
+                                                       const float* __restrict__ target, RT* __restrict__ resid,
+                                                       double* __restrict__ sse, float* __restrict__ colsum,
+                                                       int64_t N, int d) {
+  __shared__ double scratch[32];
+  const int d4 = d >> 2;
+  const int c4 = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 4-channel column group
+  double sq = 0.0;
+  if (c4 < d4) {
+    float4 cs = make_float4(0, 0, 0, 0);
+    for (int64_t t = blockIdx.y; t < N; t += gridDim.y) {
+      const float4 a = load4(sae_out + t * d + c4 * 4), x = load4(target + t * d + c4 * 4);
+      const float4 e = make_float4(a.x - x.x, a.y - x.y, a.z - x.z, a.w - x.w);
+      if (resid) store4(resid + t * d + c4 * 4, e);
+      sq += (double)(e.x * e.x + e.y * e.y) + (double)(e.z * e.z + e.w * e.w);
+      cs.x += e.x; cs.y += e.y; cs.z += e.z; cs.w += e.w;
+    }
+    if (colsum) {
+      atomicAdd(colsum + c4 * 4 + 0, cs.x);
+      atomicAdd(colsum + c4 * 4 + 1, cs.y);
+      atomicAdd(colsum + c4 * 4 + 2, cs.z);
+      atomicAdd(colsum + c4 * 4 + 3, cs.w);
+    }
+  }
+  const double tot = block_sum(sq, scratch);
+  if (sse && threadIdx.x == 0) atomicAdd(sse, tot);
+}
+
 static inline int grid_for(int64_t work, int block, int max_blocks) {
   int64_t g = (work + block - 1) / block;
   if (g > max_blocks) g = max_blocks;
@@ -726,6 +814,35 @@ extern "C" int freud_gather_rows(const void* src, const int32_t* rows, void* dst
 extern "C" int freud_index_map(const int32_t* table, const int32_t* in, int32_t* out, int64_t count, void* stream) {
   FREUD_REQUIRE(count > 0, "index_map needs count > 0");
   index_map_kernel<<<grid_for(count, 256, sm_count() * 8), 256, 0, STREAM>>>(table, in, out, count);
+  FREUD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int freud_shard_merge(const float* vals, const int32_t* idx, float* out_vals, int32_t* out_idx, int64_t N,
+                                 int64_t G, int64_t n_local, void* stream) {
+  FREUD_REQUIRE(N > 0 && G >= 1 && n_local > 0, "shard_merge: bad sizes");
+  shard_merge_kernel<<<(unsigned)((N + 7) / 8), 256, 0, STREAM>>>(vals, idx, out_vals, out_idx, N, (int)G, (int)n_local);
+  FREUD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int freud_shard_localize(const float* vals, const int32_t* gidx, float* lvals, int32_t* lidx, int64_t count,
+                                    int64_t lo, int64_t n_local, void* stream) {
+  FREUD_REQUIRE(count > 0, "shard_localize: empty");
+  shard_localize_kernel<<<grid_for(count, 256, sm_count() * 8), 256, 0, STREAM>>>(vals, gidx, lvals, lidx, count, (int)lo,
+                                                                                 (int)n_local);
+  FREUD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int freud_residual(const float* sae_out, const float* target, void* resid, int resid_is_bf16, double* sse,
+                              float* colsum, int64_t N, int64_t d, void* stream) {
+  FREUD_REQUIRE(N > 0 && d % 4 == 0, "residual needs d % 4 == 0");
+  dim3 grid((unsigned)((d / 4 + 255) / 256), (unsigned)(N < 2048 ? N : 2048));
+  if (resid_is_bf16)
+    residual_kernel<__nv_bfloat16><<<grid, 256, 0, STREAM>>>(sae_out, target, static_cast<__nv_bfloat16*>(resid), sse, colsum, N, (int)d);
+  else
+    residual_kernel<float><<<grid, 256, 0, STREAM>>>(sae_out, target, static_cast<float*>(resid), sse, colsum, N, (int)d);
   FREUD_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

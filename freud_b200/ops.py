@@ -145,6 +145,33 @@ def axpby(a, b, coef, out_dtype):
     return out
 
 
+# ------------------------------------------------------------------------------------------------ feature sharding
+def shard_merge(all_vals, all_idx, n_local: int):
+    """[G,N,32] all-gathered per-shard selections -> global (vals, dictionary indices) [N,32]."""
+    G, N, k = all_vals.shape
+    vals = torch.empty((N, k), dtype=torch.float32, device=all_vals.device)
+    idx = torch.empty((N, k), dtype=torch.int32, device=all_vals.device)
+    call("freud_shard_merge", _ptr(all_vals), _ptr(all_idx), _ptr(vals), _ptr(idx), N, G, n_local, _stream())
+    return vals, idx
+
+
+def shard_localize(vals, gidx, lo: int, n_local: int):
+    lvals, lidx = torch.empty_like(vals), torch.empty_like(gidx)
+    call("freud_shard_localize", _ptr(vals), _ptr(gidx), _ptr(lvals), _ptr(lidx), vals.numel(), lo, n_local, _stream())
+    return lvals, lidx
+
+
+def residual(sae_out, target, resid_dtype, want_colsum=True):
+    N, d = sae_out.shape
+    dev = sae_out.device
+    resid = torch.empty((N, d), dtype=resid_dtype, device=dev) if resid_dtype is not None else None
+    sse = torch.zeros(1, dtype=torch.float64, device=dev)
+    colsum = torch.zeros(d, dtype=torch.float32, device=dev) if want_colsum else None
+    call("freud_residual", _ptr(sae_out), _ptr(target), _ptr(resid), int(resid_dtype == torch.bfloat16), _ptr(sse),
+         _ptr(colsum), N, d, _stream())
+    return resid, sse, colsum
+
+
 # ------------------------------------------------------------------------------------------------ TopK backward
 def csc_build(top_idx: torch.Tensor, n: int):
     N, k = top_idx.shape

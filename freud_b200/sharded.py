@@ -1,0 +1,129 @@
+"""Feature-sharded TopK SAE training (d=1280, n=81920 over 8 GPUs).
+
+Rank r owns dictionary rows [r*n/G, (r+1)*n/G) of W_enc, b_enc and W_dec plus their Adam state; x and b_dec are
+replicated.  One step (equal to the single-GPU step of train_sae.py:421-453 on the same batch):
+
+  local fused encode (top-32 of the shard)          -- freud_topk_encode
+  all-gather the G candidate lists, global top-32   -- NCCL all_gather + freud_shard_merge
+  decode only the winners this rank owns            -- freud_shard_localize + freud_topk_decode (partial sums)
+  all-reduce the partial reconstructions [N,d]      -- NCCL all_reduce          (the one large exchange)
+  residual / SSE / losses                           -- freud_residual + freud_topk_loss_scalars
+  backward is rank-local (e is replicated): dacts, CSC of the owned winners, dW_dec / dW_enc / db_enc
+  db_dec needs one [d] all-reduce of -db_enc^T W_enc; the clip norm one scalar all-reduce; Adam is local.
+
+AuxK / multi-TopK are not offered in this mode yet (dead latents raise); the data-parallel mode has them.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from ._lib import BF16, FP32
+from .optim import FusedAdam
+from .trainer import build_scheduler
+
+_KEYS = ("encoder.weight", "encoder.bias", "W_dec", "b_dec")
+
+
+class FeatureShardedTopKTrainer:
+    def __init__(self, full_state: dict, k: int, *, lr, steps, clip_thresh=1.0, scheduler="linear",
+                 scheduler_params=None, precision="bf16", device=None, group=None):
+        """full_state: the reference state_dict (W_dec, b_dec, encoder.weight, encoder.bias) -- every rank slices
+        its own rows, so a checkpoint written by the single-GPU model loads unchanged."""
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        if k != ops.K_FUSED:
+            raise NotImplementedError("feature-sharded mode uses the fused k == 32 encoder")
+        self.group = group
+        self.G = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        n, d = full_state["encoder.weight"].shape
+        if n % self.G:
+            raise ValueError("dictionary size must divide evenly over the ranks")
+        self.n, self.d, self.k = n, d, k
+        self.n_local = n // self.G
+        self.lo = self.rank * self.n_local
+        dev = torch.device(device if device is not None else torch.cuda.current_device())
+        if dev.type != "cuda":
+            raise RuntimeError("feature-sharded training runs on CUDA only (no CPU fallback)")
+        sl = slice(self.lo, self.lo + self.n_local)
+        self.params = {
+            "encoder.weight": full_state["encoder.weight"][sl].detach().to(dev, torch.float32).contiguous(),
+            "encoder.bias": full_state["encoder.bias"][sl].detach().to(dev, torch.float32).contiguous(),
+            "W_dec": full_state["W_dec"][sl].detach().to(dev, torch.float32).contiguous(),
+            "b_dec": full_state["b_dec"].detach().to(dev, torch.float32).contiguous(),
+        }
+        self.plist = [torch.nn.Parameter(self.params[k_]) for k_ in _KEYS]
+        for p in self.plist:
+            p.grad = torch.zeros_like(p)
+        self.precision = {"bf16": BF16, "fp32": FP32}[precision]
+        self.clip_thresh = clip_thresh
+        self.optimizer = FusedAdam(self.plist, lr=lr, max_grad_norm=clip_thresh)
+        self.scheduler = build_scheduler(self.optimizer, scheduler, scheduler_params or {}, steps)
+        self.num_frames_since_fired = torch.zeros(self.n_local, device=dev, dtype=torch.long)
+        self.device = dev
+
+    def _allreduce(self, t):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def gathered_state(self) -> dict:
+        """Full (unsharded) state_dict on every rank, in the reference layout."""
+        out = {}
+        for key, p in zip(_KEYS, self.plist):
+            if key == "b_dec":
+                out[key] = p.data.clone()
+                continue
+            parts = [torch.empty_like(p.data) for _ in range(self.G)]
+            dist.all_gather(parts, p.data.contiguous(), group=self.group)
+            out[key] = torch.cat(parts, 0)
+        return out
+
+    def step(self, x: torch.Tensor):
+        if not x.is_cuda:
+            raise RuntimeError("activations must already be on the CUDA device")
+        x = x.float().contiguous()
+        B, T, d = x.shape
+        N, k, prec = B * T, self.k, self.precision
+        W_enc, b_enc, W_dec, b_dec = (p.data for p in self.plist)
+        x2 = x.view(N, d)
+        xc_hi, xc_lo, tv = ops.topk_prep_x(x, b_dec, prec)
+        we_hi, we_lo = ops.split_operand(W_enc, prec)
+        wd = ops.split_operand(W_dec, BF16)[0] if prec == BF16 else W_dec
+        lvals, lidx = ops.topk_encode(xc_hi, xc_lo, we_hi, we_lo, b_enc, prec)          # shard-local top-32
+        all_vals = torch.empty((self.G, N, k), dtype=torch.float32, device=x.device)
+        all_idx = torch.empty((self.G, N, k), dtype=torch.int32, device=x.device)
+        dist.all_gather_into_tensor(all_vals, lvals, group=self.group)
+        dist.all_gather_into_tensor(all_idx, lidx, group=self.group)
+        top_vals, top_gidx = ops.shard_merge(all_vals, all_idx, self.n_local)           # identical on every rank
+        own_vals, own_idx = ops.shard_localize(top_vals, top_gidx, self.lo, self.n_local)
+        bias = b_dec if self.rank == 0 else torch.zeros_like(b_dec)                     # b_dec enters the sum once
+        partial, _, _, _ = ops.topk_decode(own_vals, own_idx, wd, bias)
+        sae_out = self._allreduce(partial)                                              # [N,d] fp32
+        rdt = torch.bfloat16 if prec == BF16 else torch.float32
+        e, sse, colsum_e = ops.residual(sae_out, x2, rdt)
+        scal = ops.topk_loss_scalars(sse, tv, N * d)
+        # ---- backward (rank-local): loss = fvu
+        scales = scal[2:4]
+        dacts = ops.topk_dacts(e, own_idx, wd)
+        offsets, entries = ops.csc_build(own_idx, self.n_local)
+        g = {k_: p.grad for k_, p in zip(_KEYS, self.plist)}
+        xc = xc_hi if prec == BF16 else x2
+        ops.topk_sparse_grads(offsets, entries, own_vals, dacts, e, xc, b_dec, scales, g["W_dec"], g["encoder.weight"],
+                              g["encoder.bias"], k, False)
+        ops.topk_bdec_grad(colsum_e if self.rank == 0 else None, scales if self.rank == 0 else None,
+                           g["encoder.bias"], W_enc, g["b_dec"], False)
+        self._allreduce(g["b_dec"])                                                     # [d]
+        # ---- global-norm clip + Adam: b_dec's gradient is replicated, count it once
+        tl_local = ops.make_tensor_list([p.data for p in self.plist[:3]], [p.grad for p in self.plist[:3]])
+        sumsq = ops.grad_sumsq(tl_local, x.device)
+        if self.rank == 0:
+            tl_b = ops.make_tensor_list([self.plist[3].data], [self.plist[3].grad])
+            sumsq = sumsq + ops.grad_sumsq(tl_b, x.device)
+        self._allreduce(sumsq)
+        self.optimizer.step(grad_sumsq=sumsq)
+        self.scheduler.step()
+        ops.dead_latent_update(offsets, self.num_frames_since_fired, N)
+        return {"loss": scal[0], "fvu": scal[0], "grad_sumsq": sumsq, "top_idx": top_gidx, "top_acts": top_vals,
+                "sae_out": sae_out}

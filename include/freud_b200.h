@@ -95,6 +95,21 @@ int freud_topk_dacts(const void* g, int g_is_bf16, const int32_t* top_idx, const
 int freud_axpby(const float* a, const float* b, const float* coef, void* out, int out_is_bf16,
                 int64_t numel, void* stream);
 
+/* ------------------------------------------------------------------ feature-sharded mode
+ * Encoder / decoder rows are split across ranks; each rank runs freud_topk_encode on its shard.
+ *   freud_shard_merge   : vals/idx [G,N,32] (all-gathered per-shard top-32, shard-local indices, each list sorted
+ *                         value desc / index asc) -> global top-32 with dictionary indices idx + g*n_local
+ *   freud_shard_localize: keep the winners in [lo, lo+n_local): local index or -1, value or 0.  Entries with
+ *                         index -1 are skipped by freud_topk_decode / freud_topk_dacts / freud_csc_build.
+ *   freud_residual      : after the partial reconstructions are all-reduced: resid = sae_out - target, SSE and
+ *                         column sums (the tail of freud_topk_decode). */
+int freud_shard_merge(const float* vals, const int32_t* idx, float* out_vals, int32_t* out_idx, int64_t N,
+                      int64_t G, int64_t n_local, void* stream);
+int freud_shard_localize(const float* vals, const int32_t* gidx, float* lvals, int32_t* lidx, int64_t count,
+                         int64_t lo, int64_t n_local, void* stream);
+int freud_residual(const float* sae_out, const float* target, void* resid, int resid_is_bf16, double* sse,
+                   float* colsum, int64_t N, int64_t d, void* stream);
+
 /* ------------------------------------------------------------------ TopK SAE backward */
 
 /* Feature-major (CSC) index of the selected entries: offsets[f]..offsets[f+1] lists the flat positions
