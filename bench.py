@@ -35,6 +35,10 @@ WORKLOADS = {
                dead_feature_threshold=1e6, desc="TopK SAE d=768 n=24576 (32x) k=32, B=32x1500 tokens per GPU"),
     "c2": dict(d=384, n=6144, k=32, B=50, T=1500, lr=1e-4, warmup_steps=1000, auxk_alpha=1 / 32,
                dead_feature_threshold=1e6, desc="TopK SAE d=384 n=6144 (16x) k=32, B=50x1500 tokens"),
+    # feature-sharded (strong scaling): the same 24 000-token batch on every rank, dictionary rows split over ranks
+    "c4": dict(d=1280, n=81920, k=32, B=16, T=1500, lr=1e-4, warmup_steps=1000, auxk_alpha=0.0,
+               dead_feature_threshold=None, sharded=True,
+               desc="TopK SAE d=1280 n=81920 (64x) k=32, B=16x1500 tokens, dictionary sharded over the ranks"),
 }
 METRIC = "sae_train_activation_tokens_per_sec"
 
@@ -203,6 +207,19 @@ def build_trainer(w, precision, dp, device):
     from freud_b200.trainer import SAETrainer
 
     torch.manual_seed(0)
+    if w.get("sharded"):
+        from freud_b200.sharded import FeatureShardedTopKTrainer
+
+        # same init recipe as TopKAutoEncoder.__init__ (kaiming-uniform encoder, unit-norm decoder copy), built
+        # row-block by row-block so no rank ever holds more than it needs
+        enc = torch.nn.Linear(w["d"], w["n"])
+        W = enc.weight.data
+        state = {"encoder.weight": W, "encoder.bias": torch.zeros(w["n"]),
+                 "W_dec": W / (W.norm(dim=1, keepdim=True) + torch.finfo(torch.float32).eps),
+                 "b_dec": torch.zeros(w["d"])}
+        return FeatureShardedTopKTrainer(state, w["k"], lr=w["lr"], steps=100000, clip_thresh=1.0, scheduler="linear",
+                                         scheduler_params={"num_warmup_steps": w["warmup_steps"]},
+                                         precision=precision, device=device)
     cfg = TopKAutoEncoderConfig.from_dict({"n_dict_components": w["n"], "k": w["k"], "auxk_alpha": w["auxk_alpha"],
                                            "multi_topk": False, "normalize_decoder": True})
     model = TopKAutoEncoder(w["d"], cfg).to(device)
@@ -240,19 +257,26 @@ def main():
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     dp = None
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
-        from freud_b200.parallel import DataParallel
+    sharded = bool(w.get("sharded"))
+    if world > 1 or sharded:
+        if world == 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29533")
+            dist.init_process_group("nccl", rank=0, world_size=1, device_id=device)
+        else:
+            dist.init_process_group("nccl", device_id=device)
+        if not sharded:
+            from freud_b200.parallel import DataParallel
 
-        dp = DataParallel()
+            dp = DataParallel()
     # all work runs on an explicit non-blocking stream: the legacy default stream serialises with copy streams
     main_stream = torch.cuda.Stream(device)
     torch.cuda.set_stream(main_stream)
     tr = build_trainer(w, args.precision, dp, device)
     B, T, d = w["B"], w["T"], w["d"]
-    tokens_per_step = B * T * world
+    tokens_per_step = B * T * (1 if sharded else world)  # sharded: every rank sees the same batch (strong scaling)
     n_bufs = 3  # 3 x 147 MB (c3) of distinct inputs, each larger than the 126 MB L2
-    host = [synth_batch(B, T, d, 1000 + 17 * rank + i, pin=True) for i in range(n_bufs)]
+    host = [synth_batch(B, T, d, 1000 + (0 if sharded else 17 * rank) + i, pin=True) for i in range(n_bufs)]
     dev_x = [h.to(device) for h in host]
 
     def barrier():
@@ -341,7 +365,8 @@ def main():
     step_kernel_ms = sum(v[1] for v in prof.values())
     roofline = None
     if enc_calls:
-        flops = 2.0 * B * T * d * w["n"]  # 2*d*n per token (algorithmic, one bf16 pass)
+        # 2*d*n per token (algorithmic, one bf16 pass); a shard multiplies n/world features
+        flops = 2.0 * B * T * d * (w["n"] // world if sharded else w["n"])
         achieved = flops / (enc_ms / enc_calls * 1e-3) / 1e12
         roofline = {"kernel": "sm100_gemm_kernel<EPI_TOPK> (freud_topk_encode)", "bound": "tensor",
                     "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
@@ -356,11 +381,11 @@ def main():
                        "ms_per_step": ms_per_step, "kernels": shares}, f, indent=1)
 
     if rank != 0:
-        if world > 1:
+        if dist.is_initialized():
             dist.destroy_process_group()
         return
     cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not sharded:
         Bc = 1 if args.workload == "c3" else 2
         v, ms, cores = run_cpu_port(w, 3, 1, Bc)
         cpu_baseline = {"value": v, "unit": "tokens/s", "cores": cores, "kind": "port",
@@ -368,20 +393,21 @@ def main():
                                   f"{ms:.0f} ms/step (oracle/ CPU port of the reference step)"}
     line = {
         "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if sharded else "weak",
         "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
         "config": {"workload": f"{args.workload}: {w['desc']}", "global_batch_tokens": tokens_per_step,
-                   "parallelism": f"dp{world}", "optimizer": "adam+clip(1.0)+linear-warmup",
+                   "parallelism": (f"feature-sharded x{world}" if sharded else f"dp{world}"), "optimizer": "adam+clip(1.0)+linear-warmup",
                    "l2": f"{n_bufs} rotating input batches of {B * T * d * 4 / 1e6:.0f} MB (> 126 MB L2)"
                    if B * T * d * 4 > 126e6 else f"{n_bufs} rotating input batches ({B * T * d * 4 / 1e6:.0f} MB each, "
                    f"{n_bufs * B * T * d * 4 / 1e6:.0f} MB total > 126 MB L2)"},
         "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": B * T * d * 4 * world,
                 "d2h_bytes_per_step": 4 * world, "ms_per_step": e2e_ms / args.steps},
+
         "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
         "loss": last_loss, "kernel_shares": {k_: round(v["share"], 4) for k_, v in shares.items()},
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
+    if dist.is_initialized():
         dist.destroy_process_group()
 
 
