@@ -39,7 +39,8 @@ constexpr int kBM = 128;        // token rows per CTA (UMMA M)
 constexpr int kBKBytes = 128;   // one swizzle-128B row per k-block
 constexpr int kTopK = 32;       // fused selection width
 constexpr int kNewSlots = 32;   // candidate slots per token between compactions
-constexpr int kChunk = 16;      // accumulator columns per TMEM load / occupancy check
+constexpr int kChunk = 16;      // accumulator columns per TMEM load
+constexpr int kCheck = 8;       // columns between candidate-column occupancy checks
 constexpr int kSlotStride = 33 * 8;  // bytes between slots of one lane ([slot][33 lanes] x 8 B, conflict-free)
 
 enum { EPI_TOPK = 0, EPI_STORE = 1, EPI_NONE = 2 };
@@ -68,8 +69,9 @@ struct GemmSmem {
   static constexpr int kBufPerWarp = kNewSlots * kSlotStride;
   static constexpr int kBuf = EPI == EPI_TOPK ? kEpiWarps * kBufPerWarp : 0;
   static constexpr int kThr = 2 * kBM * 4;  // per-set published thresholds
+  static constexpr int kBiasS = 4 * BN * 4; // staged bias rows: [accumulator buffer][tile parity][BN]
   static constexpr int kBars = (2 * STAGES + 4) * 8 + 16;
-  static constexpr int kTotal = kRing + kBuf + kThr + kBars;
+  static constexpr int kTotal = kRing + kBuf + kThr + kBiasS + kBars;
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -163,7 +165,8 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   uint8_t* ring = smem;
   uint8_t* cand = smem + L::kRing;
   float* thr_s = reinterpret_cast<float*>(smem + L::kRing + L::kBuf);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kRing + L::kBuf + L::kThr);
+  float* bias_s = reinterpret_cast<float*>(smem + L::kRing + L::kBuf + L::kThr);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kRing + L::kBuf + L::kThr + L::kBiasS);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tfull_bar = bars + 2 * STAGES;
@@ -286,24 +289,32 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     const int row = m0 + stid;
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
 
-    // Write tile nt's bias row into accumulator buffer (nt & 1) and hand the buffer to the MMA issuer.
+    // Bias of tile nt: fetched into shared memory early (global-load latency off the critical path), written into
+    // accumulator buffer (nt & 1) with tcgen05.st once that buffer is drained, then handed to the MMA issuer.
+    auto fetch_bias = [&](int nt) {
+      if (nt < num_nt) {
+        float* bs = bias_s + ((nt & 1) * 2 + ((nt >> 1) & 1)) * BN;  // double-buffered per accumulator buffer
+        for (int c = stid; c < BN; c += 128) {
+          const int gc = nt * BN + c;
+          bs[c] = gc < p.N ? (p.bias ? __ldg(p.bias + gc) : 0.f) : -INFINITY;
+        }
+      }
+    };
     auto prestore_bias = [&](int nt) {
       if (nt < num_nt) {
+        // the four warps of the set wrote disjoint parts of the row: make them visible to each other
+        if (set == 0)
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        else
+          asm volatile("bar.sync 2, 128;" ::: "memory");
         const uint32_t t_addr = lane_taddr + (nt & 1) * BN;
-#pragma unroll 1
+        const uint32_t bs_addr = smem_u32(bias_s + ((nt & 1) * 2 + ((nt >> 1) & 1)) * BN);
+#pragma unroll 2
         for (int c0 = 0; c0 < BN; c0 += 32) {
           uint32_t bv[32];
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const int gc = nt * BN + c0 + j;
-            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (gc + 3 < p.N) {
-              if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gc));
-            } else {
-              float* pb = &b4.x;
-              for (int u = 0; u < 4; ++u)
-                pb[u] = gc + u < p.N ? (p.bias ? __ldg(p.bias + gc + u) : 0.f) : -INFINITY;
-            }
+            const float4 b4 = lds128(bs_addr + (c0 + j) * 4);
             bv[j] = __float_as_uint(b4.x);
             bv[j + 1] = __float_as_uint(b4.y);
             bv[j + 2] = __float_as_uint(b4.z);
@@ -321,7 +332,7 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     uint64_t surv[kTopK];
     float thresh = 0.f;
     const uint32_t my_base = smem_u32(cand) + ew * L::kBufPerWarp + lane * 8;
-    const uint32_t ptr_limit = my_base + (kNewSlots - kChunk) * kSlotStride;
+    const uint32_t ptr_limit = my_base + (kNewSlots - kCheck) * kSlotStride;
     uint32_t ptr = my_base;
     if constexpr (EPI == EPI_TOPK) {
 #pragma unroll
@@ -329,8 +340,11 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     }
     // initial bias for the first tile(s) this set will see
     if constexpr (SETS == 2) {
+      fetch_bias(set);
       prestore_bias(set);
     } else {
+      fetch_bias(0);
+      fetch_bias(1);
       prestore_bias(0);
       prestore_bias(1);
     }
@@ -340,6 +354,7 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         // any lower bound of the row's 32nd largest value is a valid filter: adopt the other set's if tighter
         thresh = fmaxf(thresh, thr_s[(set ^ 1) * kBM + stid]);
       }
+      fetch_bias(nt + 2);  // lands in shared memory while this tile is scanned
       mbar_wait(&tfull_bar[buf], (nt >> 1) & 1);
       tc_fence_after();
       const uint32_t t_addr = lane_taddr + buf * BN;
@@ -355,18 +370,22 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           if constexpr (EPI == EPI_TOPK) {
             const uint32_t nidx0 = ~static_cast<uint32_t>(nt * BN + cc);  // ~(col) == nidx0 - j
 #pragma unroll
-            for (int j = 0; j < kChunk; ++j) {
-              if (__uint_as_float(r[h][j]) > thresh) {  // thresh >= 0: this is also the ReLU
-                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(ptr), "r"(nidx0 - j), "r"(r[h][j]) : "memory");
-                ptr += kSlotStride;
+            for (int g = 0; g < kChunk; g += kCheck) {
+#pragma unroll
+              for (int j = g; j < g + kCheck; ++j) {
+                if (__uint_as_float(r[h][j]) > thresh) {  // thresh >= 0: this is also the ReLU
+                  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(ptr), "r"(nidx0 - j), "r"(r[h][j])
+                               : "memory");
+                  ptr += kSlotStride;
+                }
               }
-            }
-            if (__any_sync(0xffffffffu, ptr > ptr_limit)) {
-              // next chunk could overflow some lane's column: all lanes compact their own rows in lock-step
-              const float t = compact_rows(surv, my_base, ptr);
-              thresh = fmaxf(thresh, t);
-              ptr = my_base;
-              if constexpr (SETS == 2) thr_s[set * kBM + stid] = thresh;
+              if (__any_sync(0xffffffffu, ptr > ptr_limit)) {
+                // the next kCheck columns could overflow some lane's column: all lanes compact their own rows
+                const float t = compact_rows(surv, my_base, ptr);
+                thresh = fmaxf(thresh, t);
+                ptr = my_base;
+                if constexpr (SETS == 2) thr_s[set * kBM + stid] = thresh;
+              }
             }
           } else if constexpr (EPI == EPI_NONE) {
             if (__uint_as_float(r[h][0]) == 1.2345e38f) p.out[0] = 1.f;  // keep the loads alive
