@@ -390,7 +390,9 @@ template <> struct RowVec<float> {
   }
 };
 
-template <typename GT, typename XT>
+// WHICH: 0 = both gradients in one pass; 1 = dW_dec only (gathers g); 2 = dW_enc + db_enc only (gathers xc).
+// Two single-matrix passes keep the gathered working set (one [N,d] bf16 matrix) inside the 126 MB L2.
+template <typename GT, typename XT, int WHICH>
 __global__ void __launch_bounds__(256) sparse_grads_kernel(
     const int32_t* __restrict__ offsets, const int32_t* __restrict__ chunk_off, const int32_t* __restrict__ entries,
     const float* __restrict__ top_vals, const float* __restrict__ dacts, const GT* __restrict__ g,
@@ -456,29 +458,29 @@ __global__ void __launch_bounds__(256) sparse_grads_kernel(
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int64_t t = tok_s[i + u * groups];
-          RowVec<GT>::load(g + t * d + c, gv[u]);
-          RowVec<XT>::load(xc + t * d + c, xv[u]);
+          if (WHICH != 2) RowVec<GT>::load(g + t * d + c, gv[u]);
+          if (WHICH != 1) RowVec<XT>::load(xc + t * d + c, xv[u]);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const float a = a_s[i + u * groups], dp = dp_s[i + u * groups];
 #pragma unroll
           for (int e = 0; e < V; ++e) {
-            accd[e] = fmaf(a, gv[u][e], accd[e]);
-            acce[e] = fmaf(dp, xv[u][e] - bd[e], acce[e]);
+            if (WHICH != 2) accd[e] = fmaf(a, gv[u][e], accd[e]);
+            if (WHICH != 1) acce[e] = fmaf(dp, xv[u][e] - bd[e], acce[e]);
           }
         }
       }
       for (; i < cnt; i += groups) {
         const int64_t t = tok_s[i];
         float gv[V], xv[V];
-        RowVec<GT>::load(g + t * d + c, gv);
-        RowVec<XT>::load(xc + t * d + c, xv);
+        if (WHICH != 2) RowVec<GT>::load(g + t * d + c, gv);
+        if (WHICH != 1) RowVec<XT>::load(xc + t * d + c, xv);
         const float a = a_s[i], dp = dp_s[i];
 #pragma unroll
         for (int e = 0; e < V; ++e) {
-          accd[e] = fmaf(a, gv[e], accd[e]);
-          acce[e] = fmaf(dp, xv[e] - bd[e], acce[e]);
+          if (WHICH != 2) accd[e] = fmaf(a, gv[e], accd[e]);
+          if (WHICH != 1) acce[e] = fmaf(dp, xv[e] - bd[e], acce[e]);
         }
       }
     }
@@ -497,6 +499,7 @@ __global__ void __launch_bounds__(256) sparse_grads_kernel(
     const int span4 = (c_hi - c_lo) / 4;  // d % 4 == 0
     for (int q = threadIdx.x; q < 2 * span4; q += blockDim.x) {
       const int m = q / span4;
+      if ((WHICH == 1 && m == 1) || (WHICH == 2 && m == 0)) continue;
       const int cc = c_lo + (q - m * span4) * 4;
       float4 sum = make_float4(0, 0, 0, 0);
       for (int t = 0; t < groups; ++t) {
@@ -515,7 +518,7 @@ __global__ void __launch_bounds__(256) sparse_grads_kernel(
   dpsum = warp_sum(dpsum);
   if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = dpsum;
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && WHICH != 1) {
     float tot = 0.f;
     for (int w = 0; w < (blockDim.x >> 5); ++w) tot += wsum[w];
     if (multi) atomicAdd(db_enc + f, tot); else db_enc[f] += tot;
@@ -882,19 +885,34 @@ extern "C" int freud_topk_sparse_grads(const int32_t* offsets, const int32_t* en
   const int groups = tpr > 256 ? 1 : (256 / tpr > 0 ? 256 / tpr : 1);
   const size_t smem = static_cast<size_t>(groups) * 2 * d * sizeof(float);
   FREUD_REQUIRE(smem + 3 * kChunk * 4 + 64 <= 227 * 1024, "activation size too wide for sparse_grads");
+  // one pass per gradient matrix when the two gathered [N,d] matrices together would not stay in L2
+  const int64_t N_tok = n_entries / k;
+  const bool split = 2 * N_tok * d * (g_is_bf16 ? 2 : 4) > (96ll << 20);
+#define FREUD_SG_LAUNCH(GT, WHICH)                                                                                   \
+  do {                                                                                                               \
+    auto kern = sparse_grads_kernel<GT, GT, WHICH>;                                                                  \
+    if (smem > 32 * 1024)                                                                                            \
+      FREUD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+    kern<<<(unsigned)max_items, 256, smem, STREAM>>>(offsets, chunk_off, entries, top_vals, dacts,                   \
+                                                     static_cast<const GT*>(g), static_cast<const GT*>(xc), b_dec,   \
+                                                     scales, dW_dec, dW_enc, db_enc, (int)n, (int)d, (int)k);       \
+  } while (0)
   if (g_is_bf16) {
-    auto kern = sparse_grads_kernel<__nv_bfloat16, __nv_bfloat16>;
-    if (smem > 32 * 1024) FREUD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)max_items, 256, smem, STREAM>>>(
-        offsets, chunk_off, entries, top_vals, dacts, static_cast<const __nv_bfloat16*>(g),
-        static_cast<const __nv_bfloat16*>(xc), b_dec, scales, dW_dec, dW_enc, db_enc, (int)n, (int)d, (int)k);
+    if (split) {
+      FREUD_SG_LAUNCH(__nv_bfloat16, 1);
+      FREUD_SG_LAUNCH(__nv_bfloat16, 2);
+    } else {
+      FREUD_SG_LAUNCH(__nv_bfloat16, 0);
+    }
   } else {
-    auto kern = sparse_grads_kernel<float, float>;
-    if (smem > 32 * 1024) FREUD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)max_items, 256, smem, STREAM>>>(
-        offsets, chunk_off, entries, top_vals, dacts, static_cast<const float*>(g), static_cast<const float*>(xc),
-        b_dec, scales, dW_dec, dW_enc, db_enc, (int)n, (int)d, (int)k);
+    if (split) {
+      FREUD_SG_LAUNCH(float, 1);
+      FREUD_SG_LAUNCH(float, 2);
+    } else {
+      FREUD_SG_LAUNCH(float, 0);
+    }
   }
+#undef FREUD_SG_LAUNCH
   FREUD_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -74,7 +74,7 @@ class SAETrainer:
                 p.grad = torch.zeros_like(p)
             # load torch's lazily-initialised kernels for the dead-mask read-back now, not in the first step that
             # crosses the threshold (a one-off ~60 ms module load otherwise lands inside the training loop)
-            int((self.num_frames_since_fired > 0).sum())
+            int((self.num_frames_since_fired > (dead_feature_threshold or 0)).sum())
         self.last_state = None
 
     # ------------------------------------------------------------------------------------------ TopK
