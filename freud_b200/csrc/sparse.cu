@@ -330,9 +330,10 @@ __global__ void __launch_bounds__(256) csc_sort_kernel(const int32_t* __restrict
 //   dW_dec[f,:] += a_p * g[t_p,:]      dW_enc[f,:] += dpre_p * xc[t_p,:]      db_enc[f] += dpre_p
 // Single-chunk features store their rows; multi-chunk features accumulate with vector atomics into zeroed rows.
 constexpr int kChunk = 1024;
+constexpr int kShortList = 192;  // lists up to this length: one row-team per feature, no block-level machinery
 
 __global__ void __launch_bounds__(1024) chunk_scan_kernel(const int32_t* __restrict__ offsets,
-                                                          int32_t* __restrict__ chunk_off, int n) {
+                                                          int32_t* __restrict__ chunk_off, int n, int short_len) {
   __shared__ int32_t warp_tot[32];
   __shared__ int32_t carry_s;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -340,7 +341,11 @@ __global__ void __launch_bounds__(1024) chunk_scan_kernel(const int32_t* __restr
   __syncthreads();
   for (int base = 0; base < n; base += 1024) {
     const int i = base + threadIdx.x;
-    const int32_t v = i < n ? (offsets[i + 1] - offsets[i] + kChunk - 1) / kChunk : 0;
+    int32_t v = 0;
+    if (i < n) {
+      const int32_t len = offsets[i + 1] - offsets[i];
+      v = len > short_len ? (len + kChunk - 1) / kChunk : 0;  // short lists belong to the team kernel
+    }
     int32_t incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -389,6 +394,82 @@ template <> struct RowVec<float> {
     v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
   }
 };
+
+// Short lists (a wide dictionary has N*k/n entries per feature on average): every row-team of `tpr` threads owns ONE
+// feature and walks its list alone -- no shared memory, no block barrier, direct row stores.  Thread c of a team owns
+// one 16-byte column slice of the gathered g / xc rows; entry metadata is read redundantly (L1 broadcast).
+template <typename GT, typename XT>
+__global__ void __launch_bounds__(256) sparse_grads_team_kernel(
+    const int32_t* __restrict__ offsets, const int32_t* __restrict__ entries, const float* __restrict__ top_vals,
+    const float* __restrict__ dacts, const GT* __restrict__ g, const XT* __restrict__ xc,
+    const float* __restrict__ b_dec, const float* __restrict__ scales, float* __restrict__ dW_dec,
+    float* __restrict__ dW_enc, float* __restrict__ db_enc, int n, int d, int k, int tpr, int teams) {
+  constexpr int V = RowVec<GT>::kVec;
+  constexpr bool kRecenter = sizeof(XT) == 4;
+  const int team = threadIdx.x / tpr;
+  const int lane_c = threadIdx.x - team * tpr;
+  const int f = blockIdx.x * teams + team;
+  if (team >= teams || f >= n) return;
+  const int beg = offsets[f], len = offsets[f + 1] - beg;
+  if (len == 0 || len > kShortList) return;  // empty rows stay zero; long lists belong to the chunk kernel
+  const int c = lane_c * V;
+  const float s_dec = scales[0], s_enc = scales[1];
+  float accd[V], acce[V], bd[V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) {
+    accd[e] = 0.f;
+    acce[e] = 0.f;
+    bd[e] = kRecenter ? b_dec[c + e] : 0.f;
+  }
+  float dpsum = 0.f;
+  int i = 0;
+  for (; i + 4 <= len; i += 4) {
+    float gv[4][V], xv[4][V], a4[4], dp4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int p = __ldg(entries + beg + i + u);
+      const float a = __ldg(top_vals + p);
+      a4[u] = a * s_dec;
+      dp4[u] = a > 0.f ? __ldg(dacts + p) * s_enc : 0.f;
+      const int64_t t = p / k;
+      RowVec<GT>::load(g + t * d + c, gv[u]);
+      RowVec<XT>::load(xc + t * d + c, xv[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      dpsum += dp4[u];
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        accd[e] = fmaf(a4[u], gv[u][e], accd[e]);
+        acce[e] = fmaf(dp4[u], xv[u][e] - bd[e], acce[e]);
+      }
+    }
+  }
+  for (; i < len; ++i) {
+    const int p = __ldg(entries + beg + i);
+    const float a = __ldg(top_vals + p);
+    const float dp = a > 0.f ? __ldg(dacts + p) * s_enc : 0.f;
+    const int64_t t = p / k;
+    float gv[V], xv[V];
+    RowVec<GT>::load(g + t * d + c, gv);
+    RowVec<XT>::load(xc + t * d + c, xv);
+    dpsum += dp;
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      accd[e] = fmaf(a * s_dec, gv[e], accd[e]);
+      acce[e] = fmaf(dp, xv[e] - bd[e], acce[e]);
+    }
+  }
+  float* pd = dW_dec + static_cast<int64_t>(f) * d + c;
+  float* pe = dW_enc + static_cast<int64_t>(f) * d + c;
+#pragma unroll
+  for (int e = 0; e < V; e += 4) {  // rows were zeroed, or hold earlier decodes when accumulating
+    const float4 od = *reinterpret_cast<const float4*>(pd + e), oe = *reinterpret_cast<const float4*>(pe + e);
+    *reinterpret_cast<float4*>(pd + e) = make_float4(od.x + accd[e], od.y + accd[e + 1], od.z + accd[e + 2], od.w + accd[e + 3]);
+    *reinterpret_cast<float4*>(pe + e) = make_float4(oe.x + acce[e], oe.y + acce[e + 1], oe.z + acce[e + 2], oe.w + acce[e + 3]);
+  }
+  if (lane_c == 0) db_enc[f] += dpsum;
+}
 
 // WHICH: 0 = both gradients in one pass; 1 = dW_dec only (gathers g); 2 = dW_enc + db_enc only (gathers xc).
 // Two single-matrix passes keep the gathered working set (one [N,d] bf16 matrix) inside the 126 MB L2.
@@ -878,10 +959,30 @@ extern "C" int freud_topk_sparse_grads(const int32_t* offsets, const int32_t* en
     FREUD_CHECK_CUDA(cudaMemsetAsync(dW_enc, 0, n * d * sizeof(float), STREAM));
     FREUD_CHECK_CUDA(cudaMemsetAsync(db_enc, 0, n * sizeof(float), STREAM));
   }
-  chunk_scan_kernel<<<1, 1024, 0, STREAM>>>(offsets, chunk_off, (int)n);
-  const int64_t max_items = n_entries / kChunk + n;  // ceil(len/kChunk) summed over features, upper bound
   const int V = g_is_bf16 ? 8 : 4;
   const int tpr = (int)((d + V - 1) / V);
+  // short lists: one row-team per feature (rows that need more than 256 threads keep the chunk kernel only)
+  const int short_len = (tpr <= 256 && d % V == 0) ? kShortList : 0;
+  if (short_len > 0) {
+    const int teams = 256 / tpr;
+    const unsigned tgrid = (unsigned)((n + teams - 1) / teams);
+    const int tthreads = ((teams * tpr + 31) / 32) * 32;
+    if (g_is_bf16)
+      sparse_grads_team_kernel<__nv_bfloat16, __nv_bfloat16><<<tgrid, tthreads, 0, STREAM>>>(
+          offsets, entries, top_vals, dacts, static_cast<const __nv_bfloat16*>(g),
+          static_cast<const __nv_bfloat16*>(xc), b_dec, scales, dW_dec, dW_enc, db_enc, (int)n, (int)d, (int)k, tpr,
+          teams);
+    else
+      sparse_grads_team_kernel<float, float><<<tgrid, tthreads, 0, STREAM>>>(
+          offsets, entries, top_vals, dacts, static_cast<const float*>(g), static_cast<const float*>(xc), b_dec,
+          scales, dW_dec, dW_enc, db_enc, (int)n, (int)d, (int)k, tpr, teams);
+    FREUD_CHECK_CUDA(cudaGetLastError());
+  }
+  chunk_scan_kernel<<<1, 1024, 0, STREAM>>>(offsets, chunk_off, (int)n, short_len);
+  // chunk items only exist for lists longer than short_len: at most n_entries / short_len such features
+  int64_t max_items = n_entries / kChunk + n;
+  if (short_len > 0 && n_entries / kChunk + n_entries / short_len + 1 < max_items)
+    max_items = n_entries / kChunk + n_entries / short_len + 1;
   const int groups = tpr > 256 ? 1 : (256 / tpr > 0 ? 256 / tpr : 1);
   const size_t smem = static_cast<size_t>(groups) * 2 * d * sizeof(float);
   FREUD_REQUIRE(smem + 3 * kChunk * 4 + 64 <= 227 * 1024, "activation size too wide for sparse_grads");
