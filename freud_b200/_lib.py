@@ -57,6 +57,8 @@ SIGNATURES = {
     "freud_clip_grads": [C.POINTER(TensorList), _p, _f, _p, _p],
     "freud_adam_step": [C.POINTER(TensorList), _d, _d, _d, _d, _i64, _p, _f, _p],
     "freud_radam_step": [C.POINTER(TensorList), _d, _d, _d, _d, _d, _i64, _p, _f, _p],
+    "freud_feature_absmax": [_p, _p, _i, _i64, _p, _i64, _p],
+    "freud_col_absmax": [_p, _i64, _i64, _p, _p],
     "freud_search_dense": [_p, _i, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p],
     "freud_search_indexed": [_p, _p, _i, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p],
     "freud_search_topn": [_p, _p, _i64, _i, _i, _d, _i, _d, _i64, _p, _p, _p],
@@ -70,6 +72,7 @@ KERNELS_PER_CALL = {
     "freud_dead_latent_update": 1, "freud_rownorm_project": 1, "freud_remove_parallel_grad": 1,
     "freud_l1_colnorm": 1, "freud_l1_loss_reduce": 1, "freud_l1_dz": 1, "freud_l1_weight_grad": 1,
     "freud_grad_sumsq": 1, "freud_clip_grads": 1, "freud_adam_step": 1, "freud_radam_step": 1,
+    "freud_feature_absmax": 1, "freud_col_absmax": 1,
     "freud_search_dense": 1, "freud_search_indexed": 1, "freud_search_topn": 1,
 }
 

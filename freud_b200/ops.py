@@ -293,6 +293,23 @@ def radam_step(tl: TensorList, lr, beta1, beta2, eps, weight_decay, step: int, s
          _stream())
 
 
+# ------------------------------------------------------------------------------------------------ validation stats
+def feature_absmax(acts, idx, n: int):
+    out = torch.empty(n, dtype=torch.float32, device=acts.device)
+    if idx.dtype not in (torch.int64, torch.int32):
+        raise TypeError("indices must be int64 or int32")
+    call("freud_feature_absmax", _ptr(_f32(acts, "acts")), _ptr(idx), int(idx.dtype == torch.int64), acts.numel(),
+         _ptr(out), n, _stream())
+    return out
+
+
+def col_absmax(x):
+    rows, n = x.shape
+    out = torch.empty(n, dtype=torch.float32, device=x.device)
+    call("freud_col_absmax", _ptr(_f32(x, "x")), rows, n, _ptr(out), _stream())
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ search
 def search_dense(acts, n_frames, feature: int, want_trace: bool):
     n_files, T, F = acts.shape

@@ -200,6 +200,15 @@ int freud_adam_step(const freud_tensor_list* host_list, double lr, double beta1,
 int freud_radam_step(const freud_tensor_list* host_list, double lr, double beta1, double beta2, double eps,
                      double weight_decay, int64_t step, const double* sumsq, float max_norm, void* stream);
 
+/* ------------------------------------------------------------------ validation feature statistics
+ * (src/scripts/train_sae.py:70-118,175-178)
+ * freud_feature_absmax: out[f] = max |acts[i]| over entries with idx[i] == f, 0 if f never appears
+ *                       (topk_feature_extraction on one file's [T,k] encoding; idx int64 or int32).
+ * freud_col_absmax    : out[j] = max_r |x[r,j]|   (the L1 SAE's per-file latent abs-max). */
+int freud_feature_absmax(const float* acts, const void* idx, int idx_is_int64, int64_t count, float* out, int64_t n,
+                         void* stream);
+int freud_col_absmax(const float* x, int64_t rows, int64_t n, float* out, void* stream);
+
 /* ------------------------------------------------------------------ feature search (utils/activations.py) */
 
 /* Per-file statistics of one feature over dense activations acts[N_files, T, F] (fp32 or fp16):

@@ -239,3 +239,21 @@ def l1_backward(x, W, b, out: L1Out, recon_alpha, mode="fp32"):
     dz_q = _r(dz, mode)
     dW = _r(x2, mode).T @ dz_q + dxh_q.T @ _r(c, mode)
     return {"decoder.weight": dW, "encoder_bias": dz.sum(0)}
+
+
+# --------------------------------------------------------------------------- #
+# validation feature statistics
+# --------------------------------------------------------------------------- #
+def topk_feature_absmax(top_acts, top_indices, n):
+    """train_sae.py:70-118 topk_feature_extraction for one file: out[f] = max |act| over the (t, j) entries whose
+    index is f, 0 where the feature never appears (the reference builds a [T,k,n] mask for this)."""
+    out = torch.zeros(n, dtype=top_acts.dtype)
+    flat_i = top_indices.reshape(-1).long()
+    flat_a = top_acts.reshape(-1).abs()
+    out.scatter_reduce_(0, flat_i, flat_a, reduce="amax", include_self=True)
+    return out
+
+
+def l1_feature_absmax(latent):
+    """train_sae.py:175-178: per-file max over frames of |latent|."""
+    return latent.reshape(-1, latent.shape[-1]).abs().max(0).values

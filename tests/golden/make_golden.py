@@ -188,6 +188,26 @@ def misc_case():
     print("wrote topk_decoder_norm")
 
 
+def feature_stats_case():
+    """topk_feature_extraction (train_sae.py:70-118) and the L1 per-file abs-max (:175-178) on one file's encoding."""
+    from collections import namedtuple
+
+    from src.scripts.train_sae import topk_feature_extraction
+
+    g = torch.Generator().manual_seed(11)
+    T, k, n = 50, 8, 96
+    acts = torch.randn(1, T, k, generator=g)
+    idx = torch.stack([torch.randperm(n, generator=g)[:k] for _ in range(T)]).unsqueeze(0)
+    Enc = namedtuple("Enc", "top_acts top_indices")
+    Out = namedtuple("Out", "encoded")
+    res = topk_feature_extraction(Out(Enc(acts, idx)), n, 1, "cpu")
+    latent = torch.randn(1, T, n, generator=g)
+    l1 = torch.max(torch.abs(latent).squeeze(), dim=0).values
+    np.savez_compressed(os.path.join(HERE, "feature_stats.npz"), acts=acts.numpy(), idx=idx.numpy(), topk_max=res.numpy(),
+                        latent=latent.numpy(), l1_max=l1.numpy())
+    print("wrote feature_stats")
+
+
 def search_case():
     """top_activations (utils/activations.py:61-132) through the reference's own
     MemoryMappedActivationDataLoader on a dense and an indexed on-disk set."""
@@ -250,4 +270,5 @@ if __name__ == "__main__":
     l1_case("l1_fp32_wd", 4, 6, 32, 40, recon_alpha=1.0, autocast=False, steps=7, weight_decay=0.01)
     l1_case("l1_bf16", 4, 6, 32, 40, recon_alpha=1e4, autocast=True, steps=2)
     misc_case()
+    feature_stats_case()
     search_case()

@@ -142,3 +142,13 @@ def test_search_rankings_exact():
         assert np.array_equal(np.array(mpf, dtype=np.float64), z[f"q{q}.max_per_file"]), query
         if pq:
             assert np.array_equal(pq[0][1], z[f"q{q}.trace0"])
+
+
+def test_validation_feature_statistics():
+    """topk_feature_extraction / L1 abs-max (train_sae.py:70-118,175-178), exact."""
+    from tests.util import GOLDEN
+
+    z = np.load(f"{GOLDEN}/feature_stats.npz")
+    got = osae.topk_feature_absmax(torch.from_numpy(z["acts"]), torch.from_numpy(z["idx"]), 96)
+    assert np.array_equal(got.numpy(), z["topk_max"])
+    assert np.array_equal(osae.l1_feature_absmax(torch.from_numpy(z["latent"])).numpy(), z["l1_max"])
