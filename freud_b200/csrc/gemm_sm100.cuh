@@ -373,11 +373,20 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             for (int g = 0; g < kChunk; g += kCheck) {
 #pragma unroll
               for (int j = g; j < g + kCheck; ++j) {
-                if (__uint_as_float(r[h][j]) > thresh) {  // thresh >= 0: this is also the ReLU
-                  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(ptr), "r"(nidx0 - j), "r"(r[h][j])
-                               : "memory");
-                  ptr += kSlotStride;
-                }
+                // predicated store + UNpredicated pointer bump (selp/add into a fresh register): an in-place
+                // predicated add would have to wait for the store to read its address register (WAR on the LSU)
+                uint32_t next;
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t.reg .b32 inc;\n\t"
+                    "setp.gt.f32 p, %2, %3;\n\t"
+                    "@p st.shared.v2.b32 [%1], {%4, %5};\n\t"
+                    "selp.b32 inc, %6, 0, p;\n\t"
+                    "add.u32 %0, %1, inc;\n\t}"
+                    : "=r"(next)
+                    : "r"(ptr), "f"(__uint_as_float(r[h][j])), "f"(thresh), "r"(nidx0 - j), "r"(r[h][j]),
+                      "n"(kSlotStride)
+                    : "memory");
+                ptr = next;
               }
               if (__any_sync(0xffffffffu, ptr > ptr_limit)) {
                 // the next kCheck columns could overflow some lane's column: all lanes compact their own rows

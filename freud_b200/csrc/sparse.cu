@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ t
       const int jn = min(32, k - j0);
       const float my_a = lane < jn ? __ldg(top_vals + t * k + j0 + lane) : 0.f;
       const int my_i = lane < jn ? __ldg(top_idx + t * k + j0 + lane) : 0;
-#pragma unroll 4
+#pragma unroll 8
       for (int j = 0; j < jn; ++j) {
         const float a = __shfl_sync(0xffffffffu, my_a, j);
         const int64_t f = __shfl_sync(0xffffffffu, my_i, j);

@@ -121,7 +121,7 @@ class DeviceActivationStore:
 
     def __init__(self, dataset: MemoryMappedActivationsDataset, device="cuda",
                  num_samples: Optional[dict] = None, frames_fn: Optional[Callable[[str], int]] = None,
-                 chunk_files: int = 256):
+                 chunk_files: int = 256, feature_major: Optional[bool] = None):
         self.filenames = list(dataset.metadata["filenames"])
         self.activation_type = dataset.activation_type
         T, F = dataset.metadata["tensor_shape"]
@@ -145,6 +145,13 @@ class DeviceActivationStore:
         else:
             acts = upload(dataset.mmap)
             self.acts = acts if acts.dtype in (torch.float32, torch.float16) else acts.float()
+            # Feature-major copy [F, N_files, T]: a single-feature query then streams N_files*T contiguous values
+            # (60 MB at C5) instead of one 32-byte sector per frame of the row-major store.
+            # Built once at load time (a layout change, like the upload); kept when both copies fit comfortably.
+            if feature_major is None:
+                free, _ = torch.cuda.mem_get_info(dev)
+                feature_major = self.acts.numel() * self.acts.element_size() * 1.2 < free
+            self.acts_fm = self.acts.permute(2, 0, 1).contiguous() if feature_major else None
         if frames_fn is None:
             if num_samples is not None:
                 frames_fn = lambda f: n_frames_from_samples(num_samples[f])  # noqa: E731

@@ -38,7 +38,11 @@ def top_activations(dataloader, feature_idx: int, n_files: int, max_val: Optiona
                     absolute_magnitude: bool, return_max_per_file: bool):
     store = get_store(dataloader)
     if store.activation_type == "tensor":
-        vmax, amax, vabs, _ = ops.search_dense(store.acts, store.n_frames, int(feature_idx), False)
+        if getattr(store, "acts_fm", None) is not None:
+            # contiguous [N_files, T] slab of this feature: the same kernel with a unit column stride
+            vmax, amax, vabs, _ = ops.search_dense(store.acts_fm[int(feature_idx)].unsqueeze(-1), store.n_frames, 0, False)
+        else:
+            vmax, amax, vabs, _ = ops.search_dense(store.acts, store.n_frames, int(feature_idx), False)
     else:
         vmax, amax, vabs, _ = ops.search_indexed(store.vals, store.idx, store.n_frames, int(feature_idx), False)
     files, count = ops.search_topn(vmax, vabs, bool(absolute_magnitude), min_val, max_val, int(n_files))
