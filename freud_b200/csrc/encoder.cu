@@ -32,7 +32,13 @@ static int launch_gemm(const void* a_hi, const void* a_lo, const void* b_hi, con
   int grid = (p.M + kBM - 1) / kBM;
   grid = (grid + CL - 1) / CL * CL;  // whole clusters; surplus CTAs run the protocol on out-of-range rows
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid);
+  int nsplit = 1;
+  if (p.kb_per_split > 0) {
+    const int kbe = TF32 ? 32 : 64;
+    const int total_kb = (p.K + kbe - 1) / kbe;
+    nsplit = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
+  }
+  cfg.gridDim = dim3(grid, nsplit);
   cfg.blockDim = dim3(L::kThreads);
   cfg.dynamicSmemBytes = L::kTotal;
   cfg.stream = stream;
@@ -114,4 +120,25 @@ extern "C" int freud_gemm_nt(const void* a_hi, const void* a_lo, const void* b_h
     return launch_gemm<256, 4, EPI_STORE, true, 2, 1>(a_hi, a_lo, b_hi, b_lo, p, 3, s);
   }
   FREUD_REQUIRE(false, "unknown precision");
+}
+
+// Split-K variant for "weight-gradient shaped" products (few output rows, very long K): `splits` partial results are
+// written to workspace [splits, M, N] and summed into out by freud_sum_splits.
+extern "C" int freud_gemm_nt_splitk(const void* a_hi, const void* b_hi, float* workspace, int64_t M, int64_t N, int64_t K,
+                                    int64_t splits, void* stream) {
+  FREUD_REQUIRE(M > 0 && N > 0 && K > 0 && splits >= 1, "empty split-K GEMM");
+  FREUD_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "sizes exceed int32");
+  FREUD_REQUIRE(K % 8 == 0, "K must be a multiple of 8 for bf16 operands");
+  GemmParams p{};
+  p.M = static_cast<int>(M);
+  p.N = static_cast<int>(N);
+  p.K = static_cast<int>(K);
+  p.out = workspace;
+  p.ldo = N;
+  const int total_kb = static_cast<int>((K + 63) / 64);
+  p.kb_per_split = static_cast<int>((total_kb + splits - 1) / splits);
+  FREUD_REQUIRE((total_kb + p.kb_per_split - 1) / p.kb_per_split == splits,
+                "splits must equal ceil(k_blocks / ceil(k_blocks / splits)) so that no partial is left unwritten");
+  p.split_stride = M * N;
+  return launch_gemm<256, 4, EPI_STORE, false, 2, 1>(a_hi, nullptr, b_hi, nullptr, p, 1, static_cast<cudaStream_t>(stream));
 }

@@ -56,6 +56,10 @@ struct GemmParams {
   // EPI_STORE
   float* out;           // [M, ldo]
   int64_t ldo;
+  // split-K (EPI_STORE): blockIdx.y = split, each handling kb_per_split k-blocks and writing its own partial
+  // [M, ldo] at out + split * split_stride (bias only in split 0); 0 = no split
+  int kb_per_split;
+  int64_t split_stride;
 };
 
 template <int BN, int STAGES, int EPI, int SETS>
@@ -177,7 +181,10 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   const int lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * kBM;
   const int num_nt = (p.N + BN - 1) / BN;
-  const int num_kb = (p.K + kBKe - 1) / kBKe;
+  const int total_kb = (p.K + kBKe - 1) / kBKe;
+  const int split = p.kb_per_split > 0 ? static_cast<int>(blockIdx.y) : 0;
+  const int kb0 = p.kb_per_split > 0 ? split * p.kb_per_split : 0;
+  const int num_kb = p.kb_per_split > 0 ? max(0, min(total_kb - kb0, p.kb_per_split)) : total_kb;
   const int num_vk = num_kb * p.passes;
 
   if (warp_idx == 0 && lane == 0) {
@@ -226,13 +233,13 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           uint8_t* sa = ring + stage * L::kStageBytes;
           uint8_t* sb = sa + L::kABytes;
           mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
-          tma_load_2d(sa, ma, &full_bar[stage], kb * kBKe, m0, kEvictNormal);
+          tma_load_2d(sa, ma, &full_bar[stage], (kb0 + kb) * kBKe, m0, kEvictNormal);
           if constexpr (CL == 1) {
-            tma_load_2d(sb, mb, &full_bar[stage], kb * kBKe, nt * BN, kEvictLast);
+            tma_load_2d(sb, mb, &full_bar[stage], (kb0 + kb) * kBKe, nt * BN, kEvictLast);
           } else {
             // every CTA of the cluster walks the same weight tiles: fetch 1/CL of the tile, multicast it to all
             constexpr int kSlice = BN / CL;
-            tma_load_2d_mc(sb + cta_rank * kSlice * kBKBytes, mb, &full_bar[stage], kb * kBKe,
+            tma_load_2d_mc(sb + cta_rank * kSlice * kBKBytes, mb, &full_bar[stage], (kb0 + kb) * kBKe,
                            nt * BN + static_cast<int>(cta_rank) * kSlice, kMcMask, kEvictLast);
           }
           if (++stage == STAGES) {
@@ -296,7 +303,7 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         float* bs = bias_s + ((nt & 1) * 2 + ((nt >> 1) & 1)) * BN;  // double-buffered per accumulator buffer
         for (int c = stid; c < BN; c += 128) {
           const int gc = nt * BN + c;
-          bs[c] = gc < p.N ? (p.bias ? __ldg(p.bias + gc) : 0.f) : -INFINITY;
+          bs[c] = gc < p.N ? ((p.bias && split == 0) ? __ldg(p.bias + gc) : 0.f) : -INFINITY;
         }
       }
     };
@@ -400,7 +407,7 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             if (__uint_as_float(r[h][0]) == 1.2345e38f) p.out[0] = 1.f;  // keep the loads alive
           } else {
             if (row < p.M) {
-              float* orow = p.out + static_cast<int64_t>(row) * p.ldo + nt * BN + cc;
+              float* orow = p.out + split * p.split_stride + static_cast<int64_t>(row) * p.ldo + nt * BN + cc;
               const bool full_chunk = (nt * BN + cc + kChunk <= p.N) && ((p.ldo & 3) == 0);
               if (full_chunk) {
 #pragma unroll

@@ -4,6 +4,7 @@
 // winners in index order (ties at the threshold resolved towards the lower index), then the k winners are
 // sorted (value desc, index asc) in shared memory.  Streams the row from L2/HBM; no tensor cores.
 #include "device_utils.cuh"
+#include <cuda_bf16.h>
 #include "host_common.h"
 #include "../../include/freud_b200.h"
 
@@ -145,6 +146,129 @@ __global__ void __launch_bounds__(kSelThreads) row_topk_kernel(const float* __re
   }
 }
 
+// Same exact selection, emitted as a DENSE masked row: out[row, j] = x[j] if j is among the row's top-k (ties at the
+// k-th value resolved towards the lower index) else 0, written as bf16 with row pitch `ld` (columns [n, ld) zeroed).
+// Used by the AuxK branch on the compacted dead-latent subset, where the selection feeds dense GEMMs.
+__global__ void __launch_bounds__(kSelThreads) row_topk_mask_kernel(const float* __restrict__ latents,
+                                                                    __nv_bfloat16* __restrict__ out, int n, int k,
+                                                                    int ld) {
+  __shared__ int hist[256];
+  __shared__ uint32_t s_prefix;
+  __shared__ int s_remaining;
+  __shared__ int s_eq_base;
+  __shared__ int warp_eq[kSelThreads / 32];
+  const int64_t row = blockIdx.x;
+  const float* __restrict__ x = latents + row * n;
+  __nv_bfloat16* __restrict__ o = out + row * ld;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid == 0) {
+    s_prefix = 0;
+    s_remaining = k;
+    s_eq_base = 0;
+  }
+  __syncthreads();
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    const uint32_t prefix = s_prefix;
+    const uint32_t hi_mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+    for (int i = tid; i < 256; i += kSelThreads) hist[i] = 0;
+    __syncthreads();
+    for (int j = tid; j < n; j += kSelThreads) {
+      const uint32_t key = float_key(x[j]);
+      if ((key & hi_mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xff], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int rem = s_remaining;
+      int digit = 255;
+      for (; digit > 0; --digit) {
+        if (hist[digit] >= rem) break;
+        rem -= hist[digit];
+      }
+      s_prefix = prefix | (static_cast<uint32_t>(digit) << shift);
+      s_remaining = rem;
+    }
+    __syncthreads();
+  }
+  const uint32_t kth = s_prefix;
+  const int need_eq = s_remaining;
+  for (int base = 0; base < ld; base += kSelThreads) {
+    const int j = base + tid;
+    float v = 0.f;
+    bool gt = false, eq = false;
+    if (j < n) {
+      v = x[j];
+      const uint32_t key = float_key(v);
+      gt = key > kth;
+      eq = key == kth;
+    }
+    const uint32_t me = __ballot_sync(0xffffffffu, eq);
+    if (lane == 0) warp_eq[w] = __popc(me);
+    __syncthreads();
+    int oe = s_eq_base;
+    for (int ww = 0; ww < w; ++ww) oe += warp_eq[ww];
+    const bool take = gt || (eq && oe + __popc(me & ((1u << lane) - 1u)) < need_eq);
+    if (j < ld) o[j] = __float2bfloat16_rn(take ? v : 0.f);
+    __syncthreads();
+    if (tid == 0) {
+      int te = 0;
+      for (int ww = 0; ww < kSelThreads / 32; ++ww) te += warp_eq[ww];
+      s_eq_base += te;
+    }
+    __syncthreads();
+  }
+}
+
+// out[c, r] = in[r, c] for a bf16 matrix in [rows, ld_in] -> [cols, ld_out]; columns [rows, ld_out) of out zeroed.
+__global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in,
+                                                             __nv_bfloat16* __restrict__ out, int64_t rows, int64_t cols,
+                                                             int64_t ld_in, int64_t ld_out) {
+  __shared__ __nv_bfloat16 tile[32][34];
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * 32, c0 = static_cast<int64_t>(blockIdx.x) * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < rows && c < cols) ? in[r * ld_in + c] : __float2bfloat16_rn(0.f);
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t c = c0 + i, r = r0 + tx;
+    if (c < cols && r < ld_out) out[c * ld_out + r] = tile[tx][i];
+  }
+}
+
+// dpre[r, j] = (act[r, j] > 0) ? g[r, j] : 0 (bf16, pitch ld) with column sums into colsum[j] (fp32, caller zeroes):
+// the ReLU / selection mask of the AuxK branch applied to the dense activation gradient g [rows, n] fp32.
+__global__ void __launch_bounds__(256) mask_grad_kernel(const float* __restrict__ g, const __nv_bfloat16* __restrict__ act,
+                                                        __nv_bfloat16* __restrict__ dpre, float* __restrict__ colsum,
+                                                        int64_t rows, int n, int ld, int slab) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= ld) return;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * slab, r1 = min(rows, r0 + slab);
+  float acc = 0.f;
+  for (int64_t r = r0; r < r1; ++r) {
+    float v = 0.f;
+    if (j < n && __bfloat162float(act[r * ld + j]) > 0.f) v = g[r * n + j];
+    const __nv_bfloat16 q = __float2bfloat16_rn(v);
+    dpre[r * ld + j] = q;
+    acc += __bfloat162float(q);
+  }
+  if (j < n) atomicAdd(colsum + j, acc);
+}
+
+// dst[rows_idx[r], :] += src[r, :]   (row scatter-add of the dead-subset gradients into the full matrices)
+__global__ void __launch_bounds__(256) scatter_add_rows_kernel(const float* __restrict__ src,
+                                                               const int32_t* __restrict__ rows_idx,
+                                                               float* __restrict__ dst, int64_t n_rows, int row_elems) {
+  const int64_t total = n_rows * row_elems;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / row_elems;
+    const int c = static_cast<int>(i - r * row_elems);
+    dst[static_cast<int64_t>(rows_idx[r]) * row_elems + c] += src[i];  // rows_idx entries are distinct
+  }
+}
+
 }  // namespace freud
 
 using namespace freud;
@@ -156,6 +280,49 @@ extern "C" int freud_row_topk(const float* latents, const uint8_t* col_mask, flo
   FREUD_REQUIRE(n < (1ll << 31) && rows < (1ll << 31), "row_topk sizes exceed int32");
   row_topk_kernel<<<(unsigned)rows, kSelThreads, 0, static_cast<cudaStream_t>(stream)>>>(latents, col_mask, vals, idx,
                                                                                        (int)n, (int)k);
+  FREUD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int freud_row_topk_mask(const float* latents, void* out_bf16, int64_t rows, int64_t n, int64_t k, int64_t ld,
+                                   void* stream) {
+  FREUD_REQUIRE(rows > 0 && n > 0 && k > 0 && k <= n && ld >= n, "row_topk_mask needs 0 < k <= n <= ld");
+  row_topk_mask_kernel<<<(unsigned)rows, kSelThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      latents, static_cast<__nv_bfloat16*>(out_bf16), (int)n, (int)k, (int)ld);
+  FREUD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int freud_transpose_bf16(const void* in, void* out, int64_t rows, int64_t cols, int64_t ld_in,
+                                    int64_t ld_out, void* stream) {
+  FREUD_REQUIRE(rows > 0 && cols > 0 && ld_in >= cols && ld_out >= rows, "transpose: bad sizes");
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((ld_out + 31) / 32));
+  transpose_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), rows, cols, ld_in, ld_out);
+  FREUD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int freud_mask_grad(const float* g, const void* act_bf16, void* dpre_bf16, float* colsum, int64_t rows,
+                               int64_t n, int64_t ld, void* stream) {
+  FREUD_REQUIRE(rows > 0 && n > 0 && ld >= n, "mask_grad: bad sizes");
+  const int slab = 256;
+  dim3 grid((unsigned)((ld + 255) / 256), (unsigned)((rows + slab - 1) / slab));
+  mask_grad_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      g, static_cast<const __nv_bfloat16*>(act_bf16), static_cast<__nv_bfloat16*>(dpre_bf16), colsum, rows, (int)n,
+      (int)ld, slab);
+  FREUD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int freud_scatter_add_rows(const float* src, const int32_t* rows_idx, float* dst, int64_t n_rows,
+                                      int64_t row_elems, void* stream) {
+  FREUD_REQUIRE(n_rows > 0 && row_elems > 0, "scatter_add_rows: bad sizes");
+  int64_t grid = (n_rows * row_elems + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
+  if (grid > cap) grid = cap;
+  scatter_add_rows_kernel<<<(unsigned)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, rows_idx, dst, n_rows,
+                                                                                        (int)row_elems);
   FREUD_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -769,6 +769,20 @@ __global__ void __launch_bounds__(256) residual_kernel(const float* __restrict__
   if (sse && threadIdx.x == 0) atomicAdd(sse, tot);
 }
 
+// out[i] = sum_s parts[s, i]  (split-K partial sums)
+__global__ void __launch_bounds__(256) sum_splits_kernel(const float* __restrict__ parts, float* __restrict__ out,
+                                                         int splits, int64_t n4) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float4 acc = make_float4(0, 0, 0, 0);
+    for (int s = 0; s < splits; ++s) {
+      const float4 v = load4(parts + (static_cast<int64_t>(s) * n4 + i) * 4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    store4(out + i * 4, acc);
+  }
+}
+
 static inline int grid_for(int64_t work, int block, int max_blocks) {
   int64_t g = (work + block - 1) / block;
   if (g > max_blocks) g = max_blocks;
@@ -927,6 +941,13 @@ extern "C" int freud_residual(const float* sae_out, const float* target, void* r
     residual_kernel<__nv_bfloat16><<<grid, 256, 0, STREAM>>>(sae_out, target, static_cast<__nv_bfloat16*>(resid), sse, colsum, N, (int)d);
   else
     residual_kernel<float><<<grid, 256, 0, STREAM>>>(sae_out, target, static_cast<float*>(resid), sse, colsum, N, (int)d);
+  FREUD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int freud_sum_splits(const float* parts, float* out, int64_t splits, int64_t numel, void* stream) {
+  FREUD_REQUIRE(numel > 0 && numel % 4 == 0 && splits >= 1, "sum_splits needs numel % 4 == 0");
+  sum_splits_kernel<<<grid_for(numel / 4, 256, sm_count() * 8), 256, 0, STREAM>>>(parts, out, (int)splits, numel / 4);
   FREUD_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -113,6 +113,52 @@ def index_map(table: torch.Tensor, idx: torch.Tensor):
     return out
 
 
+def row_topk_mask(latents: torch.Tensor, k: int, ld: int):
+    """Dense bf16 [rows, ld] with each row's exact top-k kept and everything else zero."""
+    rows, n = latents.shape
+    out = torch.empty((rows, ld), dtype=torch.bfloat16, device=latents.device)
+    call("freud_row_topk_mask", _ptr(_f32(latents, "latents")), _ptr(out), rows, n, k, ld, _stream())
+    return out
+
+
+def transpose_bf16(x: torch.Tensor, cols: int, ld_out: int):
+    """x [rows, ld_in] bf16 (first `cols` columns valid) -> [cols, ld_out] with zero padding."""
+    rows, ld_in = x.shape
+    out = torch.empty((cols, ld_out), dtype=torch.bfloat16, device=x.device)
+    call("freud_transpose_bf16", _ptr(x), _ptr(out), rows, cols, ld_in, ld_out, _stream())
+    return out
+
+
+def mask_grad(g: torch.Tensor, act: torch.Tensor):
+    """dpre = (act > 0) ? g : 0 as bf16 [rows, ld] + fp32 column sums [n]; g fp32 [rows, n], act bf16 [rows, ld]."""
+    rows, n = g.shape
+    ld = act.shape[1]
+    dpre = torch.empty((rows, ld), dtype=torch.bfloat16, device=g.device)
+    colsum = torch.zeros(n, dtype=torch.float32, device=g.device)
+    call("freud_mask_grad", _ptr(g), _ptr(act), _ptr(dpre), _ptr(colsum), rows, n, ld, _stream())
+    return dpre, colsum
+
+
+def scatter_add_rows(src: torch.Tensor, rows_idx: torch.Tensor, dst: torch.Tensor):
+    row_elems = 1 if src.dim() == 1 else src.shape[1]
+    call("freud_scatter_add_rows", _ptr(_f32(src, "src")), _ptr(rows_idx), _ptr(_f32(dst, "dst")), rows_idx.numel(),
+         row_elems, _stream())
+
+
+def gemm_nt_splitk(a: torch.Tensor, b: torch.Tensor, splits: int):
+    """A[M,K] @ B[N,K]^T (bf16, K long) via split-K partials on the tensor cores, summed in fp32."""
+    M, K = a.shape
+    Nn = b.shape[0]
+    total_kb = (K + 63) // 64
+    per = (total_kb + splits - 1) // splits
+    splits = (total_kb + per - 1) // per  # the split count the kernel will actually run (no empty partials)
+    ws = torch.empty((splits, M, Nn), dtype=torch.float32, device=a.device)
+    out = torch.empty((M, Nn), dtype=torch.float32, device=a.device)
+    call("freud_gemm_nt_splitk", _ptr(a), _ptr(b), _ptr(ws), M, Nn, K, splits, _stream())
+    call("freud_sum_splits", _ptr(ws), _ptr(out), splits, M * Nn, _stream())
+    return out
+
+
 def topk_decode(top_vals, top_idx, W_dec, b_dec, target=None, *, resid_dtype=None, want_sse=False,
                 want_colsum=False):
     """sae_out = sum_j a_j W_dec[i_j] + b_dec; optional residual / sse / column sums against `target`."""

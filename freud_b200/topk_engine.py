@@ -35,7 +35,8 @@ class TopKState:
     idx: torch.Tensor = None
     e: torch.Tensor = None      # residual sae_out - x (bf16 in the bf16 fast path, else fp32)
     colsum_e: torch.Tensor = None
-    aux: Optional[tuple] = None     # (a_vals, a_idx, resid_aux fp32, scale)
+    aux: Optional[tuple] = None     # (a_vals, a_idx, resid_aux fp32, scale)   row-sparse AuxK
+    aux_dense: Optional[tuple] = None  # (dead_idx, S, Sp, A bf16 [N,Sp], W_dec[dead] bf16, resid_aux fp32, scale)
     multi: Optional[tuple] = None   # (m_vals, m_idx, resid_m fp32, colsum_m)
     auxk_alpha: float = 0.0
     offsets: Optional[torch.Tensor] = None  # CSC offsets of the returned encoding (did_fire bookkeeping)
@@ -111,6 +112,23 @@ def topk_forward(x, W_enc, b_enc, W_dec, b_dec, k, *, precision, dead_mask=None,
         k_aux = min(k_aux, num_dead)
         if pre is not None:
             a_vals, a_idx = ops.row_topk(pre, k_aux, col_mask=dead_mask)
+        elif precision == BF16:
+            # Dense AuxK on the compacted dead-latent subset (S columns): k_aux = d/2 selections per token make
+            # the row-sparse kernels ~12x the main path's work, but as dense [N,S] x [S,d] products it is cheap.
+            dead_idx = torch.nonzero(dead_mask).squeeze(1).to(torch.int32)
+            S = dead_idx.numel()
+            Sp = (S + 7) // 8 * 8
+            ws = ops.gather_rows(we_hi, dead_idx)
+            bs = ops.gather_rows(b_enc, dead_idx)
+            pre_dead = ops.gemm_nt(xc_hi, None, ws, None, bs, True, precision)          # [N,S] fp32
+            A = ops.row_topk_mask(pre_dead, k_aux, Sp)                                   # [N,Sp] bf16, top-k_aux kept
+            del pre_dead
+            wd_sub = ops.gather_rows(wd, dead_idx)                                       # [S,d] bf16
+            wd_sub_T = ops.transpose_bf16(wd_sub, d, Sp)                                 # [d,Sp]
+            e_hat = ops.gemm_nt(A, None, wd_sub_T, None, b_dec, False, precision)        # A @ W_dec[dead] + b_dec
+            r_aux, sse_aux, _ = ops.residual(e_hat, e, torch.float32, want_colsum=False)
+            st.aux_dense = (dead_idx, S, Sp, A, wd_sub, r_aux, scale)
+            a_vals = a_idx = None
         else:
             # dead latents are a column subset: GEMM against their compacted encoder rows, select among them, map
             # the subset-local indices back (same (value desc, index asc) order as the masked full-width top-k)
@@ -121,12 +139,13 @@ def topk_forward(x, W_enc, b_enc, W_dec, b_dec, k, *, precision, dead_mask=None,
             pre_dead = ops.gemm_nt(xc_hi, xc_lo, ws_hi, ws_lo, bs, True, precision)
             a_vals, a_loc = ops.row_topk(pre_dead, k_aux)
             a_idx = ops.index_map(dead_idx, a_loc)
-        _, r_aux, sse_aux, _ = ops.topk_decode(a_vals, a_idx, wd, b_dec, e, resid_dtype=torch.float32,
-                                               want_sse=True)
+        if a_vals is not None:
+            _, r_aux, sse_aux, _ = ops.topk_decode(a_vals, a_idx, wd, b_dec, e, resid_dtype=torch.float32,
+                                                   want_sse=True)
+            st.aux = (a_vals, a_idx, r_aux, scale)
         if dp is not None:
             sse_aux = dp.all_reduce_sum(sse_aux)
         auxk = (scale * sse_aux[0] / scal[4].double()).float() * auxk_alpha
-        st.aux = (a_vals, a_idx, r_aux, scale)
 
     mfvu = zero
     ret_out, ret_vals, ret_idx = sae_out, vals, idx
@@ -182,7 +201,13 @@ def topk_backward(st: TopKState, g_fvu, g_aux=None, g_multi=None, *, out=None):
         zero = torch.zeros((), dtype=torch.float32, device=dev)
         decodes = []  # (tag, vals, idx, G)
         db_direct = c_main * st.colsum_e
-        if st.aux is not None:
+        dense_aux = None
+        if st.aux_dense is not None:
+            dead_idx, S, Sp, A, wd_sub, r_aux, scale = st.aux_dense
+            c_aux = as_t(g_aux) * (st.auxk_alpha * scale) * two_over_tv
+            G_main = ops.axpby(st.e, r_aux, torch.stack((c_main, -c_aux)), gdt)  # e is not detached (:126)
+            dense_aux = (dead_idx, S, Sp, A, wd_sub, ops.axpby(r_aux, None, torch.stack((c_aux, zero)), gdt))
+        elif st.aux is not None:
             a_vals, a_idx, r_aux, scale = st.aux
             # auxk_loss already carries auxk_alpha, so d auxk_loss / d e_hat = alpha*scale*2(e_hat - e)/tv
             c_aux = as_t(g_aux) * (st.auxk_alpha * scale) * two_over_tv
@@ -207,6 +232,25 @@ def topk_backward(st: TopKState, g_fvu, g_aux=None, g_multi=None, *, out=None):
             first = False
             if tag == returned:
                 st.offsets = offsets  # did_fire is taken from the RETURNED encoding (train_sae.py:442)
+        if dense_aux is not None:
+            # dense backward of the AuxK branch on the dead subset: four tensor-core products, then a row scatter
+            dead_idx, S, Sp, A, wd_sub, G_hat = dense_aux
+            N = st.x2.shape[0]
+            Np = (N + 7) // 8 * 8
+            gA = ops.gemm_nt(G_hat, None, wd_sub, None, None, False, BF16)               # [N,S] = G_hat @ W_dec[dead]^T
+            dpre, db_sub = ops.mask_grad(gA, A)                                          # relu/top-k mask, bf16 [N,Sp]
+            del gA
+            splits = max(1, min(16, (148 * 2) // max(1, (S + 127) // 128)))
+            A_T = ops.transpose_bf16(A, S, Np)                                           # [S,Np]
+            G_T = ops.transpose_bf16(G_hat, d, Np)                                       # [d,Np]
+            dWdec_sub = ops.gemm_nt_splitk(A_T, G_T, splits)                             # A^T @ G_hat       [S,d]
+            del A_T, G_T
+            P_T = ops.transpose_bf16(dpre, S, Np)
+            X_T = ops.transpose_bf16(st.xc_hi, d, Np)
+            dWenc_sub = ops.gemm_nt_splitk(P_T, X_T, splits)                             # dpre^T @ (x - b_dec)
+            ops.scatter_add_rows(dWdec_sub, dead_idx, dW_dec)
+            ops.scatter_add_rows(dWenc_sub, dead_idx, dW_enc)
+            ops.scatter_add_rows(db_sub, dead_idx, db_enc)
         db_dec.copy_(db_direct)
         ops.topk_bdec_grad(None, None, db_enc, st.W_enc, db_dec, True)
     return {"encoder.weight": dW_enc, "encoder.bias": db_enc, "W_dec": dW_dec, "b_dec": db_dec}

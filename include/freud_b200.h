@@ -73,6 +73,26 @@ int freud_gather_rows(const void* src, const int32_t* rows, void* dst, int64_t n
                       void* stream);
 int freud_index_map(const int32_t* table, const int32_t* in, int32_t* out, int64_t count, void* stream);
 
+/* Dense AuxK branch on the compacted dead-latent subset (bf16 mode).  k_aux = d/2 selected latents per token make
+ * the row-sparse kernels 12x the main path's work, while a dense GEMM over the S dead latents is cheap:
+ *   freud_row_topk_mask   : out[r,j] = latents[r,j] if j is in row r's top-k else 0 (bf16, row pitch ld >= n)
+ *   freud_transpose_bf16  : out[c,r] = in[r,c] (pitches ld_in / ld_out, padding zeroed) -- K-major GEMM operands
+ *   freud_mask_grad       : dpre = (act > 0) ? g : 0 (bf16) with fp32 column sums (autograd of relu + topk)
+ *   freud_scatter_add_rows: dst[rows_idx[r],:] += src[r,:] (subset gradients back into the full matrices) */
+int freud_row_topk_mask(const float* latents, void* out_bf16, int64_t rows, int64_t n, int64_t k, int64_t ld,
+                        void* stream);
+int freud_transpose_bf16(const void* in, void* out, int64_t rows, int64_t cols, int64_t ld_in, int64_t ld_out,
+                         void* stream);
+int freud_mask_grad(const float* g, const void* act_bf16, void* dpre_bf16, float* colsum, int64_t rows, int64_t n,
+                    int64_t ld, void* stream);
+int freud_scatter_add_rows(const float* src, const int32_t* rows_idx, float* dst, int64_t n_rows, int64_t row_elems,
+                           void* stream);
+/* Split-K tensor-core product for few output rows and a very long K (the subset weight gradients, K = tokens):
+ * workspace [splits, M, N] receives partial A[M,K] @ B[N,K]^T products (bf16 operands), freud_sum_splits adds them. */
+int freud_gemm_nt_splitk(const void* a_bf16, const void* b_bf16, float* workspace, int64_t M, int64_t N, int64_t K,
+                         int64_t splits, void* stream);
+int freud_sum_splits(const float* parts, float* out, int64_t splits, int64_t numel, void* stream);
+
 /* Sparse decode + residual (eager_decode + decode, topkautoencoder.py:15-18,87-91,101):
  *   sae_out[t,:] = sum_j top_vals[t,j] * W_dec[top_idx[t,j],:] + b_dec
  * W_dec is fp32 (w_is_bf16 == 0) or a bf16 copy.  Optional outputs (NULL to skip):

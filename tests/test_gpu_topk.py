@@ -157,11 +157,23 @@ def test_fused_main_with_live_auxk_vs_oracle(precision, tol, n_dead):
     prec = BF16 if precision == "bf16" else FP32
     cu = [v.cuda() for v in (x, W_enc, b_enc, W_dec, b_dec)]
     res, st = topk_engine.topk_forward(*cu, k, precision=prec, dead_mask=dead.cuda(), auxk_alpha=alpha)
-    assert st.aux is not None
+    assert st.aux is not None or st.aux_dense is not None
     grads = topk_engine.topk_backward(st, 1.0, 1.0, 0.125)
     torch.cuda.synchronize()
     same_main = sets_equal_rows(res.top_idx.cpu(), ref.top_indices.reshape(-1, k))
-    same_aux = sets_equal_rows(st.aux[1].cpu(), ref.aux[1].reshape(-1, ref.aux[1].shape[-1]))
+    ka = ref.aux[1].shape[-1]
+    if st.aux is not None:
+        same_aux = sets_equal_rows(st.aux[1].cpu(), ref.aux[1].reshape(-1, ka))
+    else:
+        # dense AuxK (bf16 mode): the selection lives in the non-zero pattern of A [N, S]; compare the sets of
+        # POSITIVE selected latents (zero-valued selections are indistinguishable and contribute nothing)
+        dead_idx, S, Sp, A = st.aux_dense[:4]
+        got = torch.zeros(B * T, n, dtype=torch.bool)
+        got[:, dead_idx.cpu().long()] = A[:, :S].float().cpu() > 0
+        want = torch.zeros(B * T, n, dtype=torch.bool)
+        ra, ri = ref.aux[0].reshape(-1, ka), ref.aux[1].reshape(-1, ka)
+        want.scatter_(1, ri, ra > 0)
+        same_aux = (got == want).all(-1)
     assert same_main.float().mean() > 0.97 and same_aux.float().mean() > 0.97
     assert rel_err(res.fvu.cpu(), ref.fvu) < max(tol, 1e-5)
     if bool(same_main.all()) and bool(same_aux.all()):
