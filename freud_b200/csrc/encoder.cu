@@ -7,10 +7,10 @@
 
 namespace freud {
 
-template <int BN, int STAGES, int EPI, bool TF32, int SETS, int CL>
+template <int BN, int STAGES, int EPI, bool TF32, int SETS, int CL, int NBUF = 2>
 static int launch_gemm(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, GemmParams p,
                        int passes, cudaStream_t stream) {
-  using L = GemmSmem<BN, STAGES, EPI, SETS>;
+  using L = GemmSmem<BN, STAGES, EPI, SETS, NBUF>;
   const int eb = TF32 ? 4 : 2;
   CUtensorMap mA0, mA1, mB0, mB1;
   if (make_tensor_map_2d(&mA0, a_hi, p.M, p.K, p.K, eb, kBM)) return 3;
@@ -23,7 +23,7 @@ static int launch_gemm(const void* a_hi, const void* a_lo, const void* b_hi, con
     mB1 = mB0;
   }
   p.passes = passes;
-  auto kern = sm100_gemm_kernel<BN, STAGES, EPI, TF32, SETS, CL>;
+  auto kern = sm100_gemm_kernel<BN, STAGES, EPI, TF32, SETS, CL, NBUF>;
   static bool attr_set = false;
   if (!attr_set) {
     FREUD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -85,6 +85,8 @@ extern "C" int freud_topk_encode(const void* xc_hi, const void* xc_lo, const voi
   if (precision == FREUD_BF16) {
     switch (encoder_variant()) {
       case 2: return launch_gemm<256, 3, EPI_TOPK, false, 2, 2>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
+      // (a triple-buffered BN = 160 variant, launch_gemm<160, 4, EPI_TOPK, false, 2, 1, 3>, measured slower:
+      //  2.02 vs 1.78 ms on C3 -- per-tile fixed costs outweigh the extra MMA/scan overlap)
       case 3: return launch_gemm<256, 3, EPI_TOPK, false, 1, 1>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
       case 6: p.out = top_vals; return launch_gemm<256, 3, EPI_NONE, false, 1, 1>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
       case 7: p.out = top_vals; return launch_gemm<256, 4, EPI_NONE, false, 1, 1>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);

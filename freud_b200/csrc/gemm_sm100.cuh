@@ -62,7 +62,7 @@ struct GemmParams {
   int64_t split_stride;
 };
 
-template <int BN, int STAGES, int EPI, int SETS>
+template <int BN, int STAGES, int EPI, int SETS, int NBUF = 2>
 struct GemmSmem {
   static constexpr int kEpiWarps = 4 * SETS;
   static constexpr int kThreads = 128 + kEpiWarps * 32;
@@ -73,8 +73,8 @@ struct GemmSmem {
   static constexpr int kBufPerWarp = kNewSlots * kSlotStride;
   static constexpr int kBuf = EPI == EPI_TOPK ? kEpiWarps * kBufPerWarp : 0;
   static constexpr int kThr = 2 * kBM * 4;  // per-set published thresholds
-  static constexpr int kBiasS = 4 * BN * 4; // staged bias rows: [accumulator buffer][tile parity][BN]
-  static constexpr int kBars = (2 * STAGES + 4) * 8 + 16;
+  static constexpr int kBiasS = 2 * NBUF * BN * 4; // staged bias rows: [accumulator buffer][use parity][BN]
+  static constexpr int kBars = (2 * STAGES + 2 * NBUF) * 8 + 16;
   static constexpr int kTotal = kRing + kBuf + kThr + kBiasS + kBars;
 };
 
@@ -150,17 +150,21 @@ __device__ __noinline__ float compact_rows(uint64_t (&surv)[kTopK], uint32_t my_
   return __uint_as_float(static_cast<uint32_t>(surv[kTopK - 1] >> 32));
 }
 
-template <int BN, int STAGES, int EPI, bool TF32, int SETS, int CL>
+// NBUF accumulator buffers of BN columns live in TMEM (NBUF * BN <= 512).  With two epilogue sets scanning two
+// buffers, a THIRD buffer (BN = 160) lets the MMA issuer fill the next tile meanwhile: the tile rate becomes
+// min(1/M, 2/E) instead of 2/(M + E)  (M = MMA time, E = scan + bias pre-store time of one tile).
+template <int BN, int STAGES, int EPI, bool TF32, int SETS, int CL, int NBUF = 2>
 __global__ void __launch_bounds__(128 + SETS * 128, 1)
 sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                   const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
                   const GemmParams p) {
-  using L = GemmSmem<BN, STAGES, EPI, SETS>;
+  using L = GemmSmem<BN, STAGES, EPI, SETS, NBUF>;
   constexpr int kEpiWarps = L::kEpiWarps;
   constexpr uint16_t kMcMask = static_cast<uint16_t>((1u << CL) - 1u);
   constexpr int kBKe = TF32 ? 32 : 64;  // elements per 128-byte k-block
-  constexpr uint32_t kTmemCols = 2 * BN;
-  static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns must be pow2 <= 512");
+  constexpr uint32_t kTmemCols = NBUF * BN <= 32 ? 32 : NBUF * BN <= 64 ? 64 : NBUF * BN <= 128 ? 128
+                                 : NBUF * BN <= 256 ? 256 : 512;  // allocation granularity: power of two
+  static_assert(NBUF * BN <= 512, "accumulator buffers exceed the 512 TMEM columns");
   static_assert(kNewSlots == kTopK, "the merge step pairs survivor i with candidate 31-i");
   const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0u;
 
@@ -174,8 +178,8 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tfull_bar = bars + 2 * STAGES;
-  uint64_t* tempty_bar = bars + 2 * STAGES + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* tempty_bar = bars + 2 * STAGES + NBUF;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * NBUF);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -200,7 +204,7 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], CL);  // every CTA of the cluster releases a slot its peers multicast into
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < NBUF; ++b) {
       mbar_init(&tfull_bar[b], 1);
       mbar_init(&tempty_bar[b], 4);  // the four lane-quarter warps that drain (and re-bias) buffer b
     }
@@ -256,9 +260,9 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       for (int nt = 0; nt < num_nt; ++nt) {
-        const int buf = nt & 1;
+        const int buf = nt % NBUF;
         // the epilogue arrives once the buffer holds this tile's bias row (initially, and after each drain)
-        mbar_wait(&tempty_bar[buf], (nt >> 1) & 1);
+        mbar_wait(&tempty_bar[buf], (nt / NBUF) & 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * BN;
         for (int vk = 0; vk < num_vk; ++vk) {
@@ -297,10 +301,10 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
 
     // Bias of tile nt: fetched into shared memory early (global-load latency off the critical path), written into
-    // accumulator buffer (nt & 1) with tcgen05.st once that buffer is drained, then handed to the MMA issuer.
+    // accumulator buffer (nt % NBUF) with tcgen05.st once that buffer is drained, then handed to the MMA issuer.
     auto fetch_bias = [&](int nt) {
       if (nt < num_nt) {
-        float* bs = bias_s + ((nt & 1) * 2 + ((nt >> 1) & 1)) * BN;  // double-buffered per accumulator buffer
+        float* bs = bias_s + ((nt % NBUF) * 2 + ((nt / NBUF) & 1)) * BN;  // double-buffered per accumulator buffer
         for (int c = stid; c < BN; c += 128) {
           const int gc = nt * BN + c;
           bs[c] = gc < p.N ? ((p.bias && split == 0) ? __ldg(p.bias + gc) : 0.f) : -INFINITY;
@@ -314,8 +318,8 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           asm volatile("bar.sync 1, 128;" ::: "memory");
         else
           asm volatile("bar.sync 2, 128;" ::: "memory");
-        const uint32_t t_addr = lane_taddr + (nt & 1) * BN;
-        const uint32_t bs_addr = smem_u32(bias_s + ((nt & 1) * 2 + ((nt >> 1) & 1)) * BN);
+        const uint32_t t_addr = lane_taddr + (nt % NBUF) * BN;
+        const uint32_t bs_addr = smem_u32(bias_s + ((nt % NBUF) * 2 + ((nt / NBUF) & 1)) * BN);
 #pragma unroll 2
         for (int c0 = 0; c0 < BN; c0 += 32) {
           uint32_t bv[32];
@@ -333,7 +337,7 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[nt & 1]);
+      if (lane == 0) mbar_arrive(&tempty_bar[nt % NBUF]);
     };
 
     uint64_t surv[kTopK];
@@ -346,23 +350,21 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       for (int s = 0; s < kTopK; ++s) surv[s] = 0ull;
     }
     // initial bias for the first tile(s) this set will see
-    if constexpr (SETS == 2) {
-      fetch_bias(set);
-      prestore_bias(set);
-    } else {
-      fetch_bias(0);
-      fetch_bias(1);
-      prestore_bias(0);
-      prestore_bias(1);
-    }
+    // (tile t < NBUF is primed by the set that will scan it)
+#pragma unroll
+    for (int t0 = 0; t0 < NBUF; ++t0)
+      if (SETS == 1 || (t0 & 1) == set) fetch_bias(t0);
+#pragma unroll
+    for (int t0 = 0; t0 < NBUF; ++t0)
+      if (SETS == 1 || (t0 & 1) == set) prestore_bias(t0);
     for (int nt = set; nt < num_nt; nt += SETS) {
-      const int buf = nt & 1;
+      const int buf = nt % NBUF;
       if constexpr (EPI == EPI_TOPK && SETS == 2) {
         // any lower bound of the row's 32nd largest value is a valid filter: adopt the other set's if tighter
         thresh = fmaxf(thresh, thr_s[(set ^ 1) * kBM + stid]);
       }
-      fetch_bias(nt + 2);  // lands in shared memory while this tile is scanned
-      mbar_wait(&tfull_bar[buf], (nt >> 1) & 1);
+      fetch_bias(nt + NBUF);  // lands in shared memory while this tile is scanned
+      mbar_wait(&tfull_bar[buf], (nt / NBUF) & 1);
       tc_fence_after();
       const uint32_t t_addr = lane_taddr + buf * BN;
       uint32_t r[2][kChunk];
@@ -437,7 +439,7 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         }
       }
       // buffer drained: pre-store the bias of the tile that will reuse it, then release it to the MMA issuer
-      prestore_bias(nt + 2);
+      prestore_bias(nt + NBUF);
     }
     if constexpr (EPI == EPI_TOPK) {
       // final compaction; with two sets, set 1 hands its survivors to set 0 through its (now idle) candidate
