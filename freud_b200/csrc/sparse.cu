@@ -75,6 +75,183 @@ __global__ void __launch_bounds__(256) split_operand_kernel(const float* __restr
   }
 }
 
+// 16-byte slice of a gathered row: kVec elements, widened to fp32 after the loads of a batch have been issued.
+template <typename T> struct RowVec;
+template <> struct RowVec<__nv_bfloat16> {
+  static constexpr int kVec = 8;
+  __device__ static __forceinline__ void unpack(const uint4& raw, float (&v)[8]) {
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  __device__ static __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+    unpack(__ldg(reinterpret_cast<const uint4*>(p)), v);
+  }
+  __device__ static __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 raw;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = raw;
+  }
+};
+template <> struct RowVec<float> {
+  static constexpr int kVec = 4;
+  __device__ static __forceinline__ void unpack(const uint4& raw, float (&v)[4]) {
+    v[0] = __uint_as_float(raw.x); v[1] = __uint_as_float(raw.y);
+    v[2] = __uint_as_float(raw.z); v[3] = __uint_as_float(raw.w);
+  }
+  __device__ static __forceinline__ void load(const float* p, float (&v)[4]) {
+    unpack(__ldg(reinterpret_cast<const uint4*>(p)), v);
+  }
+  __device__ static __forceinline__ void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+
+// Pack the entries a shard owns (index >= 0) to the front of the warp's 32 slots, order preserved; returns the count.
+__device__ __forceinline__ int compact_valid(int& my_i, float& my_a, int lane) {
+  const unsigned m = __ballot_sync(0xffffffffu, my_i >= 0);
+  const int cnt = __popc(m);
+  if (m != 0xffffffffu) {  // warp-uniform; never taken without feature sharding
+    const int src = static_cast<int>(__fns(m, 0, lane + 1)) & 31;
+    const int ci = __shfl_sync(0xffffffffu, my_i, src);
+    const float ca = __shfl_sync(0xffffffffu, my_a, src);
+    my_i = lane < cnt ? ci : -1;
+    my_a = lane < cnt ? ca : 0.f;
+  }
+  return cnt;
+}
+
+// ------------------------------------------------------------------------------------- decode, fixed row width
+// Same contract as decode_kernel for the activation widths the Whisper family has (D known at compile time):
+// lane l owns the 16-byte slices {(32 i + l) * V}, and the k gathered rows are fetched R at a time with every load
+// of a batch issued before the first FMA (no branch inside a batch: absent entries gather row 0 with a = 0).
+template <typename WT, typename RT, int D>
+__global__ void __launch_bounds__(256) decode_fixed_kernel(const float* __restrict__ top_vals,
+                                                           const int32_t* __restrict__ top_idx,
+                                                           const WT* __restrict__ W, const float* __restrict__ b_dec,
+                                                           const float* __restrict__ target,
+                                                           float* __restrict__ sae_out, RT* __restrict__ resid,
+                                                           double* __restrict__ sse, float* __restrict__ colsum,
+                                                           int64_t N, int k) {
+  constexpr int V = RowVec<WT>::kVec;
+  constexpr int CH = (D + 32 * V - 1) / (32 * V);
+  constexpr int R = CH <= 3 ? 8 : (CH <= 6 ? 4 : 2);  // rows in flight: <= 24 16-byte loads per lane
+  __shared__ double scratch[32];
+  __shared__ float colsum_s[D];
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  if (colsum) {
+    for (int c = threadIdx.x; c < D; c += blockDim.x) colsum_s[c] = 0.f;
+    __syncthreads();
+  }
+  double sq = 0.0;
+  float csum[CH][V];
+#pragma unroll
+  for (int i = 0; i < CH; ++i)
+#pragma unroll
+    for (int e = 0; e < V; ++e) csum[i][e] = 0.f;
+  for (int64_t t = static_cast<int64_t>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); t < N;
+       t += static_cast<int64_t>(gridDim.x) * warps_per_block) {
+    float acc[CH][V];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const int c = (i * 32 + lane) * V;
+#pragma unroll
+      for (int e = 0; e < V; e += 4) {
+        const float4 b = c < D ? load4(b_dec + c + e) : make_float4(0, 0, 0, 0);
+        acc[i][e] = b.x; acc[i][e + 1] = b.y; acc[i][e + 2] = b.z; acc[i][e + 3] = b.w;
+      }
+    }
+    for (int j0 = 0; j0 < k; j0 += 32) {
+      const int jn = min(32, k - j0);
+      float my_a = lane < jn ? __ldg(top_vals + t * k + j0 + lane) : 0.f;
+      int my_i = lane < jn ? __ldg(top_idx + t * k + j0 + lane) : -1;
+      const int cnt = compact_valid(my_i, my_a, lane);
+      for (int jb = 0; jb < cnt; jb += R) {
+        uint4 raw[R][CH];
+        float a[R];
+#pragma unroll
+        for (int u = 0; u < R; ++u) {
+          const int fi = __shfl_sync(0xffffffffu, my_i, (jb + u) & 31);
+          const float av = __shfl_sync(0xffffffffu, my_a, (jb + u) & 31);
+          const bool ok = jb + u < cnt;
+          a[u] = ok ? av : 0.f;
+          const WT* wr = W + static_cast<int64_t>(ok ? fi : 0) * D;
+#pragma unroll
+          for (int i = 0; i < CH; ++i) {
+            const int c = (i * 32 + lane) * V;
+            if (c < D) raw[u][i] = __ldg(reinterpret_cast<const uint4*>(wr + c));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < R; ++u) {
+#pragma unroll
+          for (int i = 0; i < CH; ++i) {
+            const int c = (i * 32 + lane) * V;
+            if (c < D) {
+              float w[V];
+              RowVec<WT>::unpack(raw[u][i], w);
+#pragma unroll
+              for (int e = 0; e < V; ++e) acc[i][e] = fmaf(a[u], w[e], acc[i][e]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const int c = (i * 32 + lane) * V;
+      if (c < D) {
+#pragma unroll
+        for (int e = 0; e < V; e += 4)
+          store4(sae_out + t * D + c + e, make_float4(acc[i][e], acc[i][e + 1], acc[i][e + 2], acc[i][e + 3]));
+        if (target) {
+          float err[V];
+#pragma unroll
+          for (int e = 0; e < V; e += 4) {
+            const float4 xv = load4(target + t * D + c + e);
+            err[e] = acc[i][e] - xv.x; err[e + 1] = acc[i][e + 1] - xv.y;
+            err[e + 2] = acc[i][e + 2] - xv.z; err[e + 3] = acc[i][e + 3] - xv.w;
+            sq += (double)(err[e] * err[e] + err[e + 1] * err[e + 1]) +
+                  (double)(err[e + 2] * err[e + 2] + err[e + 3] * err[e + 3]);
+          }
+          if (resid) {
+#pragma unroll
+            for (int e = 0; e < V; e += 4)
+              store4(resid + t * D + c + e, make_float4(err[e], err[e + 1], err[e + 2], err[e + 3]));
+          }
+#pragma unroll
+          for (int e = 0; e < V; ++e) csum[i][e] += err[e];
+        }
+      }
+    }
+  }
+  if (colsum) {
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const int c = (i * 32 + lane) * V;
+      if (c < D) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) atomicAdd(colsum_s + c + e, csum[i][e]);
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += blockDim.x) atomicAdd(colsum + c, colsum_s[c]);
+  }
+  if (sse) {
+    const double tot = block_sum(sq, scratch);
+    if (threadIdx.x == 0) atomicAdd(sse, tot);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ decode
 // One warp per token.  Lane l owns channels {4l + 128i .. +3}; the k gathered decoder rows stream through
 // registers 4 at a time (independent 16-byte loads in flight), fp32 accumulate.
@@ -203,6 +380,73 @@ __global__ void __launch_bounds__(256) dacts_kernel(const GT* __restrict__ g, co
           }
         }
         part[j] = s;
+      }
+      const float tot = warp_transpose_reduce32(part, lane);
+      if (lane < jn) dacts[t * k + j0 + lane] = tot;
+    }
+  }
+}
+
+// Fixed-width twin of dacts_kernel: rows fetched R at a time, all loads of a batch in flight before the dots.
+template <typename GT, typename WT, int D>
+__global__ void __launch_bounds__(256) dacts_fixed_kernel(const GT* __restrict__ g, const int32_t* __restrict__ top_idx,
+                                                          const WT* __restrict__ W, float* __restrict__ dacts,
+                                                          int64_t N, int k) {
+  constexpr int V = RowVec<WT>::kVec;
+  constexpr int CH = (D + 32 * V - 1) / (32 * V);
+  constexpr int R = CH <= 3 ? 8 : (CH <= 6 ? 4 : 2);
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  for (int64_t t = static_cast<int64_t>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); t < N;
+       t += static_cast<int64_t>(gridDim.x) * warps_per_block) {
+    float gv[CH][V];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const int c = (i * 32 + lane) * V;
+#pragma unroll
+      for (int e = 0; e < V; e += 4) {
+        const float4 v = c < D ? load4(g + t * D + c + e) : make_float4(0, 0, 0, 0);
+        gv[i][e] = v.x; gv[i][e + 1] = v.y; gv[i][e + 2] = v.z; gv[i][e + 3] = v.w;
+      }
+    }
+    for (int j0 = 0; j0 < k; j0 += 32) {
+      const int jn = min(32, k - j0);
+      const int my_i = lane < jn ? __ldg(top_idx + t * k + j0 + lane) : -1;
+      const unsigned live = __ballot_sync(0xffffffffu, my_i >= 0);
+      float part[32];
+#pragma unroll
+      for (int jb = 0; jb < 32; jb += R) {
+        if ((live >> jb) & ((1u << R) - 1u)) {  // warp-uniform: skip batches with no owned entry
+          uint4 raw[R][CH];
+#pragma unroll
+          for (int u = 0; u < R; ++u) {
+            const int fi = __shfl_sync(0xffffffffu, my_i, jb + u);
+            const WT* wr = W + static_cast<int64_t>(fi < 0 ? 0 : fi) * D;
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+              const int c = (i * 32 + lane) * V;
+              if (c < D) raw[u][i] = __ldg(reinterpret_cast<const uint4*>(wr + c));
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < R; ++u) {
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+              const int c = (i * 32 + lane) * V;
+              if (c < D) {
+                float w[V];
+                RowVec<WT>::unpack(raw[u][i], w);
+#pragma unroll
+                for (int e = 0; e < V; ++e) s = fmaf(gv[i][e], w[e], s);
+              }
+            }
+            part[jb + u] = ((live >> (jb + u)) & 1u) ? s : 0.f;
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < R; ++u) part[jb + u] = 0.f;
+        }
       }
       const float tot = warp_transpose_reduce32(part, lane);
       if (lane < jn) dacts[t * k + j0 + lane] = tot;
@@ -372,28 +616,6 @@ __global__ void __launch_bounds__(1024) chunk_scan_kernel(const int32_t* __restr
   }
   if (threadIdx.x == 0) chunk_off[n] = carry_s;
 }
-
-template <typename T> struct RowVec;
-template <> struct RowVec<__nv_bfloat16> {
-  static constexpr int kVec = 8;
-  __device__ static __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
-    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p));
-    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
-      v[2 * i] = f.x;
-      v[2 * i + 1] = f.y;
-    }
-  }
-};
-template <> struct RowVec<float> {
-  static constexpr int kVec = 4;
-  __device__ static __forceinline__ void load(const float* p, float (&v)[4]) {
-    const float4 f = __ldg(reinterpret_cast<const float4*>(p));
-    v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
-  }
-};
 
 // Short lists (a wide dictionary has N*k/n entries per feature on average): every row-team of `tpr` threads owns ONE
 // feature and walks its list alone -- no shared memory, no block barrier, direct row stores.  Thread c of a team owns
@@ -826,6 +1048,18 @@ int launch_decode(const float* tv, const int32_t* ti, const void* W, const float
                   float* sae_out, void* resid, double* sse, float* colsum, int64_t N, int d, int k, cudaStream_t s) {
   const int grid = grid_for(N, 8, sm_count() * 8);
   const size_t sm = d * sizeof(float);
+#define LF(D)                                                                                                    \
+  decode_fixed_kernel<WT, RT, D><<<grid, 256, 0, s>>>(tv, ti, static_cast<const WT*>(W), b_dec, target,       \
+                                                         sae_out, static_cast<RT*>(resid), sse, colsum, N, k)
+  switch (d) {
+    case 384: LF(384); return 0;
+    case 512: LF(512); return 0;
+    case 768: LF(768); return 0;
+    case 1024: LF(1024); return 0;
+    case 1280: LF(1280); return 0;
+    default: break;
+  }
+#undef LF
 #define LD(CH)                                                                                                   \
   decode_kernel<WT, RT, CH><<<grid, 256, sm, s>>>(tv, ti, static_cast<const WT*>(W), b_dec, target, sae_out,     \
                                                    static_cast<RT*>(resid), sse, colsum, N, d, k)
@@ -840,6 +1074,18 @@ template <typename GT, typename WT>
 int launch_dacts(const void* g, const int32_t* ti, const void* W, float* dacts, int64_t N, int d, int k,
                  cudaStream_t s) {
   const int grid = grid_for(N, 8, sm_count() * 8);
+#define LF(D)                                                                                                 \
+  dacts_fixed_kernel<GT, WT, D><<<grid, 256, 0, s>>>(static_cast<const GT*>(g), ti, static_cast<const WT*>(W), \
+                                                        dacts, N, k)
+  switch (d) {
+    case 384: LF(384); return 0;
+    case 512: LF(512); return 0;
+    case 768: LF(768); return 0;
+    case 1024: LF(1024); return 0;
+    case 1280: LF(1280); return 0;
+    default: break;
+  }
+#undef LF
 #define LD(CH) \
   dacts_kernel<GT, WT, CH><<<grid, 256, 0, s>>>(static_cast<const GT*>(g), ti, static_cast<const WT*>(W), dacts, N, d, k)
   if (d <= 384) LD(3);
