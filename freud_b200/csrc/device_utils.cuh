@@ -67,6 +67,32 @@ __device__ __forceinline__ void store4(__nv_bfloat16* p, float4 v) {
   *reinterpret_cast<uint2*>(p) = raw;
 }
 
+// L2 residency hints for the gather kernels: the gathered matrix (tens of MB, re-read ~k times) is loaded with an
+// evict_last policy while the large once-touched outputs stream through with evict_first (__stcs / __ldcs), so
+// the streams do not push the gathered rows out of the 126 MB L2.
+__device__ __forceinline__ uint64_t l2_keep_policy() {
+  uint64_t pol;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint4 ldg_keep(const void* p, uint64_t pol) {
+  uint4 r;
+  asm("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+      : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+      : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ void store4_stream(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
+__device__ __forceinline__ void store4_stream(__nv_bfloat16* p, float4 v) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+  const __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 raw;
+  raw.x = *reinterpret_cast<const uint32_t*>(&a);
+  raw.y = *reinterpret_cast<const uint32_t*>(&b);
+  __stcs(reinterpret_cast<uint2*>(p), raw);
+}
+__device__ __forceinline__ float4 load4_stream(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+
 __device__ __forceinline__ float to_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));

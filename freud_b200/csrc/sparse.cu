@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(256) decode_fixed_kernel(const float* __restri
   __shared__ float colsum_s[D];
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
+  const uint64_t keep = l2_keep_policy();
   if (colsum) {
     for (int c = threadIdx.x; c < D; c += blockDim.x) colsum_s[c] = 0.f;
     __syncthreads();
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(256) decode_fixed_kernel(const float* __restri
 #pragma unroll
           for (int i = 0; i < CH; ++i) {
             const int c = (i * 32 + lane) * V;
-            if (c < D) raw[u][i] = __ldg(reinterpret_cast<const uint4*>(wr + c));
+            if (c < D) raw[u][i] = ldg_keep(wr + c, keep);
           }
         }
 #pragma unroll
@@ -212,12 +213,12 @@ __global__ void __launch_bounds__(256) decode_fixed_kernel(const float* __restri
       if (c < D) {
 #pragma unroll
         for (int e = 0; e < V; e += 4)
-          store4(sae_out + t * D + c + e, make_float4(acc[i][e], acc[i][e + 1], acc[i][e + 2], acc[i][e + 3]));
+          store4_stream(sae_out + t * D + c + e, make_float4(acc[i][e], acc[i][e + 1], acc[i][e + 2], acc[i][e + 3]));
         if (target) {
           float err[V];
 #pragma unroll
           for (int e = 0; e < V; e += 4) {
-            const float4 xv = load4(target + t * D + c + e);
+            const float4 xv = load4_stream(target + t * D + c + e);
             err[e] = acc[i][e] - xv.x; err[e + 1] = acc[i][e + 1] - xv.y;
             err[e + 2] = acc[i][e + 2] - xv.z; err[e + 3] = acc[i][e + 3] - xv.w;
             sq += (double)(err[e] * err[e] + err[e + 1] * err[e + 1]) +
@@ -397,6 +398,7 @@ __global__ void __launch_bounds__(256) dacts_fixed_kernel(const GT* __restrict__
   constexpr int R = CH <= 3 ? 8 : (CH <= 6 ? 4 : 2);
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
+  const uint64_t keep = l2_keep_policy();
   for (int64_t t = static_cast<int64_t>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); t < N;
        t += static_cast<int64_t>(gridDim.x) * warps_per_block) {
     float gv[CH][V];
@@ -425,7 +427,7 @@ __global__ void __launch_bounds__(256) dacts_fixed_kernel(const GT* __restrict__
 #pragma unroll
             for (int i = 0; i < CH; ++i) {
               const int c = (i * 32 + lane) * V;
-              if (c < D) raw[u][i] = __ldg(reinterpret_cast<const uint4*>(wr + c));
+              if (c < D) raw[u][i] = ldg_keep(wr + c, keep);
             }
           }
 #pragma unroll
@@ -617,90 +619,137 @@ __global__ void __launch_bounds__(1024) chunk_scan_kernel(const int32_t* __restr
   if (threadIdx.x == 0) chunk_off[n] = carry_s;
 }
 
-// Short lists (a wide dictionary has N*k/n entries per feature on average): every row-team of `tpr` threads owns ONE
-// feature and walks its list alone -- no shared memory, no block barrier, direct row stores.  Thread c of a team owns
-// one 16-byte column slice of the gathered g / xc rows; entry metadata is read redundantly (L1 broadcast).
-template <typename GT, typename XT>
-__global__ void __launch_bounds__(256) sparse_grads_team_kernel(
-    const int32_t* __restrict__ offsets, const int32_t* __restrict__ entries, const float* __restrict__ top_vals,
-    const float* __restrict__ dacts, const GT* __restrict__ g, const XT* __restrict__ xc,
-    const float* __restrict__ b_dec, const float* __restrict__ scales, float* __restrict__ dW_dec,
-    float* __restrict__ dW_enc, float* __restrict__ db_enc, int n, int d, int k, int tpr, int teams) {
-  constexpr int V = RowVec<GT>::kVec;
-  constexpr bool kRecenter = sizeof(XT) == 4;
-  const int team = threadIdx.x / tpr;
-  const int lane_c = threadIdx.x - team * tpr;
-  const int f = blockIdx.x * teams + team;
-  if (team >= teams || f >= n) return;
-  const int beg = offsets[f], len = offsets[f + 1] - beg;
-  if (len == 0 || len > kShortList) return;  // empty rows stay zero; long lists belong to the chunk kernel
-  const int c = lane_c * V;
+// List-ordered metadata of the CSC entries, so the gradient kernels read (token, a * s_dec, dpre) with coalesced
+// loads instead of chasing entries -> top_vals / dacts:  dpre = ReLU mask of the selected pre-activation * s_enc.
+__global__ void __launch_bounds__(256) csc_meta_kernel(const int32_t* __restrict__ offsets,
+                                                       const int32_t* __restrict__ entries,
+                                                       const float* __restrict__ top_vals,
+                                                       const float* __restrict__ dacts, const float* __restrict__ scales,
+                                                       int32_t* __restrict__ tok, float* __restrict__ a_sc,
+                                                       float* __restrict__ dp_sc, int n, int k) {
+  const int total = offsets[n];  // entries owned by other feature shards are not in the index
   const float s_dec = scales[0], s_enc = scales[1];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int p = __ldg(entries + i);
+    const float a = __ldg(top_vals + p);
+    tok[i] = p / k;
+    a_sc[i] = a * s_dec;
+    dp_sc[i] = a > 0.f ? __ldg(dacts + p) * s_enc : 0.f;
+  }
+}
+
+// Short lists (a wide dictionary has N*k/n entries per feature on average): one WARP per (32-slice column slab,
+// feature) item, slab-major (blockIdx.y = slab): the CTAs resident at any moment all gather the same 512-byte
+// column slab of g and xc (2 * N * 512 B: 49 MB at N = 48000), which stays in L2 however wide the rows are.
+// The warp reads the metadata of up to 32 entries with one coalesced load per array, broadcasts it by shuffle
+// (all shuffles of a batch before any load, in converged code), and gathers its 16-byte row slices 8 entries at a
+// time from both matrices.  No shared memory, no barrier, direct row stores -- which also zero the rows of silent
+// features, so the gradient matrices need no memset.  Rows of long lists are zeroed here and accumulated by the
+// chunk kernel.  Lanes past the row end (last slab of a row that is not a multiple of 32 slices) gather column 0
+// and skip the stores, so the warp never diverges.
+template <typename GT, typename XT>
+__global__ void __launch_bounds__(256) sparse_grads_warp_kernel(
+    const int32_t* __restrict__ offsets, const int32_t* __restrict__ tok, const float* __restrict__ a_sc,
+    const float* __restrict__ dp_sc, const GT* __restrict__ g, const XT* __restrict__ xc,
+    const float* __restrict__ b_dec, float* __restrict__ dW_dec, float* __restrict__ dW_enc,
+    float* __restrict__ db_enc, int n, int d, int short_len, int accumulate) {
+  constexpr int V = RowVec<GT>::kVec;
+  constexpr int R = 8;
+  constexpr bool kRecenter = sizeof(XT) == 4;
+  const int lane = threadIdx.x & 31;
+  const uint64_t keep = l2_keep_policy();
+  const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int slab = blockIdx.y;
+  if (f >= n) return;
+  const int c = (slab * 32 + lane) * V;
+  const bool active = c < d;
+  const int cl = active ? c : 0;
+  const int beg = offsets[f], len = offsets[f + 1] - beg;
+  float* pd = dW_dec + static_cast<int64_t>(f) * d + c;
+  float* pe = dW_enc + static_cast<int64_t>(f) * d + c;
+  if (len == 0 || len > short_len) {
+    if (!accumulate) {
+      if (active) {
+#pragma unroll
+        for (int e = 0; e < V; e += 4) {
+          store4_stream(pd + e, make_float4(0, 0, 0, 0));
+          store4_stream(pe + e, make_float4(0, 0, 0, 0));
+        }
+      }
+      if (slab == 0 && lane == 0) db_enc[f] = 0.f;
+    }
+    return;
+  }
   float accd[V], acce[V], bd[V];
 #pragma unroll
   for (int e = 0; e < V; ++e) {
     accd[e] = 0.f;
     acce[e] = 0.f;
-    bd[e] = kRecenter ? b_dec[c + e] : 0.f;
+    bd[e] = kRecenter ? b_dec[cl + e] : 0.f;
   }
+  const GT* gcol = g + cl;
+  const XT* xcol = xc + cl;
   float dpsum = 0.f;
-  int i = 0;
-  for (; i + 4 <= len; i += 4) {
-    float gv[4][V], xv[4][V], a4[4], dp4[4];
+  for (int base = 0; base < len; base += 32) {
+    const int cnt = min(32, len - base);
+    const int my_t = lane < cnt ? __ldg(tok + beg + base + lane) : 0;
+    const float my_a = lane < cnt ? __ldg(a_sc + beg + base + lane) : 0.f;
+    const float my_dp = lane < cnt ? __ldg(dp_sc + beg + base + lane) : 0.f;
+    dpsum += my_dp;
+    for (int jb = 0; jb < cnt; jb += R) {  // slots past the list gather row 0 with zero coefficients
+      int t[R];
+      float a[R], dp[R];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int p = __ldg(entries + beg + i + u);
-      const float a = __ldg(top_vals + p);
-      a4[u] = a * s_dec;
-      dp4[u] = a > 0.f ? __ldg(dacts + p) * s_enc : 0.f;
-      const int64_t t = p / k;
-      RowVec<GT>::load(g + t * d + c, gv[u]);
-      RowVec<XT>::load(xc + t * d + c, xv[u]);
-    }
+      for (int u = 0; u < R; ++u) {
+        t[u] = __shfl_sync(0xffffffffu, my_t, jb + u);
+        a[u] = __shfl_sync(0xffffffffu, my_a, jb + u);
+        dp[u] = __shfl_sync(0xffffffffu, my_dp, jb + u);
+      }
+      uint4 rg[R], rx[R];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      dpsum += dp4[u];
+      for (int u = 0; u < R; ++u) {
+        rg[u] = ldg_keep(gcol + static_cast<int64_t>(t[u]) * d, keep);
+        rx[u] = ldg_keep(xcol + static_cast<int64_t>(t[u]) * d, keep);
+      }
 #pragma unroll
-      for (int e = 0; e < V; ++e) {
-        accd[e] = fmaf(a4[u], gv[u][e], accd[e]);
-        acce[e] = fmaf(dp4[u], xv[u][e] - bd[e], acce[e]);
+      for (int u = 0; u < R; ++u) {
+        float gv[V], xv[V];
+        RowVec<GT>::unpack(rg[u], gv);
+        RowVec<XT>::unpack(rx[u], xv);
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          accd[e] = fmaf(a[u], gv[e], accd[e]);
+          acce[e] = fmaf(dp[u], kRecenter ? xv[e] - bd[e] : xv[e], acce[e]);
+        }
       }
     }
   }
-  for (; i < len; ++i) {
-    const int p = __ldg(entries + beg + i);
-    const float a = __ldg(top_vals + p);
-    const float dp = a > 0.f ? __ldg(dacts + p) * s_enc : 0.f;
-    const int64_t t = p / k;
-    float gv[V], xv[V];
-    RowVec<GT>::load(g + t * d + c, gv);
-    RowVec<XT>::load(xc + t * d + c, xv);
-    dpsum += dp;
+  if (active) {
 #pragma unroll
-    for (int e = 0; e < V; ++e) {
-      accd[e] = fmaf(a * s_dec, gv[e], accd[e]);
-      acce[e] = fmaf(dp, xv[e] - bd[e], acce[e]);
+    for (int e = 0; e < V; e += 4) {
+      float4 od = make_float4(0, 0, 0, 0), oe = make_float4(0, 0, 0, 0);
+      if (accumulate) {
+        od = load4_stream(pd + e);
+        oe = load4_stream(pe + e);
+      }
+      store4_stream(pd + e, make_float4(od.x + accd[e], od.y + accd[e + 1], od.z + accd[e + 2], od.w + accd[e + 3]));
+      store4_stream(pe + e, make_float4(oe.x + acce[e], oe.y + acce[e + 1], oe.z + acce[e + 2], oe.w + acce[e + 3]));
     }
   }
-  float* pd = dW_dec + static_cast<int64_t>(f) * d + c;
-  float* pe = dW_enc + static_cast<int64_t>(f) * d + c;
-#pragma unroll
-  for (int e = 0; e < V; e += 4) {  // rows were zeroed, or hold earlier decodes when accumulating
-    const float4 od = *reinterpret_cast<const float4*>(pd + e), oe = *reinterpret_cast<const float4*>(pe + e);
-    *reinterpret_cast<float4*>(pd + e) = make_float4(od.x + accd[e], od.y + accd[e + 1], od.z + accd[e + 2], od.w + accd[e + 3]);
-    *reinterpret_cast<float4*>(pe + e) = make_float4(oe.x + acce[e], oe.y + acce[e + 1], oe.z + acce[e + 2], oe.w + acce[e + 3]);
+  if (slab == 0) {
+    dpsum = warp_sum(dpsum);
+    if (lane == 0) db_enc[f] = (accumulate ? db_enc[f] : 0.f) + dpsum;
   }
-  if (lane_c == 0) db_enc[f] += dpsum;
 }
 
 // WHICH: 0 = both gradients in one pass; 1 = dW_dec only (gathers g); 2 = dW_enc + db_enc only (gathers xc).
 // Two single-matrix passes keep the gathered working set (one [N,d] bf16 matrix) inside the 126 MB L2.
 template <typename GT, typename XT, int WHICH>
 __global__ void __launch_bounds__(256) sparse_grads_kernel(
-    const int32_t* __restrict__ offsets, const int32_t* __restrict__ chunk_off, const int32_t* __restrict__ entries,
-    const float* __restrict__ top_vals, const float* __restrict__ dacts, const GT* __restrict__ g,
-    const XT* __restrict__ xc, const float* __restrict__ b_dec, const float* __restrict__ scales,
-    float* __restrict__ dW_dec, float* __restrict__ dW_enc, float* __restrict__ db_enc, int n, int d, int k) {
+    const int32_t* __restrict__ offsets, const int32_t* __restrict__ chunk_off, const int32_t* __restrict__ tok,
+    const float* __restrict__ a_sc, const float* __restrict__ dp_sc, const GT* __restrict__ g,
+    const XT* __restrict__ xc, const float* __restrict__ b_dec, float* __restrict__ dW_dec,
+    float* __restrict__ dW_enc, float* __restrict__ db_enc, int n, int d) {
   constexpr int V = RowVec<GT>::kVec;
   static_assert(RowVec<XT>::kVec == V, "g and xc share a storage type");
   constexpr bool kRecenter = sizeof(XT) == 4;  // fp32 path: xc = x - b_dec recomputed on the fly
@@ -725,14 +774,11 @@ __global__ void __launch_bounds__(256) sparse_grads_kernel(
   const int nchunks = chunk_off[f + 1] - chunk_off[f];
   const int beg = offsets[f] + (item - chunk_off[f]) * kChunk;
   const int cnt = min(kChunk, offsets[f + 1] - beg);
-  const float s_dec = scales[0], s_enc = scales[1];
   float dpsum = 0.f;
   for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-    const int p = entries[beg + i];
-    const float a = top_vals[p];
-    const float dp = a > 0.f ? dacts[p] * s_enc : 0.f;  // ReLU mask of pre_acts at the selected entries
-    tok_s[i] = p / k;
-    a_s[i] = a * s_dec;
+    const float dp = dp_sc[beg + i];
+    tok_s[i] = tok[beg + i];
+    a_s[i] = a_sc[beg + i];
     dp_s[i] = dp;
     dpsum += dp;
   }
@@ -1215,41 +1261,38 @@ extern "C" int freud_csc_build(const int32_t* top_idx, int64_t N, int64_t k, int
 extern "C" int freud_topk_sparse_grads(const int32_t* offsets, const int32_t* entries, const float* top_vals,
                                        const float* dacts, const void* g, int g_is_bf16, const void* xc,
                                        int xc_is_bf16, const float* b_dec, const float* scales, float* dW_dec,
-                                       float* dW_enc, float* db_enc, int32_t* chunk_off, int64_t n_entries,
-                                       int64_t n, int64_t d, int64_t k, int accumulate, void* stream) {
+                                       float* dW_enc, float* db_enc, int32_t* chunk_off, int32_t* meta,
+                                       int64_t n_entries, int64_t n, int64_t d, int64_t k, int accumulate,
+                                       void* stream) {
   FREUD_REQUIRE(n > 0 && d % 4 == 0, "sparse_grads needs d % 4 == 0");
   FREUD_REQUIRE(g_is_bf16 == xc_is_bf16, "g and xc must share a storage type");
   FREUD_REQUIRE(!g_is_bf16 || d % 8 == 0, "bf16 rows need d % 8 == 0");
   FREUD_REQUIRE(xc_is_bf16 || b_dec != nullptr, "fp32 path recomputes x - b_dec and needs b_dec");
-  if (!accumulate) {
-    FREUD_CHECK_CUDA(cudaMemsetAsync(dW_dec, 0, n * d * sizeof(float), STREAM));
-    FREUD_CHECK_CUDA(cudaMemsetAsync(dW_enc, 0, n * d * sizeof(float), STREAM));
-    FREUD_CHECK_CUDA(cudaMemsetAsync(db_enc, 0, n * sizeof(float), STREAM));
-  }
+  FREUD_REQUIRE(n_entries > 0 && n_entries < (1ll << 31), "sparse_grads: entry count out of range");
+  int32_t* tok = meta;
+  float* a_sc = reinterpret_cast<float*>(meta + n_entries);
+  float* dp_sc = reinterpret_cast<float*>(meta + 2 * n_entries);
+  csc_meta_kernel<<<grid_for(n_entries, 256, sm_count() * 8), 256, 0, STREAM>>>(offsets, entries, top_vals, dacts, scales,
+                                                                               tok, a_sc, dp_sc, (int)n, (int)k);
   const int V = g_is_bf16 ? 8 : 4;
   const int tpr = (int)((d + V - 1) / V);
-  // short lists: one row-team per feature (rows that need more than 256 threads keep the chunk kernel only)
-  const int short_len = (tpr <= 256 && d % V == 0) ? kShortList : 0;
-  if (short_len > 0) {
-    const int teams = 256 / tpr;
-    const unsigned tgrid = (unsigned)((n + teams - 1) / teams);
-    const int tthreads = ((teams * tpr + 31) / 32) * 32;
-    if (g_is_bf16)
-      sparse_grads_team_kernel<__nv_bfloat16, __nv_bfloat16><<<tgrid, tthreads, 0, STREAM>>>(
-          offsets, entries, top_vals, dacts, static_cast<const __nv_bfloat16*>(g),
-          static_cast<const __nv_bfloat16*>(xc), b_dec, scales, dW_dec, dW_enc, db_enc, (int)n, (int)d, (int)k, tpr,
-          teams);
-    else
-      sparse_grads_team_kernel<float, float><<<tgrid, tthreads, 0, STREAM>>>(
-          offsets, entries, top_vals, dacts, static_cast<const float*>(g), static_cast<const float*>(xc), b_dec,
-          scales, dW_dec, dW_enc, db_enc, (int)n, (int)d, (int)k, tpr, teams);
-    FREUD_CHECK_CUDA(cudaGetLastError());
-  }
-  chunk_scan_kernel<<<1, 1024, 0, STREAM>>>(offsets, chunk_off, (int)n, short_len);
-  // chunk items only exist for lists longer than short_len: at most n_entries / short_len such features
+  // short lists (and the zero fill of every other row): one warp per (feature, 32-slice slab)
+  const int slabs = (tpr + 31) / 32;
+  const dim3 wgrid((unsigned)((n + 7) / 8), (unsigned)slabs);
+  if (g_is_bf16)
+    sparse_grads_warp_kernel<__nv_bfloat16, __nv_bfloat16><<<wgrid, 256, 0, STREAM>>>(
+        offsets, tok, a_sc, dp_sc, static_cast<const __nv_bfloat16*>(g), static_cast<const __nv_bfloat16*>(xc), b_dec,
+        dW_dec, dW_enc, db_enc, (int)n, (int)d, kShortList, accumulate);
+  else
+    sparse_grads_warp_kernel<float, float><<<wgrid, 256, 0, STREAM>>>(
+        offsets, tok, a_sc, dp_sc, static_cast<const float*>(g), static_cast<const float*>(xc), b_dec, dW_dec, dW_enc,
+        db_enc, (int)n, (int)d, kShortList, accumulate);
+  FREUD_CHECK_CUDA(cudaGetLastError());
+  chunk_scan_kernel<<<1, 1024, 0, STREAM>>>(offsets, chunk_off, (int)n, kShortList);
+  // chunk items only exist for lists longer than kShortList: at most n_entries / kShortList such features
   int64_t max_items = n_entries / kChunk + n;
-  if (short_len > 0 && n_entries / kChunk + n_entries / short_len + 1 < max_items)
-    max_items = n_entries / kChunk + n_entries / short_len + 1;
+  if (n_entries / kChunk + n_entries / kShortList + 1 < max_items)
+    max_items = n_entries / kChunk + n_entries / kShortList + 1;
   const int groups = tpr > 256 ? 1 : (256 / tpr > 0 ? 256 / tpr : 1);
   const size_t smem = static_cast<size_t>(groups) * 2 * d * sizeof(float);
   FREUD_REQUIRE(smem + 3 * kChunk * 4 + 64 <= 227 * 1024, "activation size too wide for sparse_grads");
@@ -1261,9 +1304,9 @@ extern "C" int freud_topk_sparse_grads(const int32_t* offsets, const int32_t* en
     auto kern = sparse_grads_kernel<GT, GT, WHICH>;                                                                  \
     if (smem > 32 * 1024)                                                                                            \
       FREUD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
-    kern<<<(unsigned)max_items, 256, smem, STREAM>>>(offsets, chunk_off, entries, top_vals, dacts,                   \
+    kern<<<(unsigned)max_items, 256, smem, STREAM>>>(offsets, chunk_off, tok, a_sc, dp_sc,                           \
                                                      static_cast<const GT*>(g), static_cast<const GT*>(xc), b_dec,   \
-                                                     scales, dW_dec, dW_enc, db_enc, (int)n, (int)d, (int)k);       \
+                                                     dW_dec, dW_enc, db_enc, (int)n, (int)d);                        \
   } while (0)
   if (g_is_bf16) {
     if (split) {

@@ -233,10 +233,11 @@ def topk_sparse_grads(offsets, entries, top_vals, dacts, g, xc, b_dec, scales, d
                       accumulate: bool):
     n, d = dW_dec.shape
     chunk_off = torch.empty(n + 1, dtype=torch.int32, device=dW_dec.device)
+    meta = torch.empty(3 * entries.numel(), dtype=torch.int32, device=dW_dec.device)
     call("freud_topk_sparse_grads", _ptr(offsets), _ptr(entries), _ptr(top_vals), _ptr(dacts), _ptr(g),
          int(g.dtype == torch.bfloat16), _ptr(xc), int(xc.dtype == torch.bfloat16), _ptr(b_dec), _ptr(scales),
-         _ptr(dW_dec), _ptr(dW_enc), _ptr(db_enc), _ptr(chunk_off), entries.numel(), n, d, k, int(accumulate),
-         _stream())
+         _ptr(dW_dec), _ptr(dW_enc), _ptr(db_enc), _ptr(chunk_off), _ptr(meta), entries.numel(), n, d, k,
+         int(accumulate), _stream())
 
 
 def topk_bdec_grad(colsum, scales, db_enc, W_enc, db_dec, accumulate: bool):

@@ -144,13 +144,15 @@ int freud_csc_build(const int32_t* top_idx, int64_t N, int64_t k, int64_t n, int
  *   dW_enc[f,:] (+)= sum_p dpre[p] * xc[t(p),:]        db_enc[f] (+)= sum_p dpre[p]
  * s_dec = scales[0], s_enc = scales[1] (device floats).  g / xc: bf16 [N,d], or fp32 with xc = x - b_dec
  * recomputed from x and b_dec when xc_is_bf16 == 0.  accumulate != 0 adds to the existing gradients.
- * Lists are split into chunks of 1024 entries (one CTA each); chunk_off is an int32 [n+1] workspace,
- * n_entries = N*k the length of `entries`. */
+ * Lists of up to 192 entries are walked by one warp per 32-slice column slab, longer ones in chunks of 1024
+ * entries (one CTA each).  Workspaces: chunk_off int32 [n+1]; meta int32 [3 * n_entries] (list-ordered token,
+ * a * s_dec and dpre planes); n_entries = N*k the length of `entries`.  Every row of dW_dec / dW_enc / db_enc is
+ * written (accumulate == 0) or added to (accumulate != 0); no memset is needed beforehand. */
 int freud_topk_sparse_grads(const int32_t* offsets, const int32_t* entries, const float* top_vals,
                             const float* dacts, const void* g, int g_is_bf16, const void* xc,
                             int xc_is_bf16, const float* b_dec, const float* scales,
-                            float* dW_dec, float* dW_enc, float* db_enc, int32_t* chunk_off, int64_t n_entries,
-                            int64_t n, int64_t d, int64_t k, int accumulate, void* stream);
+                            float* dW_dec, float* dW_enc, float* db_enc, int32_t* chunk_off, int32_t* meta,
+                            int64_t n_entries, int64_t n, int64_t d, int64_t k, int accumulate, void* stream);
 
 /* db_dec[c] (+)= s * colsum[c] - sum_f db_enc_part[f] * W_enc[f,c]   (s = scales[0]; either term may be
  * skipped with a NULL pointer).  Autograd of `x - b_dec` (:74) and `+ b_dec` (:91). */
