@@ -49,7 +49,8 @@ SIGNATURES = {
     "freud_shard_localize": [_p, _p, _p, _p, _i64, _i64, _i64, _p],
     "freud_residual": [_p, _p, _p, _i, _p, _p, _i64, _i64, _p],
     "freud_csc_build": [_p, _i64, _i64, _i64, _p, _p, _p, _p],
-    "freud_topk_sparse_grads": [_p, _p, _p, _p, _p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i, _p],
+    "freud_csc_meta": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _p],
+    "freud_topk_sparse_grads": [_p, _p, _p, _i, _p, _i, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i, _p],
     "freud_topk_bdec_grad": [_p, _p, _p, _p, _p, _i64, _i64, _i, _p],
     "freud_topk_loss_scalars": [_p, _p, _p, _i64, _p],
     "freud_dead_latent_update": [_p, _p, _i64, _i64, _p],
@@ -59,6 +60,7 @@ SIGNATURES = {
     "freud_l1_loss_reduce": [_p, _p, _p, _p, _p, _i64, _i64, _i64, _p],
     "freud_l1_dz": [_p, _p, _p, _p, _i64, _i64, _p],
     "freud_l1_weight_grad": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _p],
+    "freud_l1_grad_operands": [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _p],
     "freud_grad_sumsq": [C.POINTER(TensorList), _p, _p],
     "freud_clip_grads": [C.POINTER(TensorList), _p, _f, _p, _p],
     "freud_adam_step": [C.POINTER(TensorList), _d, _d, _d, _d, _i64, _p, _f, _p],
@@ -75,9 +77,9 @@ KERNELS_PER_CALL = {
     "freud_topk_prep_x": 1, "freud_split_operand": 1, "freud_topk_encode": 1, "freud_gemm_nt": 1,
     "freud_row_topk": 1, "freud_gather_rows": 1, "freud_index_map": 1, "freud_row_topk_mask": 1, "freud_transpose_bf16": 1, "freud_mask_grad": 1, "freud_scatter_add_rows": 1, "freud_gemm_nt_splitk": 1, "freud_sum_splits": 1,
     "freud_topk_decode": 1, "freud_topk_dacts": 1, "freud_axpby": 1, "freud_shard_merge": 1, "freud_shard_localize": 1, "freud_residual": 1, "freud_csc_build": 4,
-    "freud_topk_sparse_grads": 4, "freud_topk_bdec_grad": 1, "freud_topk_loss_scalars": 1,
+    "freud_csc_meta": 1, "freud_topk_sparse_grads": 3, "freud_topk_bdec_grad": 1, "freud_topk_loss_scalars": 1,
     "freud_dead_latent_update": 1, "freud_rownorm_project": 1, "freud_remove_parallel_grad": 1,
-    "freud_l1_colnorm": 1, "freud_l1_loss_reduce": 1, "freud_l1_dz": 1, "freud_l1_weight_grad": 1,
+    "freud_l1_colnorm": 1, "freud_l1_loss_reduce": 1, "freud_l1_dz": 1, "freud_l1_weight_grad": 1, "freud_l1_grad_operands": 1,
     "freud_grad_sumsq": 1, "freud_clip_grads": 1, "freud_adam_step": 1, "freud_radam_step": 1,
     "freud_feature_absmax": 1, "freud_col_absmax": 1,
     "freud_search_dense": 1, "freud_search_indexed": 1, "freud_search_topn": 1,

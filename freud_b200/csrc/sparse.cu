@@ -1258,22 +1258,29 @@ extern "C" int freud_csc_build(const int32_t* top_idx, int64_t N, int64_t k, int
   return 0;
 }
 
-extern "C" int freud_topk_sparse_grads(const int32_t* offsets, const int32_t* entries, const float* top_vals,
-                                       const float* dacts, const void* g, int g_is_bf16, const void* xc,
-                                       int xc_is_bf16, const float* b_dec, const float* scales, float* dW_dec,
-                                       float* dW_enc, float* db_enc, int32_t* chunk_off, int32_t* meta,
-                                       int64_t n_entries, int64_t n, int64_t d, int64_t k, int accumulate,
-                                       void* stream) {
+extern "C" int freud_csc_meta(const int32_t* offsets, const int32_t* entries, const float* top_vals,
+                              const float* dacts, const float* scales, int32_t* meta, int64_t n_entries, int64_t n,
+                              int64_t k, void* stream) {
+  FREUD_REQUIRE(n_entries > 0 && n_entries < (1ll << 31) && n > 0 && k > 0, "csc_meta: sizes out of range");
+  csc_meta_kernel<<<grid_for(n_entries, 256, sm_count() * 8), 256, 0, STREAM>>>(
+      offsets, entries, top_vals, dacts, scales, meta, reinterpret_cast<float*>(meta + n_entries),
+      reinterpret_cast<float*>(meta + 2 * n_entries), (int)n, (int)k);
+  FREUD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int freud_topk_sparse_grads(const int32_t* offsets, const int32_t* meta, const void* g, int g_is_bf16,
+                                       const void* xc, int xc_is_bf16, const float* b_dec, float* dW_dec,
+                                       float* dW_enc, float* db_enc, int32_t* chunk_off, int64_t n_entries,
+                                       int64_t n, int64_t d, int64_t k, int accumulate, void* stream) {
   FREUD_REQUIRE(n > 0 && d % 4 == 0, "sparse_grads needs d % 4 == 0");
   FREUD_REQUIRE(g_is_bf16 == xc_is_bf16, "g and xc must share a storage type");
   FREUD_REQUIRE(!g_is_bf16 || d % 8 == 0, "bf16 rows need d % 8 == 0");
   FREUD_REQUIRE(xc_is_bf16 || b_dec != nullptr, "fp32 path recomputes x - b_dec and needs b_dec");
   FREUD_REQUIRE(n_entries > 0 && n_entries < (1ll << 31), "sparse_grads: entry count out of range");
-  int32_t* tok = meta;
-  float* a_sc = reinterpret_cast<float*>(meta + n_entries);
-  float* dp_sc = reinterpret_cast<float*>(meta + 2 * n_entries);
-  csc_meta_kernel<<<grid_for(n_entries, 256, sm_count() * 8), 256, 0, STREAM>>>(offsets, entries, top_vals, dacts, scales,
-                                                                               tok, a_sc, dp_sc, (int)n, (int)k);
+  const int32_t* tok = meta;
+  const float* a_sc = reinterpret_cast<const float*>(meta + n_entries);
+  const float* dp_sc = reinterpret_cast<const float*>(meta + 2 * n_entries);
   const int V = g_is_bf16 ? 8 : 4;
   const int tpr = (int)((d + V - 1) / V);
   // short lists (and the zero fill of every other row): one warp per (feature, 32-slice slab)

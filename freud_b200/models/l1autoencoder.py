@@ -83,8 +83,13 @@ class _L1ForwardFn(torch.autograd.Function):
         # dc (unscaled) = dxhat_raw @ W  as  A = dxhat [N, K=d], B = W^T [n, K=d]
         dx_ops = _gemm_operands(dxhat, precision)
         dc = ops.gemm_nt(dx_ops[0], dx_ops[1], wt_ops[0], wt_ops[1], None, False, precision)
-        db = ops.l1_dz(dc, latent, torch.stack((s_recon, s_l1)))              # dc becomes dz in place
-        dW = ops.l1_weight_grad(x2, dc, dxhat, latent, torch.stack((torch.ones_like(s_recon), s_recon)))
+        if precision == BF16:
+            # tensor-core path: dz formed while packing the K-major operands, dW = [x^T | s dxhat^T] @ [dz | c]
+            dW, db = ops.l1_weight_grad_tc(x2, dxhat, dc, latent,
+                                           torch.stack((s_recon, s_l1, torch.ones_like(s_recon), s_recon)))
+        else:
+            db = ops.l1_dz(dc, latent, torch.stack((s_recon, s_l1)))          # dc becomes dz in place
+            dW = ops.l1_weight_grad(x2, dc, dxhat, latent, torch.stack((torch.ones_like(s_recon), s_recon)))
         ctx.saved = None
         return None, dW, db, None, None
 

@@ -232,12 +232,15 @@ def csc_build(top_idx: torch.Tensor, n: int):
 def topk_sparse_grads(offsets, entries, top_vals, dacts, g, xc, b_dec, scales, dW_dec, dW_enc, db_enc, k,
                       accumulate: bool):
     n, d = dW_dec.shape
-    chunk_off = torch.empty(n + 1, dtype=torch.int32, device=dW_dec.device)
-    meta = torch.empty(3 * entries.numel(), dtype=torch.int32, device=dW_dec.device)
-    call("freud_topk_sparse_grads", _ptr(offsets), _ptr(entries), _ptr(top_vals), _ptr(dacts), _ptr(g),
-         int(g.dtype == torch.bfloat16), _ptr(xc), int(xc.dtype == torch.bfloat16), _ptr(b_dec), _ptr(scales),
-         _ptr(dW_dec), _ptr(dW_enc), _ptr(db_enc), _ptr(chunk_off), _ptr(meta), entries.numel(), n, d, k,
-         int(accumulate), _stream())
+    dev = dW_dec.device
+    n_entries = entries.numel()
+    meta = torch.empty(3 * n_entries, dtype=torch.int32, device=dev)
+    chunk_off = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    call("freud_csc_meta", _ptr(offsets), _ptr(entries), _ptr(top_vals), _ptr(dacts), _ptr(scales), _ptr(meta),
+         n_entries, n, k, _stream())
+    call("freud_topk_sparse_grads", _ptr(offsets), _ptr(meta), _ptr(g), int(g.dtype == torch.bfloat16), _ptr(xc),
+         int(xc.dtype == torch.bfloat16), _ptr(b_dec), _ptr(dW_dec), _ptr(dW_enc), _ptr(db_enc), _ptr(chunk_off),
+         n_entries, n, d, k, int(accumulate), _stream())
 
 
 def topk_bdec_grad(colsum, scales, db_enc, W_enc, db_dec, accumulate: bool):
@@ -298,6 +301,22 @@ def l1_weight_grad(x, dz, dxhat, latent, scales):
     call("freud_l1_weight_grad", _ptr(x), _ptr(dz), _ptr(dxhat), _ptr(latent), _ptr(scales), _ptr(dW), N, d, n,
          _stream())
     return dW
+
+
+def l1_weight_grad_tc(x, dxhat, dc, latent, scales4):
+    """bf16-mode tied weight gradient on the tensor cores: (dW [d,n], db [n]) from one operand-packing pass over
+    the activations and a split-K GEMM over K = 2 * tokens.  scales4 = (s_recon, s_l1, s0, s1) device floats."""
+    N, d = x.shape
+    n = latent.shape[1]
+    Np = (N + 63) // 64 * 64
+    At = torch.empty((d, 2 * Np), dtype=torch.bfloat16, device=x.device)
+    Bt = torch.empty((n, 2 * Np), dtype=torch.bfloat16, device=x.device)
+    db = torch.empty(n, dtype=torch.float32, device=x.device)
+    call("freud_l1_grad_operands", _ptr(x), _ptr(dxhat), _ptr(dc), _ptr(latent), _ptr(scales4), _ptr(At), _ptr(Bt),
+         _ptr(db), N, Np, d, n, _stream())
+    row_blocks = (d + 127) // 128
+    splits = max(1, min((2 * Np) // 64, -(-148 // row_blocks)))  # one CTA per SM
+    return gemm_nt_splitk(At, Bt, splits), db
 
 
 # ------------------------------------------------------------------------------------------------ optimiser

@@ -15,6 +15,15 @@ class DataParallel:
         self.group = group
         self.world_size = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        self._side = None
+
+    def side_stream(self):
+        """CUDA stream for the scalar-sized exchanges (variance, SSE, fire counts): they and their small torch
+        kernels run beside the encoder / backward kernels instead of stalling the main stream for a collective's
+        launch latency each.  None without CUDA (gloo tests)."""
+        if self._side is None and torch.cuda.is_available():
+            self._side = torch.cuda.Stream()
+        return self._side
 
     def all_reduce_sum(self, t: torch.Tensor) -> torch.Tensor:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
@@ -29,9 +38,14 @@ class DataParallel:
         tv = tv_local + between
         return self.all_reduce_sum(tv)
 
-    def all_reduce_grads(self, grads):
+    def all_reduce_grads(self, grads, flat=None):
         """One fp32 gradient allreduce (sum) per step over a single flat bucket: NVSwitch makes collective cost
-        latency- rather than link-bound, so one large message beats many small ones."""
+        latency- rather than link-bound, so one large message beats many small ones (overlapping four row-range
+        reductions with the backward was measured: 4.01 vs 3.94 ms per C3 step at 2 GPUs, not adopted).
+        `flat`: the buffer the gradients are views of, when the caller laid them out that way (no copies)."""
+        if flat is not None:
+            self.all_reduce_sum(flat)
+            return
         flat = torch.cat([g.reshape(-1) for g in grads])
         self.all_reduce_sum(flat)
         off = 0

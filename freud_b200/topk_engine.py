@@ -40,6 +40,8 @@ class TopKState:
     multi: Optional[tuple] = None   # (m_vals, m_idx, resid_m fp32, colsum_m)
     auxk_alpha: float = 0.0
     offsets: Optional[torch.Tensor] = None  # CSC offsets of the returned encoding (did_fire bookkeeping)
+    scal_ready: Optional[torch.cuda.Event] = None  # set when `scal` is still being produced on a side stream
+    csc_ready: Optional[torch.cuda.Event] = None   # recorded once `offsets` is complete on the main stream
     extra: dict = field(default_factory=dict)
 
 
@@ -60,15 +62,25 @@ def encode_operands(x, W_enc, b_dec, precision, dp=None):
     else:
         # data parallel: variance of the CONCATENATED batch = sum_r tv_r + sum_r B_r * sum (mean_r - mean)^2
         xc_hi, xc_lo, tv, colmean = ops.topk_prep_x(x, b_dec, precision, want_colmean=True)
-        tv = dp.global_total_variance(tv, colmean, x.shape[0])
+        side = dp.side_stream()
+        if side is None:
+            tv = dp.global_total_variance(tv, colmean, x.shape[0])
+        else:  # the two small allreduces + their torch kernels run beside the encoder; joined before the loss scalars
+            side.wait_stream(torch.cuda.current_stream())
+            tv.record_stream(side)
+            colmean.record_stream(side)
+            with torch.cuda.stream(side):
+                tv = dp.global_total_variance(tv, colmean, x.shape[0])
     we_hi, we_lo = ops.split_operand(W_enc, precision)
     return xc_hi, xc_lo, we_hi, we_lo, tv
 
 
 def topk_forward(x, W_enc, b_enc, W_dec, b_dec, k, *, precision, dead_mask=None, auxk_alpha=0.0, multi_topk=False,
-                 need_grad=True, dp=None):
+                 need_grad=True, dp=None, defer_scal=False):
     """dp: optional freud_b200.parallel.DataParallel -- makes tv / sse (and with them every loss and gradient
-    scale) those of the batch concatenated over ranks; gradients stay rank-local sums for the caller to allreduce."""
+    scale) those of the batch concatenated over ranks; gradients stay rank-local sums for the caller to allreduce.
+    defer_scal (data parallel, fused main path only): the loss scalars are produced on dp's side stream and the
+    main stream is NOT joined; st.scal_ready is the event to wait for before reading them (topk_backward does)."""
     if x.dim() != 3:
         raise ValueError("x must be [B, T, d]")
     x = x.contiguous()
@@ -98,12 +110,32 @@ def topk_forward(x, W_enc, b_enc, W_dec, b_dec, k, *, precision, dead_mask=None,
     sae_out, e, sse, colsum_e = ops.topk_decode(vals, idx, wd, b_dec, x2, resid_dtype=resid_dtype, want_sse=True,
                                                 want_colsum=need_grad)
     numel = N * d
+    scal_ready = None
+    side = dp.side_stream() if dp is not None else None
     if dp is not None:
-        sse = dp.all_reduce_sum(sse)
         numel *= dp.world_size
-    scal = ops.topk_loss_scalars(sse, tv, numel)
+    if side is None:
+        if dp is not None:
+            sse = dp.all_reduce_sum(sse)
+        scal = ops.topk_loss_scalars(sse, tv, numel)
+    else:
+        # SSE allreduce + loss scalars on the side stream (which already holds the global variance); the main
+        # stream joins here, or -- defer_scal -- only where the backward first needs the gradient scale
+        cur = torch.cuda.current_stream()
+        side.wait_stream(cur)
+        sse.record_stream(side)
+        with torch.cuda.stream(side):
+            sse = dp.all_reduce_sum(sse)
+            scal = ops.topk_loss_scalars(sse, tv, numel)
+            scal_ready = side.record_event()
+        scal.record_stream(cur)
+        tv.record_stream(cur)
+        if not (defer_scal and not generic):
+            cur.wait_event(scal_ready)
+            scal_ready = None
     st = TopKState(precision, x2, xc_hi, wd, W_enc, b_dec, k, n, scal, generic, vals, idx, e, colsum_e,
                    auxk_alpha=auxk_alpha)
+    st.scal_ready = scal_ready
 
     auxk = zero
     if num_dead > 0:
@@ -178,6 +210,9 @@ def topk_backward(st: TopKState, g_fvu, g_aux=None, g_multi=None, *, out=None):
     two_over_tv = st.scal[2]
 
     if not st.generic:
+        if st.scal_ready is not None and not (isinstance(g_fvu, float) and g_fvu == 1.0):
+            torch.cuda.current_stream().wait_event(st.scal_ready)  # the scale is about to be read by a torch kernel
+            st.scal_ready = None
         if isinstance(g_fvu, torch.Tensor):
             scales = st.scal[2:4] * g_fvu.to(torch.float32)
         elif g_fvu == 1.0:
@@ -187,6 +222,10 @@ def topk_backward(st: TopKState, g_fvu, g_aux=None, g_multi=None, *, out=None):
         dacts = ops.topk_dacts(st.e, st.idx, st.wd)
         offsets, entries = ops.csc_build(st.idx, n)
         st.offsets = offsets
+        st.csc_ready = torch.cuda.current_stream().record_event()
+        if st.scal_ready is not None:  # gradient scale produced on the data-parallel side stream
+            torch.cuda.current_stream().wait_event(st.scal_ready)
+            st.scal_ready = None
         ops.topk_sparse_grads(offsets, entries, st.vals, dacts, st.e, xc, st.b_dec, scales, dW_dec, dW_enc, db_enc,
                               k, False)
         ops.topk_bdec_grad(st.colsum_e, scales, db_enc, st.W_enc, db_dec, False)

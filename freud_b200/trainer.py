@@ -70,8 +70,14 @@ class SAETrainer:
             self.num_frames_since_fired = torch.zeros(model.n_dict_components, device=dev, dtype=torch.long)
             self.params = {"encoder.weight": model.encoder.weight, "encoder.bias": model.encoder.bias,
                            "W_dec": model.W_dec, "b_dec": model.b_dec}
-            for p in self.params.values():
-                p.grad = torch.zeros_like(p)
+            # gradients are views of one flat fp32 buffer: data parallel reduces it in a single call, no copies
+            flat = torch.zeros(sum(p.numel() for p in self.params.values()), dtype=torch.float32, device=dev)
+            off = 0
+            for key in _TOPK_KEYS:
+                p = self.params[key]
+                p.grad = flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+            self._flat_grad = flat
             # load torch's lazily-initialised kernels for the dead-mask read-back now, not in the first step that
             # crosses the threshold (a one-off ~60 ms module load otherwise lands inside the training loop)
             int((self.num_frames_since_fired > (dead_feature_threshold or 0)).sum())
@@ -92,13 +98,23 @@ class SAETrainer:
         res, st = topk_engine.topk_forward(x, m.encoder.weight.data, m.encoder.bias.data, m.W_dec.data,
                                            m.b_dec.data, cfg.k, precision=self.precision, dead_mask=dead_mask,
                                            auxk_alpha=float(cfg.auxk_alpha), multi_topk=bool(cfg.multi_topk),
-                                           need_grad=True, dp=self.dp)
+                                           need_grad=True, dp=self.dp, defer_scal=self.dp is not None)
         # loss = fvu + auxk_loss + multi_topk_fvu / 8   (train_sae.py:441)
         grads = {k: p.grad for k, p in self.params.items()}
         topk_engine.topk_backward(st, 1.0, 1.0, 1.0 / 8.0, out=grads)
         glist = [self.params[k].grad for k in _TOPK_KEYS]
+        fired_done = None
         if self.dp is not None:
-            self.dp.all_reduce_grads(glist)
+            side = self.dp.side_stream()
+            if side is not None and st.csc_ready is not None:
+                # did_fire over all ranks (train_sae.py:442-446 on the concatenated batch): exchanged on the side
+                # stream as soon as the CSC index exists, beside the weight-gradient kernels
+                side.wait_event(st.csc_ready)
+                st.offsets.record_stream(side)
+                with torch.cuda.stream(side):
+                    self._update_fired_dp(st.offsets, n_tokens)
+                    fired_done = side.record_event()
+            self.dp.all_reduce_grads(glist, flat=self._flat_grad)
         tl = ops.make_tensor_list([self.params[k].data for k in _TOPK_KEYS], glist)
         sumsq = ops.grad_sumsq(tl, x.device)
         self.optimizer.step(grad_sumsq=sumsq)  # clip_grad_norm_ + optimizer.step (train_sae.py:449-450), fused
@@ -109,12 +125,10 @@ class SAETrainer:
             offsets, _ = ops.csc_build(res.top_idx, m.n_dict_components)
         if self.dp is None:
             ops.dead_latent_update(offsets, self.num_frames_since_fired, n_tokens)
+        elif fired_done is not None:
+            torch.cuda.current_stream().wait_event(fired_done)
         else:
-            counts = (offsets[1:] - offsets[:-1]).contiguous()
-            self.dp.all_reduce_sum(counts)
-            f = self.num_frames_since_fired
-            f.add_(n_tokens)
-            f.masked_fill_(counts > 0, 0)
+            self._update_fired_dp(offsets, n_tokens)
         self.tokens_seen += n_tokens
         self.last_state = st
         if st.generic:
@@ -123,6 +137,13 @@ class SAETrainer:
             loss = res.fvu
         return {"loss": loss, "fvu": res.fvu, "auxk_loss": res.auxk_loss, "multi_topk_fvu": res.multi_topk_fvu,
                 "grad_sumsq": sumsq, "top_idx": res.top_idx, "top_acts": res.top_acts, "sae_out": res.sae_out}
+
+    def _update_fired_dp(self, offsets, n_tokens):
+        counts = (offsets[1:] - offsets[:-1]).contiguous()
+        self.dp.all_reduce_sum(counts)
+        f = self.num_frames_since_fired
+        f.add_(n_tokens)
+        f.masked_fill_(counts > 0, 0)
 
     # ------------------------------------------------------------------------------------------ L1
     def _l1_step(self, x):

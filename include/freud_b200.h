@@ -142,17 +142,20 @@ int freud_csc_build(const int32_t* top_idx, int64_t N, int64_t k, int64_t n, int
  *   dW_dec[f,:] (+)= s_dec * sum_{p in list(f)} top_vals[p] * g[t(p),:]
  *   dpre[p]       = top_vals[p] > 0 ? s_enc * dacts[p] : 0
  *   dW_enc[f,:] (+)= sum_p dpre[p] * xc[t(p),:]        db_enc[f] (+)= sum_p dpre[p]
- * s_dec = scales[0], s_enc = scales[1] (device floats).  g / xc: bf16 [N,d], or fp32 with xc = x - b_dec
- * recomputed from x and b_dec when xc_is_bf16 == 0.  accumulate != 0 adds to the existing gradients.
- * Lists of up to 192 entries are walked by one warp per 32-slice column slab, longer ones in chunks of 1024
- * entries (one CTA each).  Workspaces: chunk_off int32 [n+1]; meta int32 [3 * n_entries] (list-ordered token,
- * a * s_dec and dpre planes); n_entries = N*k the length of `entries`.  Every row of dW_dec / dW_enc / db_enc is
- * written (accumulate == 0) or added to (accumulate != 0); no memset is needed beforehand. */
-int freud_topk_sparse_grads(const int32_t* offsets, const int32_t* entries, const float* top_vals,
-                            const float* dacts, const void* g, int g_is_bf16, const void* xc,
-                            int xc_is_bf16, const float* b_dec, const float* scales,
-                            float* dW_dec, float* dW_enc, float* db_enc, int32_t* chunk_off, int32_t* meta,
-                            int64_t n_entries, int64_t n, int64_t d, int64_t k, int accumulate, void* stream);
+ * freud_csc_meta first lays the per-entry terms out in list order: meta int32 [3 * n_entries] = token t(p),
+ * top_vals[p] * s_dec and dpre[p] planes (s_dec = scales[0], s_enc = scales[1], device floats; n_entries = N*k).
+ * freud_topk_sparse_grads then walks the lists: up to 192 entries by one warp per 32-slice column slab, longer
+ * ones in chunks of 1024 entries (one CTA each; chunk_off is an int32 [n+1] workspace).  g / xc: bf16 [N,d], or
+ * fp32 with xc = x - b_dec recomputed from x and b_dec when xc_is_bf16 == 0.  Every row of dW_dec / dW_enc /
+ * db_enc is written (accumulate == 0) or added to (accumulate != 0); no memset is needed beforehand.
+ * A contiguous feature range [f0, f1) can be processed alone by passing offsets + f0, the row / element pointers
+ * of f0 and n = f1 - f0 (the lists keep their absolute positions). */
+int freud_csc_meta(const int32_t* offsets, const int32_t* entries, const float* top_vals, const float* dacts,
+                   const float* scales, int32_t* meta, int64_t n_entries, int64_t n, int64_t k, void* stream);
+int freud_topk_sparse_grads(const int32_t* offsets, const int32_t* meta, const void* g, int g_is_bf16,
+                            const void* xc, int xc_is_bf16, const float* b_dec, float* dW_dec, float* dW_enc,
+                            float* db_enc, int32_t* chunk_off, int64_t n_entries, int64_t n, int64_t d, int64_t k,
+                            int accumulate, void* stream);
 
 /* db_dec[c] (+)= s * colsum[c] - sum_f db_enc_part[f] * W_enc[f,c]   (s = scales[0]; either term may be
  * skipped with a NULL pointer).  Autograd of `x - b_dec` (:74) and `+ b_dec` (:91). */
@@ -193,6 +196,15 @@ int freud_l1_dz(float* dc, const float* latent, const float* scales, float* db, 
  * (autograd of l1autoencoder.py:74,84) as one split-K kernel over the token axis. */
 int freud_l1_weight_grad(const float* x, const float* dz, const float* dxhat, const float* latent,
                          const float* scales, float* dW, int64_t N, int64_t d, int64_t n, void* stream);
+
+/* bf16 mode of the same gradient on the tensor cores: one pass builds the K-major bf16 operands
+ *   At [d, 2*Np] = [ s0 * x^T | s1 * dxhat^T ]      Bt [n, 2*Np] = [ dz^T | c^T ]
+ * (dz = c > 0 ? s_recon * dc + s_l1 : 0 formed on the fly; db[j] = sum_t dz[t,j]; Np = N rounded up to a multiple
+ * of 64, zero padded), after which dW = At @ Bt^T is one freud_gemm_nt_splitk + freud_sum_splits over K = 2*Np.
+ * scales = (s_recon, s_l1, s0, s1) device floats.  Replaces freud_l1_dz + freud_l1_weight_grad. */
+int freud_l1_grad_operands(const float* x, const float* dxhat, const float* dc, const float* latent,
+                           const float* scales, void* At_bf16, void* Bt_bf16, float* db, int64_t N, int64_t Np,
+                           int64_t d, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------ optimiser (train_sae.py:449-450) */
 
