@@ -482,46 +482,49 @@ __global__ void __launch_bounds__(256) csc_hist_kernel(const int32_t* __restrict
   }
 }
 
-// Single-block exclusive scan of counts[0..n) -> offsets[0..n]; cursor[f] = offsets[f].
+// Block-wide exclusive scan of one value per thread (1024 threads); returns the exclusive prefix, *total = sum.
+__device__ __forceinline__ int32_t block_excl_scan_1024(int32_t v, int32_t* warp_tot, int32_t* total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int32_t incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += u;
+  }
+  if (lane == 31) warp_tot[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    int32_t t = warp_tot[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t u = __shfl_up_sync(0xffffffffu, t, o);
+      if (lane >= o) t += u;
+    }
+    warp_tot[lane] = t;
+  }
+  __syncthreads();
+  *total = warp_tot[31];
+  return (w > 0 ? warp_tot[w - 1] : 0) + incl - v;
+}
+
+// Single-block exclusive scan of counts[0..n) -> offsets[0..n]; cursor[f] = offsets[f].  Every thread owns a run
+// of ceil(n/1024) consecutive counts (serial in registers), so the block synchronises once, not once per 1024.
 __global__ void __launch_bounds__(1024) csc_scan_kernel(int32_t* __restrict__ offsets, int32_t* __restrict__ cursor,
                                                         int n) {
   __shared__ int32_t warp_tot[32];
-  __shared__ int32_t carry_s;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (threadIdx.x == 0) carry_s = 0;
-  __syncthreads();
-  for (int base = 0; base < n; base += 1024) {
-    const int i = base + threadIdx.x;
-    const int32_t v = i < n ? offsets[i] : 0;  // offsets holds the raw counts on entry
-    int32_t incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int32_t u = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += u;
-    }
-    if (lane == 31) warp_tot[w] = incl;
-    __syncthreads();
-    if (w == 0) {
-      int32_t t = warp_tot[lane];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int32_t u = __shfl_up_sync(0xffffffffu, t, o);
-        if (lane >= o) t += u;
-      }
-      warp_tot[lane] = t;
-    }
-    __syncthreads();
-    const int32_t carry = carry_s;
-    const int32_t excl = carry + (w > 0 ? warp_tot[w - 1] : 0) + incl - v;
-    if (i < n) {
-      offsets[i] = excl;
-      cursor[i] = excl;
-    }
-    __syncthreads();
-    if (threadIdx.x == 1023) carry_s = carry + warp_tot[31];
-    __syncthreads();
+  const int per = (n + 1023) / 1024;
+  const int lo = min(n, static_cast<int>(threadIdx.x) * per), hi = min(n, lo + per);
+  int32_t sum = 0;
+  for (int i = lo; i < hi; ++i) sum += offsets[i];  // offsets holds the raw counts on entry
+  int32_t total;
+  int32_t run = block_excl_scan_1024(sum, warp_tot, &total);
+  for (int i = lo; i < hi; ++i) {
+    const int32_t v = offsets[i];
+    offsets[i] = run;
+    cursor[i] = run;
+    run += v;
   }
-  if (threadIdx.x == 0) offsets[n] = carry_s;
+  if (threadIdx.x == 0) offsets[n] = total;
 }
 
 __global__ void __launch_bounds__(256) csc_fill_kernel(const int32_t* __restrict__ top_idx, int64_t total,
@@ -539,12 +542,43 @@ __global__ void __launch_bounds__(256) csc_fill_kernel(const int32_t* __restrict
 // gradients -- are run-to-run deterministic despite the atomic fill.  One CTA per feature, bitonic sort in
 // shared memory; lists longer than kSortMax entries are left in fill order (still correct, not bit-stable).
 constexpr int kSortMax = 4096;
+constexpr int kWarpSortMax = 128;
+
+// Lists of up to 128 entries (the common case: N*k/n on average): one warp per feature, 4 entries per lane, rank
+// sort by shuffle broadcast (entries are distinct positions, so rank = number of smaller entries).
+__global__ void __launch_bounds__(256) csc_sort_warp_kernel(const int32_t* __restrict__ offsets,
+                                                            int32_t* __restrict__ entries, int n) {
+  const int lane = threadIdx.x & 31;
+  const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (f >= n) return;
+  const int beg = offsets[f], len = offsets[f + 1] - beg;
+  if (len <= 1 || len > kWarpSortMax) return;
+  int32_t v[4];
+  int rank[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) v[q] = lane + 32 * q < len ? entries[beg + lane + 32 * q] : 0x7fffffff;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (32 * q < len) {  // warp-uniform
+      const int cnt = min(32, len - 32 * q);
+      for (int j = 0; j < cnt; ++j) {
+        const int32_t w = __shfl_sync(0xffffffffu, v[q], j);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) rank[r] += w < v[r];
+      }
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    if (lane + 32 * q < len) entries[beg + rank[q]] = v[q];
+}
 __global__ void __launch_bounds__(256) csc_sort_kernel(const int32_t* __restrict__ offsets,
                                                        int32_t* __restrict__ entries) {
   __shared__ int32_t buf[kSortMax];
   const int f = blockIdx.x;
   const int beg = offsets[f], len = offsets[f + 1] - beg;
-  if (len <= 1 || len > kSortMax) return;
+  if (len <= kWarpSortMax || len > kSortMax) return;  // short lists: csc_sort_warp_kernel
   int m = 2;
   while (m < len) m <<= 1;
   for (int i = threadIdx.x; i < m; i += blockDim.x) buf[i] = i < len ? entries[beg + i] : 0x7fffffff;
@@ -581,42 +615,21 @@ constexpr int kShortList = 192;  // lists up to this length: one row-team per fe
 __global__ void __launch_bounds__(1024) chunk_scan_kernel(const int32_t* __restrict__ offsets,
                                                           int32_t* __restrict__ chunk_off, int n, int short_len) {
   __shared__ int32_t warp_tot[32];
-  __shared__ int32_t carry_s;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (threadIdx.x == 0) carry_s = 0;
-  __syncthreads();
-  for (int base = 0; base < n; base += 1024) {
-    const int i = base + threadIdx.x;
-    int32_t v = 0;
-    if (i < n) {
-      const int32_t len = offsets[i + 1] - offsets[i];
-      v = len > short_len ? (len + kChunk - 1) / kChunk : 0;  // short lists belong to the team kernel
-    }
-    int32_t incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int32_t u = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += u;
-    }
-    if (lane == 31) warp_tot[w] = incl;
-    __syncthreads();
-    if (w == 0) {
-      int32_t t = warp_tot[lane];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int32_t u = __shfl_up_sync(0xffffffffu, t, o);
-        if (lane >= o) t += u;
-      }
-      warp_tot[lane] = t;
-    }
-    __syncthreads();
-    const int32_t carry = carry_s;
-    if (i < n) chunk_off[i] = carry + (w > 0 ? warp_tot[w - 1] : 0) + incl - v;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry_s = carry + warp_tot[31];
-    __syncthreads();
+  const int per = (n + 1023) / 1024;
+  const int lo = min(n, static_cast<int>(threadIdx.x) * per), hi = min(n, lo + per);
+  auto chunks = [&](int i) {
+    const int32_t len = offsets[i + 1] - offsets[i];
+    return len > short_len ? (len + kChunk - 1) / kChunk : 0;  // short lists belong to the warp kernel
+  };
+  int32_t sum = 0;
+  for (int i = lo; i < hi; ++i) sum += chunks(i);
+  int32_t total;
+  int32_t run = block_excl_scan_1024(sum, warp_tot, &total);
+  for (int i = lo; i < hi; ++i) {
+    chunk_off[i] = run;
+    run += chunks(i);
   }
-  if (threadIdx.x == 0) chunk_off[n] = carry_s;
+  if (threadIdx.x == 0) chunk_off[n] = total;
 }
 
 // List-ordered metadata of the CSC entries, so the gradient kernels read (token, a * s_dec, dpre) with coalesced
@@ -1253,6 +1266,7 @@ extern "C" int freud_csc_build(const int32_t* top_idx, int64_t N, int64_t k, int
   csc_hist_kernel<<<grid, 256, 0, STREAM>>>(top_idx, total, offsets);
   csc_scan_kernel<<<1, 1024, 0, STREAM>>>(offsets, cursor, (int)n);
   csc_fill_kernel<<<grid, 256, 0, STREAM>>>(top_idx, total, cursor, entries);
+  csc_sort_warp_kernel<<<(int)((n + 7) / 8), 256, 0, STREAM>>>(offsets, entries, (int)n);
   csc_sort_kernel<<<(int)n, 256, 0, STREAM>>>(offsets, entries);
   FREUD_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -51,7 +51,7 @@ class _L1ForwardFn(torch.autograd.Function):
     """(x, W, b) -> (x_hat, latent, l1_loss, reconstruction_loss, mse); losses carry gradient to W and b."""
 
     @staticmethod
-    def forward(ctx, x2, W, b, recon_alpha, precision):
+    def forward(ctx, x2, W, b, recon_alpha, precision, dp=None):
         N, d = x2.shape
         n = W.shape[1]
         Wt = ops.l1_colnorm(W.data)  # in place on decoder.weight.data + K-major transposed copy
@@ -63,23 +63,27 @@ class _L1ForwardFn(torch.autograd.Function):
         x_hat = ops.gemm_nt(c_ops[0], c_ops[1], w_ops[0], w_ops[1], None, False, precision)      # c @ W.T
         need_grad = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
         acc, dxhat = ops.l1_loss_reduce(latent, x_hat, x2, need_grad)
-        l1 = (acc[0] / N).float()
+        n_glob = N
+        if dp is not None:  # losses (and with them the gradient scales) of the batch concatenated over ranks
+            acc = dp.all_reduce_sum(acc)
+            n_glob = N * dp.world_size
+        l1 = (acc[0] / n_glob).float()
         recon = (recon_alpha * acc[1] / acc[2]).float()
-        mse = (acc[3] / (N * d)).float()
-        ctx.saved = (x2, latent, dxhat, acc, wt_ops, Wt, precision, recon_alpha)
+        mse = (acc[3] / (n_glob * d)).float()
+        ctx.saved = (x2, latent, dxhat, acc, wt_ops, Wt, precision, recon_alpha, n_glob)
         ctx.mark_non_differentiable(x_hat, latent, mse)
         return x_hat, latent, l1, recon, mse
 
     @staticmethod
     def backward(ctx, g_xhat, g_latent, g_l1, g_recon, g_mse):
-        x2, latent, dxhat, acc, wt_ops, Wt, precision, recon_alpha = ctx.saved
+        x2, latent, dxhat, acc, wt_ops, Wt, precision, recon_alpha, n_glob = ctx.saved
         N, d = x2.shape
         dev = x2.device
         zero = torch.zeros((), dtype=torch.float32, device=dev)
         g_l1 = zero if g_l1 is None else g_l1.float()
         g_recon = zero if g_recon is None else g_recon.float()
         s_recon = (g_recon.double() * (2.0 * recon_alpha) / acc[2]).float()   # d recon / d x_hat = 2*alpha*(x_hat-x)/N_unmasked
-        s_l1 = g_l1 / N                                                       # d l1 / d c = 1[c>0]/N
+        s_l1 = g_l1 / n_glob                                                  # d l1 / d c = 1[c>0]/N
         # dc (unscaled) = dxhat_raw @ W  as  A = dxhat [N, K=d], B = W^T [n, K=d]
         dx_ops = _gemm_operands(dxhat, precision)
         dc = ops.gemm_nt(dx_ops[0], dx_ops[1], wt_ops[0], wt_ops[1], None, False, precision)
@@ -91,7 +95,7 @@ class _L1ForwardFn(torch.autograd.Function):
             db = ops.l1_dz(dc, latent, torch.stack((s_recon, s_l1)))          # dc becomes dz in place
             dW = ops.l1_weight_grad(x2, dc, dxhat, latent, torch.stack((torch.ones_like(s_recon), s_recon)))
         ctx.saved = None
-        return None, dW, db, None, None
+        return None, dW, db, None, None, None
 
 
 class L1AutoEncoder(nn.Module):
@@ -109,6 +113,7 @@ class L1AutoEncoder(nn.Module):
         nn.init.orthogonal_(self.decoder.weight)
         self.encoder = nn.Sequential(nn.ReLU())
         self.precision = "auto"
+        self.dp = None  # freud_b200.parallel.DataParallel: losses over the concatenated batch (set by SAETrainer)
 
     def _check(self, x: Tensor):
         if not x.is_cuda:
@@ -141,7 +146,8 @@ class L1AutoEncoder(nn.Module):
         x = self._check(x)
         d = x.shape[-1]
         x_hat, latent, l1, recon, mse = _L1ForwardFn.apply(x.view(-1, d), self.decoder.weight, self.encoder_bias,
-                                                           float(self.recon_alpha), _precision(self.precision))
+                                                           float(self.recon_alpha), _precision(self.precision),
+                                                           self.dp)
         lead = x.shape[:-1]
         c = latent.view(*lead, self.n_dict_components)
         forward_output = L1ForwardOutput(

@@ -147,12 +147,13 @@ class SAETrainer:
 
     # ------------------------------------------------------------------------------------------ L1
     def _l1_step(self, x):
-        if self.dp is not None:
-            raise NotImplementedError("data-parallel L1 training is not implemented in this round")
         self.optimizer.zero_grad(set_to_none=True)
+        self.model.dp = self.dp
         out = self.model(x)
         loss = out.reconstruction_loss + out.l1_loss  # train_sae.py:433-434
         loss.backward()
+        if self.dp is not None:  # rank-local sums of gradients whose scales already are those of the global batch
+            self.dp.all_reduce_grads([p.grad for p in self.model.parameters()])
         self.optimizer.step()
         self.scheduler.step()
         return {"loss": loss.detach(), "loss_recon": out.reconstruction_loss.detach(), "loss_l1": out.l1_loss.detach(),

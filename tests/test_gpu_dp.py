@@ -70,3 +70,53 @@ def test_two_rank_step_equals_single_rank_on_concatenated_batch():
     assert out, "rank 0 reported nothing"
     for k, v in out.items():
         assert v < (1e-12 if k == "frames" else 2e-5), (k, v)
+
+
+def _l1_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from freud_b200.models.config import L1AutoEncoderConfig
+        from freud_b200.models.l1autoencoder import L1AutoEncoder
+        from freud_b200.parallel import DataParallel
+        from freud_b200.trainer import SAETrainer
+
+        def build():
+            torch.manual_seed(0)
+            return L1AutoEncoder(64, L1AutoEncoderConfig.from_dict({"n_dict_components": 96, "recon_alpha": 1e2})).to(dev)
+
+        g = torch.Generator().manual_seed(11)
+        B, T, d = 8, 80, 64
+        xs = [torch.randn(B, T, d, generator=g) for _ in range(3)]
+        xs[1][0, :5] = -1.0  # ignored_index entries: the masked count is a global quantity too
+        kw = dict(lr=4e-4, steps=100, clip_thresh=1.0, optimizer="radam", scheduler="cosine", precision="fp32")
+        tr = SAETrainer(build(), dp=DataParallel(), **kw)
+        per = B // world
+        for x in xs:
+            o = tr.step(x[rank * per:(rank + 1) * per].to(dev))
+        torch.cuda.synchronize()
+        if rank == 0:
+            ref = SAETrainer(build(), dp=None, **kw)
+            for x in xs:
+                r = ref.step(x.to(dev))
+            torch.cuda.synchronize()
+            pa, pb = dict(tr.model.named_parameters()), dict(ref.model.named_parameters())
+            errs = {k: float((pa[k].data - pb[k].data).abs().max() / pb[k].data.abs().max()) for k in pa}
+            for k in ("loss_recon", "loss_l1"):
+                errs[k] = abs(float(o[k]) - float(r[k])) / abs(float(r[k]))
+            out.update(errs)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_rank_l1_step_equals_single_rank_on_concatenated_batch():
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_l1_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert out, "rank 0 reported nothing"
+    for k, v in out.items():
+        assert v < 2e-5, (k, v)
