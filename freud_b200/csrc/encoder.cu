@@ -7,6 +7,76 @@
 
 namespace freud {
 
+// Tail of the fused encoder: rows of a row block whose column tiles were scanned by several CTAs have one sorted
+// top-32 list per piece (indices already global); one warp per row folds them together exactly like
+// shard_merge_kernel does for feature shards (max with the reversed other list + a 5-stage bitonic merge).
+__device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src) {
+  const uint32_t lo = __shfl_sync(0xffffffffu, static_cast<uint32_t>(v), src);
+  const uint32_t hi = __shfl_sync(0xffffffffu, static_cast<uint32_t>(v >> 32), src);
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+__global__ void __launch_bounds__(256) topk_merge_pieces_kernel(const float* __restrict__ part_vals,
+                                                                const int32_t* __restrict__ part_idx,
+                                                                int64_t part_stride, float* __restrict__ top_vals,
+                                                                int32_t* __restrict__ top_idx, int M, int row0,
+                                                                int pieces) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = row0 + static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  uint64_t cur = 0;
+  for (int piece = 0; piece < pieces; ++piece) {
+    const int64_t o = piece * part_stride + row * 32 + lane;
+    const uint64_t key = (static_cast<uint64_t>(__float_as_uint(part_vals[o])) << 32) |
+                         static_cast<uint32_t>(~static_cast<uint32_t>(part_idx[o]));
+    if (piece == 0) {
+      cur = key;
+    } else {
+      const uint64_t rev = shfl_u64(key, 31 - lane);
+      cur = cur > rev ? cur : rev;
+#pragma unroll
+      for (int j = 16; j > 0; j >>= 1) {
+        const uint64_t other = shfl_u64(cur, lane ^ j);
+        const bool lower = (lane & j) == 0;
+        const uint64_t mx = cur > other ? cur : other, mn = cur > other ? other : cur;
+        cur = lower ? mx : mn;
+      }
+    }
+  }
+  top_vals[row * 32 + lane] = __uint_as_float(static_cast<uint32_t>(cur >> 32));
+  top_idx[row * 32 + lane] = static_cast<int32_t>(~static_cast<uint32_t>(cur));
+}
+
+// A batch that is not a multiple of sm_count row blocks would leave SMs idle in its last wave, so the row blocks
+// of that wave are cut into S column ranges scanned by different CTAs.  S minimises the wave count of the tail,
+// charging five tiles per piece (measured on C3: pipeline fill, threshold warm-up and less L2 sharing of the weight
+// tiles; the pieces of a row do share their selection threshold).  Returns S (1 = no split)
+// and the number of row blocks in whole waves.
+static int plan_tail_split(int num_mb, int num_nt, int* full_count) {
+  const int sms = sm_count();
+  const int full = num_mb / sms * sms, tail = num_mb - full;
+  *full_count = full;
+  if (tail == 0 || getenv("FREUD_NO_TAIL_SPLIT")) return 1;
+  int best = 1;
+  double best_cost = 1.0;
+  for (int S = 2; S <= 16 && S * 2 <= num_nt; ++S) {
+    const double waves = static_cast<double>((static_cast<int64_t>(tail) * S + sms - 1) / sms) / S;
+    const double cost = waves * (1.0 + 5.0 * S / num_nt);
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = S;
+    }
+  }
+  if (const char* e = getenv("FREUD_TAIL_SPLIT")) {  // experiments: force the split factor
+    if (atoi(e) >= 1 && atoi(e) * 2 <= num_nt) best = atoi(e);
+  }
+  return best;
+}
+// partial lists [S][rows][32] (values + indices) and the shared per-row thresholds
+static int64_t tail_split_bytes(int num_mb, int S) {
+  const int64_t rows = static_cast<int64_t>(num_mb) * kBM;
+  return S > 1 ? S * rows * 32 * 8 + rows * 4 : 0;
+}
+
 template <int BN, int STAGES, int EPI, bool TF32, int SETS, int CL, int NBUF = 2>
 static int launch_gemm(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, GemmParams p,
                        int passes, cudaStream_t stream) {
@@ -31,6 +101,26 @@ static int launch_gemm(const void* a_hi, const void* a_lo, const void* b_hi, con
   }
   int grid = (p.M + kBM - 1) / kBM;
   grid = (grid + CL - 1) / CL * CL;  // whole clusters; surplus CTAs run the protocol on out-of-range rows
+  // Fused top-k encoder: the row blocks of a last, partial wave are cut into column ranges (plan_tail_split) when
+  // the caller supplied the workspace for the partial lists.
+  const int num_mb = (p.M + kBM - 1) / kBM;
+  const int num_nt = (p.N + BN - 1) / BN;
+  if (EPI == EPI_TOPK && CL == 1 && p.part_vals != nullptr) {
+    int full = 0;
+    const int S = plan_tail_split(num_mb, num_nt, &full);
+    const int64_t stride = static_cast<int64_t>(num_mb) * kBM * 32;
+    if (S > 1 && tail_split_bytes(num_mb, S) <= p.part_stride) {  // part_stride carries the workspace size in
+      p.full_count = full;
+      p.tail_split = S;
+      p.part_stride = stride;
+      p.part_idx = reinterpret_cast<int32_t*>(p.part_vals + S * stride);
+      p.part_thr = reinterpret_cast<float*>(p.part_idx + S * stride);
+      FREUD_CHECK_CUDA(cudaMemsetAsync(p.part_thr, 0, static_cast<size_t>(num_mb) * kBM * sizeof(float), stream));
+      grid = full + (num_mb - full) * S;
+    } else {
+      p.part_vals = nullptr;
+    }
+  }
   cudaLaunchConfig_t cfg{};
   int nsplit = 1;
   if (p.kb_per_split > 0) {
@@ -50,6 +140,12 @@ static int launch_gemm(const void* a_hi, const void* a_lo, const void* b_hi, con
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   FREUD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, mA0, mA1, mB0, mB1, p));
+  if (p.tail_split > 1) {
+    const int row0 = p.full_count * kBM;
+    topk_merge_pieces_kernel<<<(p.M - row0 + 7) / 8, 256, 0, stream>>>(p.part_vals, p.part_idx, p.part_stride, p.top_vals,
+                                                                       p.top_idx, p.M, row0, p.tail_split);
+    FREUD_CHECK_CUDA(cudaGetLastError());
+  }
   return 0;
 }
 
@@ -67,9 +163,18 @@ static int encoder_variant() {
 
 using namespace freud;
 
+extern "C" int freud_topk_encode_workspace(int64_t N, int64_t n, int64_t* bytes) {
+  FREUD_REQUIRE(N > 0 && n >= 64 && bytes != nullptr, "freud_topk_encode_workspace: bad arguments");
+  FREUD_REQUIRE(N < (1ll << 31) && n < (1ll << 31), "sizes exceed int32");
+  const int num_mb = static_cast<int>((N + kBM - 1) / kBM), num_nt = static_cast<int>((n + 255) / 256);
+  int full = 0;
+  *bytes = tail_split_bytes(num_mb, plan_tail_split(num_mb, num_nt, &full));
+  return 0;
+}
+
 extern "C" int freud_topk_encode(const void* xc_hi, const void* xc_lo, const void* w_hi, const void* w_lo,
                                  const float* b_enc, float* top_vals, int32_t* top_idx, int64_t N, int64_t d,
-                                 int64_t n, int precision, void* stream) {
+                                 int64_t n, int precision, void* workspace, int64_t workspace_bytes, void* stream) {
   FREUD_REQUIRE(N > 0 && d > 0 && n >= 64, "freud_topk_encode needs N > 0 and n >= 64");
   FREUD_REQUIRE(d % 8 == 0, "activation size must be a multiple of 8");
   FREUD_REQUIRE(N < (1ll << 31) && n < (1ll << 31), "sizes exceed int32");
@@ -81,6 +186,8 @@ extern "C" int freud_topk_encode(const void* xc_hi, const void* xc_lo, const voi
   p.relu = 1;
   p.top_vals = top_vals;
   p.top_idx = top_idx;
+  p.part_vals = static_cast<float*>(workspace);  // launch_gemm turns these two into the tail-split plan
+  p.part_stride = workspace ? workspace_bytes : 0;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (precision == FREUD_BF16) {
     switch (encoder_variant()) {

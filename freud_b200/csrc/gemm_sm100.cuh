@@ -60,6 +60,20 @@ struct GemmParams {
   // [M, ldo] at out + split * split_stride (bias only in split 0); 0 = no split
   int kb_per_split;
   int64_t split_stride;
+  // Tail split (EPI_TOPK): row blocks [0, full_count) -- whole waves of one CTA per SM -- are scanned by one CTA
+  // each; every row block of the last, partial wave is cut into tail_split column ranges scanned by different CTAs
+  // (CTA full_count + s * tail + i takes range s of tail row block i, so CTAs running together walk the same weight
+  // tiles), each writing a partial top-32 list at part_* + s * part_stride (+ row * 32); topk_merge_pieces_kernel
+  // folds them.  tail_split <= 1: one CTA per row block throughout.
+  int full_count;
+  int tail_split;
+  float* part_vals;
+  int32_t* part_idx;
+  int64_t part_stride;
+  // per-row selection threshold shared by the pieces of a row block (zeroed by the launcher): any piece's 32nd
+  // largest value so far bounds the row's final 32nd largest from below, so later / concurrent pieces start
+  // filtering at once instead of rebuilding a threshold from zero
+  float* part_thr;
 };
 
 template <int BN, int STAGES, int EPI, int SETS, int NBUF = 2>
@@ -183,8 +197,21 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * kBM;
   const int num_nt = (p.N + BN - 1) / BN;
+  // this CTA's run of flattened tiles g = row_block * num_nt + column_tile: a whole row block, or one column range
+  // of a row block of the split tail wave
+  int64_t g_begin = static_cast<int64_t>(blockIdx.x) * num_nt, g_end = g_begin + num_nt;
+  int piece = 0;
+  if (p.tail_split > 1 && static_cast<int>(blockIdx.x) >= p.full_count) {
+    const int tail = (p.M + kBM - 1) / kBM - p.full_count;
+    const int t = static_cast<int>(blockIdx.x) - p.full_count;
+    piece = t / tail;
+    const int64_t base = static_cast<int64_t>(p.full_count + t - piece * tail) * num_nt;
+    g_begin = base + static_cast<int64_t>(piece) * num_nt / p.tail_split;
+    g_end = base + static_cast<int64_t>(piece + 1) * num_nt / p.tail_split;
+  }
+  const int num_lt = static_cast<int>(g_end - g_begin);
+  const bool is_piece = p.tail_split > 1 && static_cast<int>(blockIdx.x) >= p.full_count;
   const int total_kb = (p.K + kBKe - 1) / kBKe;
   const int split = p.kb_per_split > 0 ? static_cast<int>(blockIdx.y) : 0;
   const int kb0 = p.kb_per_split > 0 ? split * p.kb_per_split : 0;
@@ -226,7 +253,10 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int nt = 0; nt < num_nt; ++nt) {
+      for (int lt = 0; lt < num_lt; ++lt) {
+        const int mb = static_cast<int>((g_begin + lt) / num_nt);
+        const int nt = static_cast<int>(g_begin + lt - static_cast<int64_t>(mb) * num_nt);
+        const int m0 = mb * kBM;
         for (int vk = 0; vk < num_vk; ++vk) {
           const int pass = vk / num_kb;
           const int kb = vk - pass * num_kb;
@@ -259,10 +289,10 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       constexpr uint32_t idesc = make_idesc(TF32 ? 2u : 1u, kBM, BN);
       int stage = 0;
       uint32_t phase = 0;
-      for (int nt = 0; nt < num_nt; ++nt) {
-        const int buf = nt % NBUF;
+      for (int lt = 0; lt < num_lt; ++lt) {
+        const int buf = lt % NBUF;
         // the epilogue arrives once the buffer holds this tile's bias row (initially, and after each drain)
-        mbar_wait(&tempty_bar[buf], (nt / NBUF) & 1);
+        mbar_wait(&tempty_bar[buf], (lt / NBUF) & 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * BN;
         for (int vk = 0; vk < num_vk; ++vk) {
@@ -296,23 +326,24 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     const int q = warp_idx & 3;  // TMEM lane quarter
     const int ew = warp_idx - 4;
     const int set = SETS == 2 ? (ew >> 2) : 0;
-    const int stid = q * 32 + lane;  // thread index within the set == token row within the CTA
-    const int row = m0 + stid;
+    const int stid = q * 32 + lane;  // thread index within the set == token row within the row block
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
 
     // Bias of tile nt: fetched into shared memory early (global-load latency off the critical path), written into
     // accumulator buffer (nt % NBUF) with tcgen05.st once that buffer is drained, then handed to the MMA issuer.
-    auto fetch_bias = [&](int nt) {
-      if (nt < num_nt) {
-        float* bs = bias_s + ((nt % NBUF) * 2 + ((nt / NBUF) & 1)) * BN;  // double-buffered per accumulator buffer
+    auto fetch_bias = [&](int lt) {  // lt: CTA-local tile number
+      if (lt < num_lt) {
+        const int nt = static_cast<int>((g_begin + lt) % num_nt);
+        float* bs = bias_s + ((lt % NBUF) * 2 + ((lt / NBUF) & 1)) * BN;  // double-buffered per accumulator buffer
         for (int c = stid; c < BN; c += 128) {
           const int gc = nt * BN + c;
           bs[c] = gc < p.N ? ((p.bias && split == 0) ? __ldg(p.bias + gc) : 0.f) : -INFINITY;
         }
       }
     };
-    auto prestore_bias = [&](int nt) {
-      if (nt < num_nt) {
+    auto prestore_bias = [&](int lt) {
+      const int nt = lt;  // (buffer / parity arithmetic below is in local tile numbers)
+      if (lt < num_lt) {
         // the four warps of the set wrote disjoint parts of the row: make them visible to each other
         if (set == 0)
           asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -345,10 +376,6 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     const uint32_t my_base = smem_u32(cand) + ew * L::kBufPerWarp + lane * 8;
     const uint32_t ptr_limit = my_base + (kNewSlots - kCheck) * kSlotStride;
     uint32_t ptr = my_base;
-    if constexpr (EPI == EPI_TOPK) {
-#pragma unroll
-      for (int s = 0; s < kTopK; ++s) surv[s] = 0ull;
-    }
     // initial bias for the first tile(s) this set will see
     // (tile t < NBUF is primed by the set that will scan it)
 #pragma unroll
@@ -357,15 +384,40 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
 #pragma unroll
     for (int t0 = 0; t0 < NBUF; ++t0)
       if (SETS == 1 || (t0 & 1) == set) prestore_bias(t0);
-    for (int nt = set; nt < num_nt; nt += SETS) {
-      const int buf = nt % NBUF;
+    // Segments: maximal runs of this CTA's local tiles inside one row block.  Both sets walk them in lock-step
+    // (a set may own no tile of a short segment): per-row state is reset at the start, merged and emitted at the end.
+    for (int lt0 = 0; lt0 < num_lt;) {
+      const int mb = static_cast<int>((g_begin + lt0) / num_nt);
+      const int nt0 = static_cast<int>(g_begin + lt0 - static_cast<int64_t>(mb) * num_nt);
+      const int seg_len = min(num_lt - lt0, num_nt - nt0);
+      const int seg_end = lt0 + seg_len;
+      const int row = mb * kBM + stid;
+      if constexpr (EPI == EPI_TOPK) {
+#pragma unroll
+        for (int s = 0; s < kTopK; ++s) surv[s] = 0ull;
+        thresh = 0.f;
+        ptr = my_base;
+        if (lt0 > 0) {
+          // the thresholds published for the previous row block must not leak into this one, and set 0 must be done
+          // reading set 1's hand-off column before set 1 stages new candidates in it
+          if constexpr (SETS == 2) thr_s[set * kBM + stid] = 0.f;
+          asm volatile("bar.sync 3, %0;" ::"n"(kEpiWarps * 32) : "memory");
+        }
+      }
+      int lt = lt0 + ((set - lt0) & (SETS - 1));  // first tile of the segment owned by this set
+      for (; lt < seg_end; lt += SETS) {
+      const int nt = nt0 + (lt - lt0);
+      const int buf = lt % NBUF;
       if constexpr (EPI == EPI_TOPK && SETS == 2) {
         // any lower bound of the row's 32nd largest value is a valid filter: adopt the other set's if tighter
         thresh = fmaxf(thresh, thr_s[(set ^ 1) * kBM + stid]);
       }
-      fetch_bias(nt + NBUF);  // lands in shared memory while this tile is scanned
-      mbar_wait(&tfull_bar[buf], (nt / NBUF) & 1);
+      float shared_thr = 0.f;  // ... and the one the other pieces of this row block have published (L2 load)
+      if (EPI == EPI_TOPK && is_piece && row < p.M) shared_thr = __ldcg(p.part_thr + row);
+      fetch_bias(lt + NBUF);  // lands in shared memory while this tile is scanned
+      mbar_wait(&tfull_bar[buf], (lt / NBUF) & 1);
       tc_fence_after();
+      thresh = fmaxf(thresh, shared_thr);
       const uint32_t t_addr = lane_taddr + buf * BN;
       uint32_t r[2][kChunk];
       tmem_ld_32x32b_x16(t_addr, r[0]);
@@ -403,6 +455,8 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                 thresh = fmaxf(thresh, t);
                 ptr = my_base;
                 if constexpr (SETS == 2) thr_s[set * kBM + stid] = thresh;
+                if (is_piece && row < p.M)  // non-negative floats order like their bit patterns
+                  atomicMax(reinterpret_cast<int*>(p.part_thr + row), __float_as_int(thresh));
               }
             }
           } else if constexpr (EPI == EPI_NONE) {
@@ -439,8 +493,8 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         }
       }
       // buffer drained: pre-store the bias of the tile that will reuse it, then release it to the MMA issuer
-      prestore_bias(nt + NBUF);
-    }
+      prestore_bias(lt + NBUF);
+      }
     if constexpr (EPI == EPI_TOPK) {
       // final compaction; with two sets, set 1 hands its survivors to set 0 through its (now idle) candidate
       // column and set 0 merges; then each thread emits its own row.  Short rows (fewer than 32 positive
@@ -464,11 +518,17 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         }
       }
       if (set == 0 && row < p.M) {
+        const bool whole = nt0 == 0 && seg_len == num_nt;  // otherwise one of several pieces of this row block
+        const uint32_t col_base = static_cast<uint32_t>(nt0) * BN;
         int nvalid = 0;
 #pragma unroll
         for (int s = 0; s < kTopK; ++s) nvalid += surv[s] != 0ull ? 1 : 0;
         float* ov = p.top_vals + static_cast<int64_t>(row) * kTopK;
         int32_t* oi = p.top_idx + static_cast<int64_t>(row) * kTopK;
+        if (!whole) {
+          ov = p.part_vals + piece * p.part_stride + static_cast<int64_t>(row) * kTopK;
+          oi = p.part_idx + piece * p.part_stride + static_cast<int64_t>(row) * kTopK;
+        }
         if (nvalid == kTopK) {
 #pragma unroll
           for (int s = 0; s < kTopK; s += 4) {
@@ -485,10 +545,11 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           }
         } else {
           // survivors are sorted, so the valid ones are surv[0 .. nvalid); the tail takes the free indices
-          uint64_t taken = 0;  // membership of indices [0, 64) in the valid set
+          // (a piece fills from its own first column: across pieces the merge keeps the lowest indices)
+          uint64_t taken = 0;  // membership of indices [col_base, col_base + 64) in the valid set
 #pragma unroll
           for (int s = 0; s < kTopK; ++s) {
-            const uint32_t si = ~static_cast<uint32_t>(surv[s]);
+            const uint32_t si = ~static_cast<uint32_t>(surv[s]) - col_base;
             if (surv[s] != 0ull && si < 64) taken |= 1ull << si;
           }
           uint64_t free_mask = ~taken;
@@ -497,7 +558,7 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             float val = __uint_as_float(static_cast<uint32_t>(surv[s] >> 32));
             uint32_t idx = ~static_cast<uint32_t>(surv[s]);
             if (surv[s] == 0ull) {
-              idx = __ffsll(static_cast<long long>(free_mask)) - 1;
+              idx = col_base + __ffsll(static_cast<long long>(free_mask)) - 1;
               free_mask &= free_mask - 1;
               val = 0.f;
             }
@@ -506,6 +567,8 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           }
         }
       }
+    }
+      lt0 = seg_end;
     }
   }
 

@@ -70,8 +70,11 @@ def topk_encode(xc_hi, xc_lo, w_hi, w_lo, b_enc, precision: int):
     n = w_hi.shape[0]
     vals = torch.empty((N, K_FUSED), dtype=torch.float32, device=xc_hi.device)
     idx = torch.empty((N, K_FUSED), dtype=torch.int32, device=xc_hi.device)
+    need = C.c_int64(0)
+    call("freud_topk_encode_workspace", N, n, C.byref(need))
+    ws = torch.empty(need.value, dtype=torch.uint8, device=xc_hi.device) if need.value else None
     call("freud_topk_encode", _ptr(xc_hi), _ptr(xc_lo), _ptr(w_hi), _ptr(w_lo), _ptr(b_enc), _ptr(vals), _ptr(idx),
-         N, d, n, precision, _stream())
+         N, d, n, precision, _ptr(ws), need.value, _stream())
     return vals, idx
 
 

@@ -47,10 +47,16 @@ int freud_split_operand(const float* w, void* hi, void* lo, int64_t numel, int p
 /* Fused encoder: relu((x - b_dec) @ W_enc.T + b_enc) followed by top-32 per token, without materialising
  * the [N,n] pre-activations (TopKAutoEncoder.pre_acts + select_topk, topkautoencoder.py:72-85, k == 32).
  * tcgen05/TMEM GEMM fed by TMA; selection order: value descending, index ascending (set semantics of
- * torch.topk(sorted=False)).  top_vals fp32 [N,32], top_idx int32 [N,32].  Requires n >= 64, d % 8 == 0. */
+ * torch.topk(sorted=False)).  top_vals fp32 [N,32], top_idx int32 [N,32].  Requires n >= 64, d % 8 == 0.
+ * One CTA scans all column tiles of a 128-token row block.  When N is not a multiple of 148 row blocks, the row
+ * blocks of the last wave are cut into column ranges scanned by separate CTAs and merged afterwards; this needs
+ * `workspace` of freud_topk_encode_workspace(N, n) bytes (may be 0).  With workspace == NULL (or too small) the
+ * last wave simply runs with idle SMs; results are identical. */
+int freud_topk_encode_workspace(int64_t N, int64_t n, int64_t* bytes);
 int freud_topk_encode(const void* xc_hi, const void* xc_lo, const void* w_hi, const void* w_lo,
                       const float* b_enc, float* top_vals, int32_t* top_idx,
-                      int64_t N, int64_t d, int64_t n, int precision, void* stream);
+                      int64_t N, int64_t d, int64_t n, int precision, void* workspace, int64_t workspace_bytes,
+                      void* stream);
 
 /* out[M,N] = act(A[M,K] @ B[N,K]^T + bias[N]) on the tensor cores; act = relu if relu != 0.
  * (pre_acts materialised for the AuxK / multi-TopK branches, topkautoencoder.py:72-77,121,135; and the

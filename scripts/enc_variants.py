@@ -21,6 +21,14 @@ def run(N, d, n):
     e.record(); torch.cuda.synchronize()
     ms = s.elapsed_time(e) / 10
     print(f"variant={os.environ.get('FREUD_ENC_VARIANT','0')} N={N} d={d} n={n}: match={same:.4f} {ms:.3f} ms {2.0*N*d*n/ms/1e9:.0f} TF/s", flush=True)
+if os.environ.get("ONLY_C3"):
+    run(48000, 768, 24576)
+    sys.exit(0)
+if os.environ.get("ONLY_SHAPE"):
+    run(*[int(v) for v in os.environ["ONLY_SHAPE"].split(",")])
+    sys.exit(0)
 run(1000, 64, 512)
 run(75000, 384, 6144)
 run(48000, 768, 24576)
+run(24000, 1280, 81920 // 8)   # C4 per-GPU shard at 8 GPUs
+run(24000, 1280, 81920)        # C4 on one GPU
