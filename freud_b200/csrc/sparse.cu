@@ -2,6 +2,8 @@
 // gather-dot activation gradients, feature-major (CSC) index, row-sparse weight gradients, bias gradients,
 // loss scalars, dead-latent counters and the decoder norm helpers.  All are gather / stream kernels bounded by
 // L2 / HBM bandwidth; none is reshaped into a GEMM.
+#include <type_traits>
+
 #include "device_utils.cuh"
 #include "host_common.h"
 #include "../../include/freud_b200.h"
@@ -115,6 +117,40 @@ template <> struct RowVec<float> {
   }
 };
 
+// Row slice of VB bytes per lane (16, or 8 when the row is not a multiple of 32 x 16 bytes but is one of 32 x 8:
+// d = 384 in bf16 keeps all lanes busy with three 8-byte slices instead of one and a half 16-byte ones).
+template <typename T, int VB> struct Slice {
+  static constexpr int kVec = VB / static_cast<int>(sizeof(T));
+  using Raw = typename std::conditional<VB == 16, uint4, uint2>::type;
+  __device__ static __forceinline__ Raw load_keep(const T* p, uint64_t pol) {
+    if constexpr (VB == 16) {
+      return ldg_keep(p, pol);
+    } else {
+      uint2 r;
+      asm("ld.global.nc.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(pol));
+      return r;
+    }
+  }
+  __device__ static __forceinline__ void unpack(const Raw& raw, float (&v)[kVec]) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&raw);
+    if constexpr (sizeof(T) == 2) {
+#pragma unroll
+      for (int i = 0; i < kVec / 2; ++i) {
+        v[2 * i] = __uint_as_float(w[i] << 16);
+        v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < kVec; ++i) v[i] = __uint_as_float(w[i]);
+    }
+  }
+};
+template <typename T, int D> struct SliceFor {
+  static constexpr int kBytes = (D * static_cast<int>(sizeof(T))) % 512 == 0 ? 16
+                                : ((D * static_cast<int>(sizeof(T))) % 256 == 0 ? 8 : 16);
+  using type = Slice<T, kBytes>;
+};
+
 // Pack the entries a shard owns (index >= 0) to the front of the warp's 32 slots, order preserved; returns the count.
 __device__ __forceinline__ int compact_valid(int& my_i, float& my_a, int lane) {
   const unsigned m = __ballot_sync(0xffffffffu, my_i >= 0);
@@ -141,7 +177,8 @@ __global__ void __launch_bounds__(256) decode_fixed_kernel(const float* __restri
                                                            float* __restrict__ sae_out, RT* __restrict__ resid,
                                                            double* __restrict__ sse, float* __restrict__ colsum,
                                                            int64_t N, int k) {
-  constexpr int V = RowVec<WT>::kVec;
+  using SL = typename SliceFor<WT, D>::type;
+  constexpr int V = SL::kVec;
   constexpr int CH = (D + 32 * V - 1) / (32 * V);
   constexpr int R = CH <= 3 ? 8 : (CH <= 6 ? 4 : 2);  // rows in flight: <= 24 16-byte loads per lane
   __shared__ double scratch[32];
@@ -177,7 +214,7 @@ __global__ void __launch_bounds__(256) decode_fixed_kernel(const float* __restri
       int my_i = lane < jn ? __ldg(top_idx + t * k + j0 + lane) : -1;
       const int cnt = compact_valid(my_i, my_a, lane);
       for (int jb = 0; jb < cnt; jb += R) {
-        uint4 raw[R][CH];
+        typename SL::Raw raw[R][CH];
         float a[R];
 #pragma unroll
         for (int u = 0; u < R; ++u) {
@@ -189,7 +226,7 @@ __global__ void __launch_bounds__(256) decode_fixed_kernel(const float* __restri
 #pragma unroll
           for (int i = 0; i < CH; ++i) {
             const int c = (i * 32 + lane) * V;
-            if (c < D) raw[u][i] = ldg_keep(wr + c, keep);
+            if (c < D) raw[u][i] = SL::load_keep(wr + c, keep);
           }
         }
 #pragma unroll
@@ -199,7 +236,7 @@ __global__ void __launch_bounds__(256) decode_fixed_kernel(const float* __restri
             const int c = (i * 32 + lane) * V;
             if (c < D) {
               float w[V];
-              RowVec<WT>::unpack(raw[u][i], w);
+              SL::unpack(raw[u][i], w);
 #pragma unroll
               for (int e = 0; e < V; ++e) acc[i][e] = fmaf(a[u], w[e], acc[i][e]);
             }
@@ -393,7 +430,8 @@ template <typename GT, typename WT, int D>
 __global__ void __launch_bounds__(256) dacts_fixed_kernel(const GT* __restrict__ g, const int32_t* __restrict__ top_idx,
                                                           const WT* __restrict__ W, float* __restrict__ dacts,
                                                           int64_t N, int k) {
-  constexpr int V = RowVec<WT>::kVec;
+  using SL = typename SliceFor<WT, D>::type;
+  constexpr int V = SL::kVec;
   constexpr int CH = (D + 32 * V - 1) / (32 * V);
   constexpr int R = CH <= 3 ? 8 : (CH <= 6 ? 4 : 2);
   const int lane = threadIdx.x & 31;
@@ -419,7 +457,7 @@ __global__ void __launch_bounds__(256) dacts_fixed_kernel(const GT* __restrict__
 #pragma unroll
       for (int jb = 0; jb < 32; jb += R) {
         if ((live >> jb) & ((1u << R) - 1u)) {  // warp-uniform: skip batches with no owned entry
-          uint4 raw[R][CH];
+          typename SL::Raw raw[R][CH];
 #pragma unroll
           for (int u = 0; u < R; ++u) {
             const int fi = __shfl_sync(0xffffffffu, my_i, jb + u);
@@ -427,7 +465,7 @@ __global__ void __launch_bounds__(256) dacts_fixed_kernel(const GT* __restrict__
 #pragma unroll
             for (int i = 0; i < CH; ++i) {
               const int c = (i * 32 + lane) * V;
-              if (c < D) raw[u][i] = ldg_keep(wr + c, keep);
+              if (c < D) raw[u][i] = SL::load_keep(wr + c, keep);
             }
           }
 #pragma unroll
@@ -438,7 +476,7 @@ __global__ void __launch_bounds__(256) dacts_fixed_kernel(const GT* __restrict__
               const int c = (i * 32 + lane) * V;
               if (c < D) {
                 float w[V];
-                RowVec<WT>::unpack(raw[u][i], w);
+                SL::unpack(raw[u][i], w);
 #pragma unroll
                 for (int e = 0; e < V; ++e) s = fmaf(gv[i][e], w[e], s);
               }
@@ -543,6 +581,7 @@ __global__ void __launch_bounds__(256) csc_fill_kernel(const int32_t* __restrict
 // shared memory; lists longer than kSortMax entries are left in fill order (still correct, not bit-stable).
 constexpr int kSortMax = 4096;
 constexpr int kWarpSortMax = 128;
+constexpr int kRankSortMax = 256;  // O(len^2 / 256) per thread: beyond this the bitonic network wins
 
 // Lists of up to 128 entries (the common case: N*k/n on average): one warp per feature, 4 entries per lane, rank
 // sort by shuffle broadcast (entries are distinct positions, so rank = number of smaller entries).
@@ -579,6 +618,20 @@ __global__ void __launch_bounds__(256) csc_sort_kernel(const int32_t* __restrict
   const int f = blockIdx.x;
   const int beg = offsets[f], len = offsets[f + 1] - beg;
   if (len <= kWarpSortMax || len > kSortMax) return;  // short lists: csc_sort_warp_kernel
+  if (len <= kRankSortMax) {
+    // medium lists: rank sort -- every thread counts the entries smaller than its own (shared-memory broadcast
+    // reads, one barrier) instead of ~50 barrier-separated bitonic stages
+    for (int i = threadIdx.x; i < len; i += blockDim.x) buf[i] = entries[beg + i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < len; i += blockDim.x) {
+      const int32_t v = buf[i];
+      int rank = 0;
+#pragma unroll 8
+      for (int j = 0; j < len; ++j) rank += buf[j] < v;
+      entries[beg + rank] = v;
+    }
+    return;
+  }
   int m = 2;
   while (m < len) m <<= 1;
   for (int i = threadIdx.x; i < m; i += blockDim.x) buf[i] = i < len ? entries[beg + i] : 0x7fffffff;
