@@ -64,17 +64,23 @@ def topk_prep_x(x: torch.Tensor, b_dec: torch.Tensor, precision: int, want_colme
     return hi, lo, tv
 
 
+def topk_encode_workspace_bytes(N: int, n: int) -> int:
+    """Workspace freud_topk_encode wants for splitting the row blocks of a partial last wave (0: no split)."""
+    need = C.c_int64(0)
+    call("freud_topk_encode_workspace", N, n, C.byref(need))
+    return need.value
+
+
 def topk_encode(xc_hi, xc_lo, w_hi, w_lo, b_enc, precision: int):
     """Fused GEMM + bias + ReLU + top-32.  Returns (top_vals fp32 [N,32], top_idx int32 [N,32])."""
     N, d = xc_hi.shape
     n = w_hi.shape[0]
     vals = torch.empty((N, K_FUSED), dtype=torch.float32, device=xc_hi.device)
     idx = torch.empty((N, K_FUSED), dtype=torch.int32, device=xc_hi.device)
-    need = C.c_int64(0)
-    call("freud_topk_encode_workspace", N, n, C.byref(need))
-    ws = torch.empty(need.value, dtype=torch.uint8, device=xc_hi.device) if need.value else None
+    need = topk_encode_workspace_bytes(N, n)
+    ws = torch.empty(need, dtype=torch.uint8, device=xc_hi.device) if need else None
     call("freud_topk_encode", _ptr(xc_hi), _ptr(xc_lo), _ptr(w_hi), _ptr(w_lo), _ptr(b_enc), _ptr(vals), _ptr(idx),
-         N, d, n, precision, _ptr(ws), need.value, _stream())
+         N, d, n, precision, _ptr(ws), need, _stream())
     return vals, idx
 
 
