@@ -11,14 +11,18 @@ replicated.  One step (equal to the single-GPU step of train_sae.py:421-453 on t
   backward is rank-local (e is replicated): dacts, CSC of the owned winners, dW_dec / dW_enc / db_enc
   db_dec needs one [d] all-reduce of -db_enc^T W_enc; the clip norm one scalar all-reduce; Adam is local.
 
-AuxK / multi-TopK are not offered in this mode yet (dead latents raise); the data-parallel mode has them.
+AuxK (topkautoencoder.py:109-127) follows the same pattern once a latent can be dead: every rank selects the top
+k_aux = min(d/2, num_dead) pre-activations among ITS dead latents, the candidate lists are all-gathered, the global
+top-k_aux is taken from them (value descending, dictionary index ascending -- rank-major concatenation keeps that
+order), each rank decodes the winners it owns, and the partial e_hat is all-reduced.  Its backward is rank-local like
+the main one.  multi-TopK is not offered in this mode; the data-parallel mode has it.
 """
 from __future__ import annotations
 
 import torch
 import torch.distributed as dist
 
-from . import ops
+from . import ops, topk_engine
 from ._lib import BF16, FP32
 from .optim import FusedAdam
 from .trainer import build_scheduler
@@ -28,7 +32,8 @@ _KEYS = ("encoder.weight", "encoder.bias", "W_dec", "b_dec")
 
 class FeatureShardedTopKTrainer:
     def __init__(self, full_state: dict, k: int, *, lr, steps, clip_thresh=1.0, scheduler="linear",
-                 scheduler_params=None, precision="bf16", device=None, group=None):
+                 scheduler_params=None, precision="bf16", device=None, group=None, auxk_alpha=0.0,
+                 dead_feature_threshold=None):
         """full_state: the reference state_dict (W_dec, b_dec, encoder.weight, encoder.bias) -- every rank slices
         its own rows, so a checkpoint written by the single-GPU model loads unchanged."""
         if not dist.is_initialized():
@@ -63,6 +68,9 @@ class FeatureShardedTopKTrainer:
         self.scheduler = build_scheduler(self.optimizer, scheduler, scheduler_params or {}, steps)
         self.num_frames_since_fired = torch.zeros(self.n_local, device=dev, dtype=torch.long)
         self.device = dev
+        self.auxk_alpha = float(auxk_alpha)
+        self.dead_feature_threshold = dead_feature_threshold
+        self.tokens_seen = 0
 
     def _allreduce(self, t):
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
@@ -101,19 +109,47 @@ class FeatureShardedTopKTrainer:
         bias = b_dec if self.rank == 0 else torch.zeros_like(b_dec)                     # b_dec enters the sum once
         partial, _, _, _ = ops.topk_decode(own_vals, own_idx, wd, bias)
         sae_out = self._allreduce(partial)                                              # [N,d] fp32
-        rdt = torch.bfloat16 if prec == BF16 else torch.float32
-        e, sse, colsum_e = ops.residual(sae_out, x2, rdt)
-        scal = ops.topk_loss_scalars(sse, tv, N * d)
-        # ---- backward (rank-local): loss = fvu
-        scales = scal[2:4]
-        dacts = ops.topk_dacts(e, own_idx, wd)
-        offsets, entries = ops.csc_build(own_idx, self.n_local)
+        # a latent can only be dead once more than `thr` frames have been seen (same short-cut as SAETrainer)
+        thr = self.dead_feature_threshold
+        num_dead, dead_local = 0, None
+        if thr is not None and self.auxk_alpha != 0.0 and self.tokens_seen > thr:
+            dead_local = self.num_frames_since_fired > thr
+            num_dead = int(self._allreduce(dead_local.sum()))  # the reference's own read-back (:109), over all shards
         g = {k_: p.grad for k_, p in zip(_KEYS, self.plist)}
         xc = xc_hi if prec == BF16 else x2
-        ops.topk_sparse_grads(offsets, entries, own_vals, dacts, e, xc, b_dec, scales, g["W_dec"], g["encoder.weight"],
-                              g["encoder.bias"], k, False)
-        ops.topk_bdec_grad(colsum_e if self.rank == 0 else None, scales if self.rank == 0 else None,
-                           g["encoder.bias"], W_enc, g["b_dec"], False)
+        auxk = torch.zeros((), dtype=torch.float32, device=x.device)
+        if num_dead == 0:
+            rdt = torch.bfloat16 if prec == BF16 else torch.float32
+            e, sse, colsum_e = ops.residual(sae_out, x2, rdt)
+            scal = ops.topk_loss_scalars(sse, tv, N * d)
+            # ---- backward (rank-local): loss = fvu
+            scales = scal[2:4]
+            dacts = ops.topk_dacts(e, own_idx, wd)
+            offsets, entries = ops.csc_build(own_idx, self.n_local)
+            ops.topk_sparse_grads(offsets, entries, own_vals, dacts, e, xc, b_dec, scales, g["W_dec"],
+                                  g["encoder.weight"], g["encoder.bias"], k, False)
+            ops.topk_bdec_grad(colsum_e if self.rank == 0 else None, scales if self.rank == 0 else None,
+                               g["encoder.bias"], W_enc, g["b_dec"], False)
+        else:
+            e, sse, colsum_e = ops.residual(sae_out, x2, torch.float32)
+            scal = ops.topk_loss_scalars(sse, tv, N * d)
+            k_aux = d // 2
+            scale = min(num_dead / k_aux, 1.0)
+            k_aux = min(k_aux, num_dead)
+            a_vals, a_gidx = self._auxk_select(xc_hi, xc_lo, we_hi, we_lo, b_enc, dead_local, k_aux, N, prec)
+            a_own_vals, a_own_idx = ops.shard_localize(a_vals, a_gidx, self.lo, self.n_local)
+            partial, _, _, _ = ops.topk_decode(a_own_vals, a_own_idx, wd, bias)
+            e_hat = self._allreduce(partial)
+            r_aux, sse_aux, _ = ops.residual(e_hat, e, torch.float32, want_colsum=False)  # e_hat - e, e not detached
+            auxk = (scale * sse_aux[0] / scal[4].double()).float() * self.auxk_alpha
+            # ---- backward (rank-local) through the generic engine path: two decodes (main, aux) on this shard's rows;
+            # replicated terms (the direct b_dec gradient) enter on rank 0 only, the sum over ranks completes them
+            st = topk_engine.TopKState(prec, x2, xc_hi, wd, W_enc, b_dec, k, self.n_local, scal, True, own_vals,
+                                       own_idx, e, colsum_e if self.rank == 0 else torch.zeros_like(colsum_e),
+                                       auxk_alpha=self.auxk_alpha)
+            st.aux = (a_own_vals, a_own_idx, r_aux, scale)
+            topk_engine.topk_backward(st, 1.0, 1.0, None, out=g)
+            offsets = st.offsets
         self._allreduce(g["b_dec"])                                                     # [d]
         # ---- global-norm clip + Adam: b_dec's gradient is replicated, count it once
         tl_local = ops.make_tensor_list([p.data for p in self.plist[:3]], [p.grad for p in self.plist[:3]])
@@ -125,5 +161,33 @@ class FeatureShardedTopKTrainer:
         self.optimizer.step(grad_sumsq=sumsq)
         self.scheduler.step()
         ops.dead_latent_update(offsets, self.num_frames_since_fired, N)
-        return {"loss": scal[0], "fvu": scal[0], "grad_sumsq": sumsq, "top_idx": top_gidx, "top_acts": top_vals,
-                "sae_out": sae_out}
+        self.tokens_seen += N
+        return {"loss": scal[0] + auxk, "fvu": scal[0], "auxk_loss": auxk, "grad_sumsq": sumsq, "top_idx": top_gidx,
+                "top_acts": top_vals, "sae_out": sae_out}
+
+    def _auxk_select(self, xc_hi, xc_lo, we_hi, we_lo, b_enc, dead_local, k_aux, N, prec):
+        """Global top-k_aux pre-activations among the dead latents of all shards: (vals [N,k_aux], global idx)."""
+        dev = xc_hi.device
+        lv = torch.full((N, k_aux), -1.0, dtype=torch.float32, device=dev)   # absent candidates lose to relu(.) >= 0
+        lg = torch.full((N, k_aux), -1, dtype=torch.int32, device=dev)
+        dead_idx = torch.nonzero(dead_local).squeeze(1).to(torch.int32)
+        S = dead_idx.numel()
+        if S > 0:
+            ws_hi = ops.gather_rows(we_hi, dead_idx)
+            ws_lo = ops.gather_rows(we_lo, dead_idx) if we_lo is not None else None
+            bs = ops.gather_rows(b_enc, dead_idx)
+            pre_dead = ops.gemm_nt(xc_hi, xc_lo, ws_hi, ws_lo, bs, True, prec)          # [N,S] fp32
+            kk = min(k_aux, S)
+            v, loc = ops.row_topk(pre_dead, kk)                                         # (value desc, index asc)
+            lv[:, :kk] = v
+            lg[:, :kk] = ops.index_map(dead_idx, loc) + self.lo
+        all_v = torch.empty((self.G, N, k_aux), dtype=torch.float32, device=dev)
+        all_g = torch.empty((self.G, N, k_aux), dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(all_v, lv, group=self.group)
+        dist.all_gather_into_tensor(all_g, lg, group=self.group)
+        # rank-major concatenation: among equal values the lower position is the lower dictionary index
+        cat_v = all_v.permute(1, 0, 2).reshape(N, self.G * k_aux).contiguous()
+        cat_g = all_g.permute(1, 0, 2).reshape(N, self.G * k_aux).contiguous()
+        vals, pos = ops.row_topk(cat_v, k_aux)
+        gidx = torch.gather(cat_g, 1, pos.long()).contiguous()
+        return vals, gidx

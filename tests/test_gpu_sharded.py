@@ -65,3 +65,70 @@ def test_feature_sharded_step_equals_single_gpu():
     assert out, "rank 0 reported nothing"
     for k, v in out.items():
         assert v < (0.01 if k == "set_mismatch_frac" else 3e-5), (k, v)
+
+
+def _auxk_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from freud_b200.models.config import TopKAutoEncoderConfig
+        from freud_b200.models.topkautoencoder import TopKAutoEncoder
+        from freud_b200.sharded import FeatureShardedTopKTrainer
+        from freud_b200.trainer import SAETrainer
+
+        torch.manual_seed(0)
+        n, d = 1024, 64
+        cfg = TopKAutoEncoderConfig.from_dict({"n_dict_components": n, "k": 32, "auxk_alpha": 1 / 32})
+        model = TopKAutoEncoder(d, cfg)
+        g = torch.Generator().manual_seed(5)
+        model.b_dec.data = 0.1 * torch.randn(d, generator=g)
+        model.encoder.bias.data = 0.05 * torch.randn(n, generator=g)
+        state = {k: v.clone() for k, v in model.state_dict().items()}
+        xs = [torch.randn(4, 100, d, generator=g) * (0.5 + torch.rand(100, 1, generator=g)) for _ in range(3)]
+        # 50 dead latents (> k_aux = 32), unevenly spread over the two shards; and later only 7 (< k_aux)
+        dead_sets = [torch.randperm(n, generator=g)[:50], torch.cat((torch.arange(3), torch.arange(600, 604)))]
+        kw = dict(lr=1e-3, steps=100, clip_thresh=1.0, scheduler="linear", scheduler_params={"num_warmup_steps": 2},
+                  precision="fp32", dead_feature_threshold=100)
+        sh = FeatureShardedTopKTrainer(state, 32, device=dev, auxk_alpha=1 / 32, **kw)
+        lo, hi = rank * (n // world), (rank + 1) * (n // world)
+        aux = []
+        for i, x in enumerate(xs):
+            if i > 0:
+                ds = dead_sets[i - 1]
+                mine = ds[(ds >= lo) & (ds < hi)] - lo
+                sh.num_frames_since_fired[mine.to(dev)] = 10 ** 9
+            o = sh.step(x.to(dev))
+            aux.append(float(o["auxk_loss"]))
+        full = sh.gathered_state()
+        torch.cuda.synchronize()
+        if rank == 0:
+            ref = SAETrainer(model.to(dev), optimizer="adam", **kw)
+            raux = []
+            for i, x in enumerate(xs):
+                if i > 0:
+                    ref.num_frames_since_fired[dead_sets[i - 1].to(dev)] = 10 ** 9
+                r = ref.step(x.to(dev))
+                raux.append(float(r["auxk_loss"]))
+            torch.cuda.synchronize()
+            errs = {k: float((full[k] - ref.params[k].data).abs().max() / ref.params[k].data.abs().max()) for k in full}
+            errs["fvu"] = abs(float(o["fvu"]) - float(r["fvu"])) / float(r["fvu"])
+            for i in (1, 2):
+                errs[f"auxk{i}"] = abs(aux[i] - raux[i]) / abs(raux[i])
+            errs["auxk_live"] = 0.0 if (raux[1] > 0 and raux[2] > 0 and raux[0] == 0) else 1.0
+            out.update(errs)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_feature_sharded_auxk_equals_single_gpu():
+    """AuxK over dead latents spread across shards (more and fewer than k_aux of them) == single-GPU step."""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_auxk_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert out, "rank 0 reported nothing"
+    for k, v in out.items():
+        assert v < 3e-5, (k, v)
