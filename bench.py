@@ -300,7 +300,6 @@ def main():
         tr.step(dev_x[i % n_bufs])
     barrier()
     t_begin = sampler.mark()
-    _lib.profile = {}
     k0 = _lib.kernel_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -310,9 +309,19 @@ def main():
     barrier()
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     gpu_launches = _lib.kernel_launches - k0
-    prof = _lib.profile_summary()
-    _lib.profile = None
     clocks = sampler.stop(t_begin, sampler.mark()) if rank == 0 else None
+    # second pass of the same K steps with every C-ABI call bracketed by CUDA events (the roofline's live kernel
+    # durations); kept out of the timed region above because ~40 event records per step cost a few percent
+    _lib.profile = {}
+    pv0, pv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pv0.record()
+    for i in range(args.steps):
+        tr.step(dev_x[i % n_bufs])
+    pv1.record()
+    barrier()
+    prof = _lib.profile_summary()
+    prof_ms_per_step = pv0.elapsed_time(pv1) / args.steps
+    _lib.profile = None
     ms_per_step = ms_total / args.steps
     value = tokens_per_step * args.steps / (ms_total / 1e3)
     last_loss = float(out["loss"].item())
