@@ -331,12 +331,20 @@ def main():
     stage = [torch.empty_like(dev_x[0]) for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
     freed = [torch.cuda.Event() for _ in range(2)]
+    # feature-sharded ranks all need the SAME batch: each copies B/G files over its own PCIe link and the parts are
+    # all-gathered over NVLink (FeatureShardedTopKTrainer.gather_batch) instead of G full copies from the host
+    split_feed = sharded and world > 1 and B % world == 0
+    per = B // world if split_feed else B
+    part = [torch.empty((per, T, d), dtype=torch.float32, device=device) for _ in range(2)] if split_feed else None
 
     def prefetch(i):
         s = i % 2
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(freed[s])
-            stage[s].copy_(host[i % n_bufs], non_blocking=True)
+            if split_feed:
+                part[s].copy_(host[i % n_bufs][rank * per:(rank + 1) * per], non_blocking=True)
+            else:
+                stage[s].copy_(host[i % n_bufs], non_blocking=True)
             ready[s].record(copy_stream)
 
     def e2e_loop(n):
@@ -348,6 +356,8 @@ def main():
             if i + 1 < n:
                 prefetch(i + 1)  # overlaps the next batch's H2D with this step's compute
             torch.cuda.current_stream().wait_event(ready[i % 2])
+            if split_feed:
+                tr.gather_batch(part[i % 2], out=stage[i % 2])
             o = tr.step(stage[i % 2])
             freed[i % 2].record()
             # every step's loss is read back (4-byte D2H, train_sae.py:455); reading step i-1's after enqueueing
@@ -416,7 +426,7 @@ def main():
                    "l2": f"{n_bufs} rotating input batches of {B * T * d * 4 / 1e6:.0f} MB (> 126 MB L2)"
                    if B * T * d * 4 > 126e6 else f"{n_bufs} rotating input batches ({B * T * d * 4 / 1e6:.0f} MB each, "
                    f"{n_bufs * B * T * d * 4 / 1e6:.0f} MB total > 126 MB L2)"},
-        "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": B * T * d * 4 * world,
+        "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": (per if split_feed else B) * T * d * 4 * world,
                 "d2h_bytes_per_step": 4 * world, "ms_per_step": e2e_ms / args.steps},
 
         "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,

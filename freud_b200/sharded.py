@@ -88,6 +88,15 @@ class FeatureShardedTopKTrainer:
             out[key] = torch.cat(parts, 0)
         return out
 
+    def gather_batch(self, local_files: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """Feed for the replicated input: every rank uploads only its B/G files (its own PCIe link) and the parts
+        are all-gathered over NVLink into the full [B,T,d] batch, instead of G full host->device copies."""
+        per, T, d = local_files.shape
+        if out is None:
+            out = torch.empty((per * self.G, T, d), dtype=local_files.dtype, device=local_files.device)
+        dist.all_gather_into_tensor(out, local_files.contiguous(), group=self.group)
+        return out
+
     def step(self, x: torch.Tensor):
         if not x.is_cuda:
             raise RuntimeError("activations must already be on the CUDA device")
