@@ -167,3 +167,36 @@ def test_install_as_src_aliases_reference_module_paths():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def test_npy_row_appender_and_collection_metadata(tmp_path):
+    """The appender keeps a valid, memory-mappable .npy after every append (collect_activations.py:60-63)."""
+    import json
+
+    import numpy as np
+    import torch
+
+    from freud_b200.collect import NpyRowAppender, save_data_for_memory_mapping
+
+    p = tmp_path / "rows.npy"
+    blocks = [np.arange(12, dtype=np.int64).reshape(2, 6), np.arange(12, 30, dtype=np.int64).reshape(3, 6)]
+    for b in blocks:
+        with NpyRowAppender(p) as ap:
+            ap.append(b)
+        assert np.load(p, mmap_mode="r").shape[1] == 6
+    assert np.array_equal(np.load(p), np.concatenate(blocks))
+    with pytest.raises(ValueError):
+        with NpyRowAppender(p) as ap:
+            ap.append(np.zeros((1, 5), dtype=np.int64))
+    meta = tmp_path / "layer_metadata.json"
+    files = [tmp_path / "layer_activation_values.npy", tmp_path / "layer_feature_indices.npy"]
+    for s in range(2):
+        vals = torch.rand(3, 5, 4)
+        idx = torch.randint(0, 100, (3, 5, 4))
+        save_data_for_memory_mapping(meta, files, [vals, idx], [f"f{s}{j}" for j in range(3)], [5, 4], [5, 100])
+    m = json.load(open(meta))
+    assert m["tensor_shape"] == [5, 4] and m["activation_shape"] == [5, 100] and len(m["filenames"]) == 6
+    assert np.load(files[0]).shape == (6, 20) and np.load(files[1]).dtype == np.int64
+    with pytest.raises(ValueError):
+        save_data_for_memory_mapping(meta, files, [torch.rand(1, 5, 3), torch.zeros(1, 5, 3, dtype=torch.long)],
+                                     ["x"], [5, 3], [5, 100])
