@@ -296,12 +296,12 @@ def main():
     if rank == 0 and not os.environ.get("FREUD_BENCH_NO_CLOCKS"):  # (diagnostic switch: is the sampler perturbing?)
         sampler.start()
         sampler.wait_first_sample()
-    # clocks / power state settle first: untimed steps for ~0.3 s before the W warm-up steps (a loop that starts on a
-    # GPU still ramping up from the idle set-up phase was measured up to 20 % slow)
-    t_ramp = time.perf_counter()
-    while time.perf_counter() - t_ramp < 0.3:
-        tr.step(dev_x[0])
-        torch.cuda.synchronize()
+    # clocks / power state settle first: 40 untimed steps (0.1-0.3 s; the same count on every rank, the steps hold
+    # collectives) before the W warm-up steps -- a loop that starts on a GPU still ramping up from the idle set-up
+    # phase was measured up to 20 % slow
+    for i in range(40):
+        tr.step(dev_x[i % n_bufs])
+    torch.cuda.synchronize()
     for i in range(args.warmup):
         tr.step(dev_x[i % n_bufs])
     barrier()
