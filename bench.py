@@ -297,11 +297,16 @@ def main():
         sampler.start()
         sampler.wait_first_sample()
     # clocks / power state settle first: 40 untimed steps (0.1-0.3 s; the same count on every rank, the steps hold
-    # collectives) before the W warm-up steps -- a loop that starts on a GPU still ramping up from the idle set-up
-    # phase was measured up to 20 % slow
+    # collectives) on a THROW-AWAY trainer, so the measured trainer still starts from step 0: a loop that starts on
+    # a GPU still ramping up from the idle set-up phase was measured up to 20 % slow, and 40 extra steps on the
+    # measured trainer would move the timed window into a different phase of training (past the dead-latent
+    # threshold, where some latents of the randomly initialised c2 dictionary are dead and AuxK is live)
+    ramp = build_trainer(w, args.precision, dp, device)
     for i in range(40):
-        tr.step(dev_x[i % n_bufs])
+        ramp.step(dev_x[i % n_bufs])
     torch.cuda.synchronize()
+    del ramp
+    torch.cuda.empty_cache()
     for i in range(args.warmup):
         tr.step(dev_x[i % n_bufs])
     barrier()

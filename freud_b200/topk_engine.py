@@ -76,11 +76,13 @@ def encode_operands(x, W_enc, b_dec, precision, dp=None):
 
 
 def topk_forward(x, W_enc, b_enc, W_dec, b_dec, k, *, precision, dead_mask=None, auxk_alpha=0.0, multi_topk=False,
-                 need_grad=True, dp=None, defer_scal=False):
+                 need_grad=True, dp=None, defer_scal=False, num_dead=None):
     """dp: optional freud_b200.parallel.DataParallel -- makes tv / sse (and with them every loss and gradient
     scale) those of the batch concatenated over ranks; gradients stay rank-local sums for the caller to allreduce.
     defer_scal (data parallel, fused main path only): the loss scalars are produced on dp's side stream and the
-    main stream is NOT joined; st.scal_ready is the event to wait for before reading them (topk_backward does)."""
+    main stream is NOT joined; st.scal_ready is the event to wait for before reading them (topk_backward does).
+    num_dead: `int(dead_mask.sum())` when the caller already holds it (the trainer reads it back asynchronously during
+    the previous step); otherwise it is read here, which synchronises with the device like the reference (:109)."""
     if x.dim() != 3:
         raise ValueError("x must be [B, T, d]")
     x = x.contiguous()
@@ -90,7 +92,8 @@ def topk_forward(x, W_enc, b_enc, W_dec, b_dec, k, *, precision, dead_mask=None,
     xc_hi, xc_lo, we_hi, we_lo, tv = encode_operands(x, W_enc, b_dec, precision, dp)
     wd = ops.split_operand(W_dec, BF16)[0] if precision == BF16 else W_dec
     # reference: `int(dead_mask.sum())` (topkautoencoder.py:109) -- one 8-byte device->host read, as upstream
-    num_dead = int(dead_mask.sum()) if dead_mask is not None else 0
+    if num_dead is None:
+        num_dead = int(dead_mask.sum()) if dead_mask is not None else 0
     fused_main = (k == ops.K_FUSED) and not multi_topk
     generic = not fused_main or num_dead > 0  # backward needs materialised gradient seeds (AuxK couples e_hat and e)
     zero = torch.zeros((), dtype=torch.float32, device=x.device)
@@ -194,10 +197,12 @@ def topk_forward(x, W_enc, b_enc, W_dec, b_dec, k, *, precision, dead_mask=None,
     return res, st
 
 
-def topk_backward(st: TopKState, g_fvu, g_aux=None, g_multi=None, *, out=None):
+def topk_backward(st: TopKState, g_fvu, g_aux=None, g_multi=None, *, out=None, on_offsets=None):
     """Parameter gradients of g_fvu*fvu + g_aux*auxk_loss + g_multi*multi_topk_fvu.
     g_* are 0-d device tensors (or python floats).  Returns dict name -> gradient tensor.
-    `out` may supply preallocated gradient buffers {name: tensor}."""
+    `out` may supply preallocated gradient buffers {name: tensor}.  on_offsets(offsets) is called as soon as the CSC
+    offsets of the RETURNED encoding are enqueued (the did_fire bookkeeping can then run beside the rest of the
+    backward instead of after it)."""
     dev = st.x2.device
     n, d, k = st.n, st.x2.shape[1], st.k
     out = out or {}
@@ -223,6 +228,8 @@ def topk_backward(st: TopKState, g_fvu, g_aux=None, g_multi=None, *, out=None):
         offsets, entries = ops.csc_build(st.idx, n)
         st.offsets = offsets
         st.csc_ready = torch.cuda.current_stream().record_event()
+        if on_offsets is not None:
+            on_offsets(offsets)
         if st.scal_ready is not None:  # gradient scale produced on the data-parallel side stream
             torch.cuda.current_stream().wait_event(st.scal_ready)
             st.scal_ready = None
@@ -266,11 +273,14 @@ def topk_backward(st: TopKState, g_fvu, g_aux=None, g_multi=None, *, out=None):
         for tag, vals, idx, G in decodes:
             dacts = ops.topk_dacts(G, idx, st.wd)
             offsets, entries = ops.csc_build(idx, n)
+            if tag == returned:
+                st.offsets = offsets  # did_fire is taken from the RETURNED encoding (train_sae.py:442)
+                st.csc_ready = torch.cuda.current_stream().record_event()
+                if on_offsets is not None:
+                    on_offsets(offsets)
             ops.topk_sparse_grads(offsets, entries, vals, dacts, G, xc, st.b_dec, ones, dW_dec, dW_enc, db_enc,
                                   idx.shape[1], not first)
             first = False
-            if tag == returned:
-                st.offsets = offsets  # did_fire is taken from the RETURNED encoding (train_sae.py:442)
         if dense_aux is not None:
             # dense backward of the AuxK branch on the dead subset: four tensor-core products, then a row scatter
             dead_idx, S, Sp, A, wd_sub, G_hat = dense_aux

@@ -82,6 +82,8 @@ class SAETrainer:
             # crosses the threshold (a one-off ~60 ms module load otherwise lands inside the training loop)
             int((self.num_frames_since_fired > (dead_feature_threshold or 0)).sum())
         self.last_state = None
+        self._dead_next = None  # (mask, event, counter version) prefetched for the next step
+        self._dead_pinned = torch.zeros(1, dtype=torch.int64).pin_memory() if dev.type == "cuda" else None
 
     # ------------------------------------------------------------------------------------------ TopK
     def _topk_step(self, x):
@@ -89,30 +91,52 @@ class SAETrainer:
         cfg = m.cfg
         B, T, _ = x.shape
         n_tokens = B * T * (self.dp.world_size if self.dp else 1)
-        dead_mask = None
+        dead_mask, num_dead = None, None
         thr = self.dead_feature_threshold
+        frames = self.num_frames_since_fired
         # a latent can only be dead once more than `thr` frames have been seen in total; before that the mask
         # is provably empty and the reference's per-step `dead_mask.sum()` read-back is skipped
         if thr is not None and self.tokens_seen > thr:
-            dead_mask = self.num_frames_since_fired > thr
+            if self._dead_next is not None and self._dead_next[2] == frames._version:
+                # mask and count were produced right behind the previous step's CSC build and copied to pinned memory
+                # ~1 ms before that step ended: the read-back returns at once instead of draining the device
+                dead_mask, ev, _ = self._dead_next
+                ev.synchronize()
+                num_dead = int(self._dead_pinned[0])
+            else:  # first step past the threshold, or the counters were edited from outside
+                dead_mask = frames > thr
+        self._dead_next = None
         res, st = topk_engine.topk_forward(x, m.encoder.weight.data, m.encoder.bias.data, m.W_dec.data,
                                            m.b_dec.data, cfg.k, precision=self.precision, dead_mask=dead_mask,
                                            auxk_alpha=float(cfg.auxk_alpha), multi_topk=bool(cfg.multi_topk),
-                                           need_grad=True, dp=self.dp, defer_scal=self.dp is not None)
+                                           need_grad=True, dp=self.dp, defer_scal=self.dp is not None,
+                                           num_dead=num_dead)
         # loss = fvu + auxk_loss + multi_topk_fvu / 8   (train_sae.py:441)
         grads = {k: p.grad for k, p in self.params.items()}
-        topk_engine.topk_backward(st, 1.0, 1.0, 1.0 / 8.0, out=grads)
+        fired_early = []
+
+        def after_offsets(offsets):
+            # did_fire / num_frames_since_fired (train_sae.py:442-446) as soon as the CSC index of the returned
+            # encoding exists, beside the weight-gradient kernels; then next step's dead mask and its count
+            if self.dp is None:
+                ops.dead_latent_update(offsets, frames, n_tokens)
+                self._prefetch_dead(n_tokens)
+                fired_early.append(True)
+
+        topk_engine.topk_backward(st, 1.0, 1.0, 1.0 / 8.0, out=grads, on_offsets=after_offsets)
         glist = [self.params[k].grad for k in _TOPK_KEYS]
         fired_done = None
         if self.dp is not None:
             side = self.dp.side_stream()
             if side is not None and st.csc_ready is not None:
-                # did_fire over all ranks (train_sae.py:442-446 on the concatenated batch): exchanged on the side
-                # stream as soon as the CSC index exists, beside the weight-gradient kernels
+                # did_fire over all ranks (on the concatenated batch): exchanged on the side stream
                 side.wait_event(st.csc_ready)
                 st.offsets.record_stream(side)
                 with torch.cuda.stream(side):
                     self._update_fired_dp(st.offsets, n_tokens)
+                    self._prefetch_dead(n_tokens)
+                    if self._dead_next is not None:
+                        self._dead_next[0].record_stream(torch.cuda.default_stream(x.device))
                     fired_done = side.record_event()
             self.dp.all_reduce_grads(glist, flat=self._flat_grad)
         tl = ops.make_tensor_list([self.params[k].data for k in _TOPK_KEYS], glist)
@@ -123,7 +147,9 @@ class SAETrainer:
         offsets = st.offsets
         if offsets is None:
             offsets, _ = ops.csc_build(res.top_idx, m.n_dict_components)
-        if self.dp is None:
+        if fired_early:
+            pass
+        elif self.dp is None:
             ops.dead_latent_update(offsets, self.num_frames_since_fired, n_tokens)
         elif fired_done is not None:
             torch.cuda.current_stream().wait_event(fired_done)
@@ -137,6 +163,18 @@ class SAETrainer:
             loss = res.fvu
         return {"loss": loss, "fvu": res.fvu, "auxk_loss": res.auxk_loss, "multi_topk_fvu": res.multi_topk_fvu,
                 "grad_sumsq": sumsq, "top_idx": res.top_idx, "top_acts": res.top_acts, "sae_out": res.sae_out}
+
+    def _prefetch_dead(self, n_tokens):
+        """Next step's dead mask and `dead_mask.sum()` (topkautoencoder.py:109), copied to pinned memory on the
+        current stream so that the next step's read-back does not have to wait for this step to finish."""
+        thr = self.dead_feature_threshold
+        if thr is None or self.tokens_seen + n_tokens <= thr:
+            return
+        mask = self.num_frames_since_fired > thr
+        self._dead_pinned.copy_(mask.sum().view(1), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._dead_next = (mask, ev, self.num_frames_since_fired._version)
 
     def _update_fired_dp(self, offsets, n_tokens):
         counts = (offsets[1:] - offsets[:-1]).contiguous()
