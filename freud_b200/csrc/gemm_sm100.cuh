@@ -17,9 +17,12 @@
 // s, s+2, ...) so every SM sub-partition hosts two epilogue warps that hide each other's latency.
 // Pipelines: smem ring full/empty (TMA <-> MMA), TMEM accumulator double buffer full/empty (MMA <-> epilogue).
 //
-// Bias: the epilogue pre-stores the NEXT tile's bias row into the accumulator buffer it has just drained
-// (tcgen05.st), and every MMA accumulates -- no bias add, shared-memory bias staging or extra registers in the
-// selection loop.  Out-of-range feature columns get -inf so they can never be selected.
+// Bias: each set stages the bias row of its next tile in shared memory two tiles ahead; the scan reads it with
+// broadcast loads and forms fl(accumulator + bias) per value -- the reference's own order of operations -- so the
+// accumulator buffer goes back to the MMA issuer as soon as its last chunk has been read out of TMEM.  (Pre-storing
+// the bias row into the drained buffer with tcgen05.st and letting every MMA accumulate was built first: it saves
+// one FADD per value but holds the buffer for ~4 k cycles per tile; measured 3 % slower on C3.)  Out-of-range
+// feature columns get -inf so they can never be selected.
 //
 // Selection (EPI_TOPK): each thread keeps its token's 32 best (value, ~index) keys SORTED IN REGISTERS and
 // appends candidates above its threshold to a small shared-memory column (predicated store, no divergence).
@@ -245,7 +248,7 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     }
     for (int b = 0; b < NBUF; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], 4);  // the four lane-quarter warps that drain (and re-bias) buffer b
+      mbar_init(&tempty_bar[b], 4);  // the four lane-quarter warps that drain buffer b
     }
     fence_barrier_init();
   }
@@ -303,8 +306,8 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       uint32_t phase = 0;
       for (int lt = 0; lt < num_lt; ++lt) {
         const int buf = lt % NBUF;
-        // the epilogue arrives once the buffer holds this tile's bias row (initially, and after each drain)
-        mbar_wait(&tempty_bar[buf], (lt / NBUF) & 1);
+        // the epilogue arrives once it has read the buffer's previous tile out of TMEM (fresh buffers pass at once)
+        mbar_wait(&tempty_bar[buf], ((lt / NBUF) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * BN;
         for (int vk = 0; vk < num_vk; ++vk) {
@@ -316,10 +319,11 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           for (int k4 = 0; k4 < 4; ++k4) {  // 4 x 32-byte UMMA_K steps per 128-byte k-block
             const uint64_t adesc = make_kmajor_sw128_desc(sa + k4 * 32);
             const uint64_t bdesc = make_kmajor_sw128_desc(sb + k4 * 32);
+            const uint32_t acc = (vk > 0 || k4 > 0) ? 1u : 0u;  // the tile's first MMA overwrites the buffer
             if constexpr (TF32)
-              mma_tf32_ss(d_tmem, adesc, bdesc, idesc, 1u);  // always accumulate onto the pre-stored bias
+              mma_tf32_ss(d_tmem, adesc, bdesc, idesc, acc);
             else
-              mma_f16_ss(d_tmem, adesc, bdesc, idesc, 1u);
+              mma_f16_ss(d_tmem, adesc, bdesc, idesc, acc);
           }
           if constexpr (CL == 1)
             tc_commit(&empty_bar[stage]);
@@ -353,34 +357,14 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         }
       }
     };
-    auto prestore_bias = [&](int lt) {
-      const int nt = lt;  // (buffer / parity arithmetic below is in local tile numbers)
-      if (lt < num_lt) {
-        // the four warps of the set wrote disjoint parts of the row: make them visible to each other
-        if (set == 0)
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-        else
-          asm volatile("bar.sync 2, 128;" ::: "memory");
-        const uint32_t t_addr = lane_taddr + (nt % NBUF) * BN;
-        const uint32_t bs_addr = smem_u32(bias_s + ((nt % NBUF) * 2 + ((nt / NBUF) & 1)) * BN);
-#pragma unroll 2
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t bv[32];
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = lds128(bs_addr + (c0 + j) * 4);
-            bv[j] = __float_as_uint(b4.x);
-            bv[j + 1] = __float_as_uint(b4.y);
-            bv[j + 2] = __float_as_uint(b4.z);
-            bv[j + 3] = __float_as_uint(b4.w);
-          }
-          tmem_st_32x32b_x32(t_addr + c0, bv);
-        }
-        tmem_st_wait();
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[nt % NBUF]);
+    // The set's four warps fetched disjoint parts of a bias row: this barrier (at the start of every tile) makes the
+    // row of the tile about to be scanned visible, and orders the next fetch after the last reads of the slot it
+    // overwrites (the tile two uses back).
+    auto set_barrier = [&]() {
+      if (set == 0)
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      else
+        asm volatile("bar.sync 2, 128;" ::: "memory");
     };
 
     uint64_t surv[kTopK];
@@ -388,14 +372,10 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     const uint32_t my_base = smem_u32(cand) + ew * L::kBufPerWarp + lane * 8;
     const uint32_t ptr_limit = my_base + (kNewSlots - kCheck) * kSlotStride;
     uint32_t ptr = my_base;
-    // initial bias for the first tile(s) this set will see
-    // (tile t < NBUF is primed by the set that will scan it)
+    // bias rows of the first tile(s) this set will scan
 #pragma unroll
     for (int t0 = 0; t0 < NBUF; ++t0)
       if (SETS == 1 || (t0 & 1) == set) fetch_bias(t0);
-#pragma unroll
-    for (int t0 = 0; t0 < NBUF; ++t0)
-      if (SETS == 1 || (t0 & 1) == set) prestore_bias(t0);
     // Segments: maximal runs of this CTA's local tiles inside one row block.  Both sets walk them in lock-step
     // (a set may own no tile of a short segment): per-row state is reset at the start, merged and emitted at the end.
     for (int lt0 = 0; lt0 < num_lt;) {
@@ -426,7 +406,9 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       }
       float shared_thr = 0.f;  // ... and the one the other pieces of this row block have published (L2 load)
       if (EPI == EPI_TOPK && is_piece && row < p.M) shared_thr = __ldcg(p.part_thr + row);
+      set_barrier();
       fetch_bias(lt + NBUF);  // lands in shared memory while this tile is scanned
+      const uint32_t bs_addr = smem_u32(bias_s + ((lt % NBUF) * 2 + ((lt / NBUF) & 1)) * BN);
       mbar_wait(&tfull_bar[buf], (lt / NBUF) & 1);
       tc_fence_after();
       thresh = fmaxf(thresh, shared_thr);
@@ -439,7 +421,25 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         for (int h = 0; h < 2; ++h) {
           const int cc = c0 + h * kChunk;
           tmem_ld_wait();
-          if (cc + kChunk < BN) tmem_ld_32x32b_x16(t_addr + cc + kChunk, r[h ^ 1]);  // prefetch the next chunk
+          if (cc + kChunk < BN) {
+            tmem_ld_32x32b_x16(t_addr + cc + kChunk, r[h ^ 1]);  // prefetch the next chunk
+          } else {
+            // the whole tile now sits in registers: hand the buffer back to the MMA issuer before scanning the rest
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+          }
+          // bias of these 16 columns (shared-memory broadcast reads): pre-activation = fl(accumulator + bias), the
+          // reference's own order of operations (nn.Linear: x @ W.T, then + b)
+          float v[kChunk];
+#pragma unroll
+          for (int j = 0; j < kChunk; j += 4) {
+            const float4 b4 = lds128(bs_addr + (cc + j) * 4);
+            v[j] = __uint_as_float(r[h][j]) + b4.x;
+            v[j + 1] = __uint_as_float(r[h][j + 1]) + b4.y;
+            v[j + 2] = __uint_as_float(r[h][j + 2]) + b4.z;
+            v[j + 3] = __uint_as_float(r[h][j + 3]) + b4.w;
+          }
           if constexpr (EPI == EPI_TOPK) {
             const uint32_t nidx0 = ~static_cast<uint32_t>(nt * BN + cc);  // ~(col) == nidx0 - j
 #pragma unroll
@@ -456,7 +456,7 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                     "selp.b32 inc, %6, 0, p;\n\t"
                     "add.u32 %0, %1, inc;\n\t}"
                     : "=r"(next)
-                    : "r"(ptr), "f"(__uint_as_float(r[h][j])), "f"(thresh), "r"(nidx0 - j), "r"(r[h][j]),
+                    : "r"(ptr), "f"(v[j]), "f"(thresh), "r"(nidx0 - j), "r"(__float_as_uint(v[j])),
                       "n"(kSlotStride)
                     : "memory");
                 ptr = next;
@@ -472,7 +472,7 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
               }
             }
           } else if constexpr (EPI == EPI_NONE) {
-            if (__uint_as_float(r[h][0]) == 1.2345e38f) p.out[0] = 1.f;  // keep the loads alive
+            if (v[0] == 1.2345e38f) p.out[0] = 1.f;  // keep the loads alive
           } else {
             if (row < p.M) {
               float* orow = p.out + split * p.split_stride + static_cast<int64_t>(row) * p.ldo + nt * BN + cc;
@@ -480,8 +480,7 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
               if (full_chunk) {
 #pragma unroll
                 for (int j = 0; j < kChunk; j += 4) {
-                  float4 o = make_float4(__uint_as_float(r[h][j]), __uint_as_float(r[h][j + 1]),
-                                         __uint_as_float(r[h][j + 2]), __uint_as_float(r[h][j + 3]));
+                  float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                   if (p.relu) {
                     o.x = fmaxf(o.x, 0.f);
                     o.y = fmaxf(o.y, 0.f);
@@ -494,7 +493,7 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
 #pragma unroll
                 for (int j = 0; j < kChunk; ++j) {
                   if (nt * BN + cc + j < p.N) {
-                    float o = __uint_as_float(r[h][j]);
+                    float o = v[j];
                     if (p.relu) o = fmaxf(o, 0.f);
                     orow[j] = o;
                   }
@@ -504,8 +503,6 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           }
         }
       }
-      // buffer drained: pre-store the bias of the tile that will reuse it, then release it to the MMA issuer
-      prestore_bias(lt + NBUF);
       }
     if constexpr (EPI == EPI_TOPK) {
       // final compaction; with two sets, set 1 hands its survivors to set 0 through its (now idle) candidate
