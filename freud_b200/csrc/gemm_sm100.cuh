@@ -89,7 +89,7 @@ struct GemmSmem {
   static constexpr int kRing = STAGES * kStageBytes;
   static constexpr int kBufPerWarp = kNewSlots * kSlotStride;
   static constexpr int kBuf = EPI == EPI_TOPK ? kEpiWarps * kBufPerWarp : 0;
-  static constexpr int kThr = 2 * kBM * 4;  // per-set published thresholds
+  static constexpr int kThr = 2 * kBM * 4 + 16;  // per-set published thresholds + per-set compaction generation
   static constexpr int kBiasS = 2 * NBUF * BN * 4; // staged bias rows: [accumulator buffer][use parity][BN]
   static constexpr int kBars = (2 * STAGES + 2 * NBUF) * 8 + 16;
   static constexpr int kTotal = kRing + kBuf + kThr + kBiasS + kBars;
@@ -257,6 +257,8 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     tmem_relinquish();
   }
   if (threadIdx.x < 2 * kBM) thr_s[threadIdx.x] = 0.f;  // published per-set thresholds start at the ReLU floor
+  volatile int* gen_s = reinterpret_cast<volatile int*>(thr_s + 2 * kBM);  // [set]: compactions called so far
+  if (threadIdx.x < 2) gen_s[threadIdx.x] = 0;
   tc_fence_before();
   __syncthreads();
   if constexpr (CL > 1) cluster_sync_all();  // peers' barriers are initialised before anyone signals them
@@ -367,6 +369,7 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         asm volatile("bar.sync 2, 128;" ::: "memory");
     };
 
+    int my_gen = 0;
     uint64_t surv[kTopK];
     float thresh = 0.f;
     const uint32_t my_base = smem_u32(cand) + ew * L::kBufPerWarp + lane * 8;
@@ -461,7 +464,15 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                     : "memory");
                 ptr = next;
               }
-              if (__any_sync(0xffffffffu, ptr > ptr_limit)) {
+              // Compaction is called SET-wide: a buffer cycle ends when the slowest of the set's four warps is done, so
+              // a warp compacting alone delays its three peers by a whole compaction (with per-warp triggers ~3/4 of
+              // C3's tiles contained one); when one warp must compact, the others do it at their next check too --
+              // in parallel on the other three sub-partitions -- and their own trigger moves further away.
+              const int gen_seen = gen_s[set];
+              const bool need = __any_sync(0xffffffffu, ptr > ptr_limit);
+              if (need || gen_seen != my_gen) {
+                if (need && gen_seen == my_gen && lane == 0) gen_s[set] = my_gen + 1;
+                my_gen = need && gen_seen == my_gen ? my_gen + 1 : gen_seen;
                 // the next kCheck columns could overflow some lane's column: all lanes compact their own rows
                 const float t = compact_rows(surv, my_base, ptr);
                 thresh = fmaxf(thresh, t);
