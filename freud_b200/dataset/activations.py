@@ -121,12 +121,23 @@ class DeviceActivationStore:
 
     def __init__(self, dataset: MemoryMappedActivationsDataset, device="cuda",
                  num_samples: Optional[dict] = None, frames_fn: Optional[Callable[[str], int]] = None,
-                 chunk_files: int = 256, feature_major: Optional[bool] = None):
+                 chunk_files: int = 256, feature_major: Optional[bool] = None,
+                 shard: Optional[tuple] = None):
+        """shard=(rank, world): keep only this rank's contiguous block of files on the device (files
+        are independent, so the search shards by files; `top_activations` then exchanges the per-file maxima)."""
         self.filenames = list(dataset.metadata["filenames"])
         self.activation_type = dataset.activation_type
         T, F = dataset.metadata["tensor_shape"]
         self.T = T
-        n = len(self.filenames)
+        self.n_total = len(self.filenames)
+        self.shard = shard
+        if shard is None:
+            self.lo, self.hi = 0, self.n_total
+        else:
+            rank, world = shard
+            self.per = -(-self.n_total // world)
+            self.lo, self.hi = min(self.n_total, rank * self.per), min(self.n_total, (rank + 1) * self.per)
+        n = self.hi - self.lo
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError("DeviceActivationStore lives in GPU memory (no CPU fallback)")
@@ -134,7 +145,8 @@ class DeviceActivationStore:
         def upload(mm, dtype_out=None):
             out = torch.empty((n, T, F), dtype=dtype_out or torch.from_numpy(np.zeros(1, mm.dtype)).dtype, device=dev)
             for s in range(0, n, chunk_files):
-                blk = torch.from_numpy(np.ascontiguousarray(mm[s:s + chunk_files])).view(-1, T, F)
+                blk = torch.from_numpy(np.ascontiguousarray(mm[self.lo + s:self.lo + min(n, s + chunk_files)]))
+                blk = blk.view(-1, T, F)
                 out[s:s + blk.shape[0]].copy_(blk.pin_memory(), non_blocking=True)
             torch.cuda.synchronize(dev)
             return out
@@ -160,7 +172,7 @@ class DeviceActivationStore:
                     ns, sr = audio_num_samples(f)
                     return n_frames_from_samples(ns, sr)
         self.n_frames_host = [min(int(frames_fn(f)), T) for f in self.filenames]
-        self.n_frames = torch.tensor(self.n_frames_host, dtype=torch.int32, device=dev)
+        self.n_frames = torch.tensor(self.n_frames_host[self.lo:self.hi], dtype=torch.int32, device=dev)
 
 
 class DeviceResidentActivationLoader:

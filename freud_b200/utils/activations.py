@@ -34,6 +34,18 @@ def get_store(dataloader, **store_kwargs) -> DeviceActivationStore:
 
 
 @torch.no_grad()
+def _gather_files(store, t: torch.Tensor, fill):
+    """Per-file vector of this rank's block -> the full [n_total] vector on every rank (file order)."""
+    import torch.distributed as dist
+
+    world = store.shard[1]
+    part = torch.full((store.per,), fill, dtype=t.dtype, device=t.device)
+    part[: t.numel()] = t
+    full = torch.empty(world * store.per, dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(full, part)
+    return full[: store.n_total].contiguous()
+
+
 def top_activations(dataloader, feature_idx: int, n_files: int, max_val: Optional[float], min_val: Optional[float],
                     absolute_magnitude: bool, return_max_per_file: bool):
     store = get_store(dataloader)
@@ -45,6 +57,9 @@ def top_activations(dataloader, feature_idx: int, n_files: int, max_val: Optiona
             vmax, amax, vabs, _ = ops.search_dense(store.acts, store.n_frames, int(feature_idx), False)
     else:
         vmax, amax, vabs, _ = ops.search_indexed(store.vals, store.idx, store.n_frames, int(feature_idx), False)
+    sharded = getattr(store, "shard", None) is not None and store.shard[1] > 1
+    if sharded:  # files are sharded over the ranks: exchange the per-file results, rank globally on every rank
+        vmax, amax, vabs = _gather_files(store, vmax, 0.0), _gather_files(store, amax, 0), _gather_files(store, vabs, 0.0)
     files, count = ops.search_topn(vmax, vabs, bool(absolute_magnitude), min_val, max_val, int(n_files))
     stat = vabs if absolute_magnitude else vmax
     n_found = int(count.item())
@@ -54,12 +69,21 @@ def top_activations(dataloader, feature_idx: int, n_files: int, max_val: Optiona
         sel = files[:n_found].long()
         stat_h = stat[sel].tolist()
         amax_h = amax[sel].tolist()
-        if store.activation_type == "tensor":
-            traces = store.acts[sel, :, int(feature_idx)].float().cpu()
-        else:
-            _, _, _, tr = ops.search_indexed(store.vals[sel].contiguous(), store.idx[sel].contiguous(),
-                                             store.n_frames[sel].contiguous(), int(feature_idx), True)
-            traces = tr.cpu()
+        own = [r for r, fi in enumerate(files_h) if store.lo <= fi < store.hi]
+        loc = torch.tensor([files_h[r] - store.lo for r in own], dtype=torch.long, device=sel.device)
+        traces = torch.zeros((n_found, store.T), dtype=torch.float32, device=sel.device)
+        if own:
+            if store.activation_type == "tensor":
+                tr = store.acts[loc, :, int(feature_idx)].float()
+            else:
+                _, _, _, tr = ops.search_indexed(store.vals[loc].contiguous(), store.idx[loc].contiguous(),
+                                                 store.n_frames[loc].contiguous(), int(feature_idx), True)
+            traces[torch.tensor(own, dtype=torch.long, device=sel.device)] = tr
+        if sharded:  # every winner's trace lives on exactly one rank
+            import torch.distributed as dist
+
+            dist.all_reduce(traces)
+        traces = traces.cpu()
         for r, fi in enumerate(files_h):
             nf = store.n_frames_host[fi]
             signed = stat_h[r]

@@ -1,7 +1,7 @@
 /* freud_b200 -- C ABI of the B200-native SAE training / feature-search hot path.
  *
  * Drop-in boundary for ksadov/FREUD.  The reference has no FFI: its hot path is torch ATen ops called
- * from Python (src/models/*.py, src/utils/activations.py, src/scripts/train_sae.py:421-453).  Each entry
+ * from Python (the modules under src/models, src/utils/activations.py, src/scripts/train_sae.py:421-453).  Each entry
  * point below replaces the ATen sequence cited next to it; the Python host mirror in freud_b200/ binds
  * them with ctypes.
  *

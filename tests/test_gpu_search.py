@@ -82,3 +82,56 @@ def test_search_large_against_oracle():
                 assert np.array_equal(stat, np.array(mpf))
                 sel = files[: int(cnt)].long()
                 assert np.array_equal(amax[sel].cpu().numpy() * osearch.TIMESTEP_S, np.array([p[3] for p in pq]))
+
+
+def _sharded_search_worker(rank, world, port, tmp, out):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from freud_b200.dataset.activations import DeviceActivationStore, MemoryMappedActivationDataLoader
+        from freud_b200.utils.activations import attach_store, top_activations
+
+        z, meta = load_golden("search")
+        filenames = meta["filenames"]
+        num_samples = {f: int(s) for f, s in zip(filenames, z["num_samples"])}
+        bad = []
+        for kind in ("dense", "indexed"):
+            dl = MemoryMappedActivationDataLoader(f"{tmp}/{kind}", "layer", batch_size=8, dl_max_workers=0)
+            attach_store(dl, DeviceActivationStore(dl.dataset, num_samples=num_samples, shard=(rank, world)))
+            for q, query in enumerate(meta["queries"]):
+                if query["kind"] != kind:
+                    continue
+                pq, mpf = top_activations(dl, query["feature"], query["n_files"], query["max_val"], query["min_val"],
+                                          query["abs"], True)
+                ok = ([filenames.index(p[0]) for p in pq] == z[f"q{q}.files"].tolist()
+                      and np.array_equal(np.array([p[2] for p in pq], dtype=np.float64), z[f"q{q}.values"])
+                      and np.array_equal(np.array([p[3] for p in pq], dtype=np.float64), z[f"q{q}.times"])
+                      and np.array_equal(np.array(mpf, dtype=np.float64), z[f"q{q}.max_per_file"])
+                      and (not pq or np.array_equal(pq[0][1].numpy(), z[f"q{q}.trace0"])))
+                if not ok:
+                    bad.append(q)
+        out[rank] = bad
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_file_sharded_search_matches_reference(tmp_path):
+    """Files split over two ranks: every rank returns the reference's rankings, values and traces."""
+    import socket
+
+    import torch.multiprocessing as mp
+
+    z, meta = load_golden("search")
+    _write_sets(str(tmp_path), z, meta["filenames"])
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_sharded_search_worker, args=(2, port, str(tmp_path), out), nprocs=2, join=True)
+    assert dict(out) == {0: [], 1: []}
