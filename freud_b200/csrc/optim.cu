@@ -47,7 +47,17 @@ __global__ void __launch_bounds__(256) grad_sumsq_kernel(TensorList tl, double* 
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   const int64_t i0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if ((n & 3) == 0) {
-    for (int64_t i = i0; i < (n >> 2); i += stride) {
+    const int64_t n4 = n >> 2;
+    int64_t i = i0;
+    for (; i + 3 * stride < n4; i += 4 * stride) {  // four 16-byte loads in flight per thread
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = load4(g + (i + u * stride) * 4);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        acc += (double)(v[u].x * v[u].x + v[u].y * v[u].y) + (double)(v[u].z * v[u].z + v[u].w * v[u].w);
+    }
+    for (; i < n4; i += stride) {
       const float4 v = load4(g + i * 4);
       acc += (double)(v.x * v.x + v.y * v.y) + (double)(v.z * v.z + v.w * v.w);
     }

@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(256) prep_x_kernel(const float* __restrict__ x
     const float* px = x + t * d + c;
     const float4 sh = load4(px);
     float4 s1 = make_float4(0, 0, 0, 0), s2 = make_float4(0, 0, 0, 0);
-#pragma unroll 4
+#pragma unroll 8
     for (int b = 0; b < B; ++b) {
       const float4 v = load4(px + b * stride);
       const float4 xc = make_float4(v.x - bd.x, v.y - bd.y, v.z - bd.z, v.w - bd.w);
@@ -951,7 +951,15 @@ __global__ void __launch_bounds__(256) bdec_grad_kernel(const float* __restrict_
   const int f0 = blockIdx.y * slab, f1 = min(n, f0 + slab);
   float acc = 0.f;
   if (db_enc) {
-    for (int f = f0; f < f1; ++f) acc = fmaf(-__ldg(db_enc + f), __ldg(W_enc + static_cast<int64_t>(f) * d + c), acc);
+    float part[4] = {0.f, 0.f, 0.f, 0.f};  // four independent chains: the loads of a group are all in flight
+    int f = f0;
+    for (; f + 4 <= f1; f += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        part[u] = fmaf(-__ldg(db_enc + f + u), __ldg(W_enc + static_cast<int64_t>(f + u) * d + c), part[u]);
+    }
+    for (; f < f1; ++f) part[0] = fmaf(-__ldg(db_enc + f), __ldg(W_enc + static_cast<int64_t>(f) * d + c), part[0]);
+    acc = (part[0] + part[1]) + (part[2] + part[3]);
   }
   if (blockIdx.y == 0 && colsum) acc = fmaf(scales[0], colsum[c], acc);
   atomicAdd(db_dec + c, acc);
@@ -1408,7 +1416,7 @@ extern "C" int freud_topk_bdec_grad(const float* colsum, const float* scales, co
   FREUD_REQUIRE(db_enc == nullptr || W_enc != nullptr, "db_enc term needs W_enc");
   FREUD_REQUIRE(colsum == nullptr || scales != nullptr, "colsum term needs scales");
   if (!accumulate) FREUD_CHECK_CUDA(cudaMemsetAsync(db_dec, 0, d * sizeof(float), STREAM));
-  const int slab = 256;
+  const int slab = 64;  // n/64 x d/256 CTAs: enough of them in flight to stream W_enc at HBM rate
   dim3 grid((unsigned)((d + 255) / 256), (unsigned)(db_enc ? (n + slab - 1) / slab : 1));
   bdec_grad_kernel<<<grid, 256, 0, STREAM>>>(colsum, scales, db_enc, W_enc, db_dec, (int)n, (int)d, slab);
   FREUD_CHECK_CUDA(cudaGetLastError());
