@@ -101,6 +101,10 @@ static int launch_gemm(const void* a_hi, const void* a_lo, const void* b_hi, con
   }
   int grid = (p.M + kBM - 1) / kBM;
   grid = (grid + CL - 1) / CL * CL;  // whole clusters; surplus CTAs run the protocol on out-of-range rows
+  if (EPI == EPI_STORE && CL == 1 && p.kb_per_split == 0 && grid > sm_count() && !getenv("FREUD_NO_PERSISTENT")) {
+    p.persistent = 1;  // one CTA per SM, each a contiguous run of row blocks
+    grid = sm_count();
+  }
   // Fused top-k encoder: the row blocks of a last, partial wave are cut into column ranges (plan_tail_split) when
   // the caller supplied the workspace for the partial lists.
   const int num_mb = (p.M + kBM - 1) / kBM;

@@ -77,6 +77,10 @@ struct GemmParams {
   // largest value so far bounds the row's final 32nd largest from below, so later / concurrent pieces start
   // filtering at once instead of rebuilding a threshold from zero
   float* part_thr;
+  // Persistent row-block runs (EPI_STORE): CTA b owns row blocks [b*R/grid, (b+1)*R/grid) and walks them back to
+  // back, so the TMA / MMA of the next row block overlaps the store epilogue of the previous one (a one-tile-wide
+  // product such as the L1 SAE's n = 200 otherwise pays the pipeline fill and drain once per 128 rows).
+  int persistent;
 };
 
 template <int BN, int STAGES, int EPI, int SETS, int NBUF = 2>
@@ -224,6 +228,11 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     const int64_t base = static_cast<int64_t>(p.full_count + t - piece * tail) * num_nt;
     g_begin = base + static_cast<int64_t>(piece) * num_nt / p.tail_split;
     g_end = base + static_cast<int64_t>(piece + 1) * num_nt / p.tail_split;
+  }
+  if (p.persistent) {
+    const int64_t num_mb = (p.M + kBM - 1) / kBM;
+    g_begin = blockIdx.x * num_mb / gridDim.x * num_nt;
+    g_end = (blockIdx.x + 1) * num_mb / gridDim.x * num_nt;
   }
   const int num_lt = static_cast<int>(g_end - g_begin);
   const bool is_piece = p.tail_split > 1 && static_cast<int>(blockIdx.x) >= p.full_count;
