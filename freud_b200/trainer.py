@@ -130,13 +130,14 @@ class SAETrainer:
             side = self.dp.side_stream()
             if side is not None and st.csc_ready is not None:
                 # did_fire over all ranks (on the concatenated batch): exchanged on the side stream
+                main = torch.cuda.current_stream()
                 side.wait_event(st.csc_ready)
                 st.offsets.record_stream(side)
                 with torch.cuda.stream(side):
                     self._update_fired_dp(st.offsets, n_tokens)
                     self._prefetch_dead(n_tokens)
                     if self._dead_next is not None:
-                        self._dead_next[0].record_stream(torch.cuda.default_stream(x.device))
+                        self._dead_next[0].record_stream(main)  # the mask is consumed on the main stream next step
                     fired_done = side.record_event()
             self.dp.all_reduce_grads(glist, flat=self._flat_grad)
         tl = ops.make_tensor_list([self.params[k].data for k in _TOPK_KEYS], glist)
