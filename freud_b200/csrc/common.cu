@@ -58,7 +58,10 @@ int sm_count() {
   if (n == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+      cudaGetLastError();  // no usable device (e.g. a size query on a build host): plan for a B200
+      return 148;
+    }
   }
   return n;
 }

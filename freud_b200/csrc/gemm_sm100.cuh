@@ -356,8 +356,8 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     const int stid = q * 32 + lane;  // thread index within the set == token row within the row block
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
 
-    // Bias of tile nt: fetched into shared memory early (global-load latency off the critical path), written into
-    // accumulator buffer (nt % NBUF) with tcgen05.st once that buffer is drained, then handed to the MMA issuer.
+    // Bias row of local tile lt, staged in shared memory two tiles ahead (global-load latency off the critical path);
+    // the scan adds it to the accumulator values chunk by chunk.
     auto fetch_bias = [&](int lt) {  // lt: CTA-local tile number
       if (lt < num_lt) {
         const int nt = static_cast<int>((g_begin + lt) % num_nt);

@@ -200,3 +200,25 @@ def test_npy_row_appender_and_collection_metadata(tmp_path):
     with pytest.raises(ValueError):
         save_data_for_memory_mapping(meta, files, [torch.rand(1, 5, 3), torch.zeros(1, 5, 3, dtype=torch.long)],
                                      ["x"], [5, 3], [5, 100])
+
+
+def test_encoder_tail_split_plan_sizes():
+    """freud_topk_encode_workspace is a pure host-side plan (no GPU needed): nothing to split when the row blocks fill
+    whole waves of 148 SMs or the dictionary has too few tiles; otherwise S partial lists + the per-row thresholds."""
+    from freud_b200 import _lib
+
+    def need(N, n):
+        out = ctypes.c_int64(-1)
+        _lib.call("freud_topk_encode_workspace", N, n, ctypes.byref(out))
+        return out.value
+
+    assert need(148 * 128, 24576) == 0 and need(2 * 148 * 128, 24576) == 0   # whole waves
+    assert need(77, 600) == 0                                                # 3 column tiles: not worth splitting
+    for N, n in ((48000, 24576), (24000, 81920), (300, 2560), (19109, 8192)):
+        b = need(N, n)
+        rows = -(-N // 128) * 128
+        assert b > 0 and (b - rows * 4) % (rows * 256) == 0                  # S * rows * 32 * 8 + rows * 4
+        S = (b - rows * 4) // (rows * 256)
+        assert 2 <= S <= 16 and 2 * S <= -(-n // 256)
+    with pytest.raises(RuntimeError):
+        need(128, 8)                                                         # n < 64 is rejected like the encoder
