@@ -74,3 +74,36 @@ def test_collect_sae_latents_writes_the_reference_layout(tmp_path):
     lat = l1.encode(torch.from_numpy(acts).cuda()).latent
     # not bit-equal: every L1 encode() re-normalises decoder.weight in place (reference quirk, l1autoencoder.py:71-73)
     assert float((dl[3][0] - lat[3].cpu()).abs().max()) < 1e-5
+
+
+def test_example_training_loop_writes_a_reference_checkpoint(tmp_path):
+    """examples/train_from_store.py: reference config schema in, reference checkpoint layout out, loss going down."""
+    import importlib.util
+    import sys
+
+    from freud_b200.dataset.activations import init_sae_from_checkpoint
+
+    _dense_store(f"{tmp_path}/train", n_files=24, T=50, d=64)
+    cfg = {"seed": 0, "train_folder": f"{tmp_path}/train", "val_folder": f"{tmp_path}/train", "device": "cuda",
+           "run_dir": f"{tmp_path}/run", "lr": 2e-3, "weight_decay": 0.0, "steps": 40, "clip_thresh": 1.0,
+           "batch_size": 8, "dl_max_workers": 0, "log_tb_every": 20, "save_every": 20, "val_every": 100,
+           "start_checkpoint": None, "whisper_config": {"model": "tiny", "layer_name": "layer"},
+           "optimizer": "adam", "scheduler": "linear", "scheduler_params": {"num_warmup_steps": 5}, "from_disk": True,
+           "autoencoder_variant": "topk",
+           "autoencoder_config": {"n_dict_components": 256, "k": 32, "auxk_alpha": 1 / 32, "dead_feature_threshold": 1e6}}
+    spec = importlib.util.spec_from_file_location(
+        "train_from_store", os.path.join(os.path.dirname(os.path.dirname(__file__)), "examples", "train_from_store.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    model, trainer = mod.train(cfg, precision="fp32")
+    ckpt = torch.load(f"{tmp_path}/run/steps_40.pth", map_location="cpu")
+    assert set(ckpt) == {"model", "optimizer", "scheduler", "step", "best_val_loss", "hparams"} and ckpt["step"] == 40
+    assert set(ckpt["model"]) == {"W_dec", "b_dec", "encoder.weight", "encoder.bias"}
+    assert ckpt["hparams"]["activation_size"] == 64
+    loaded = init_sae_from_checkpoint(f"{tmp_path}/run/steps_40.pth", device="cuda")
+    x = torch.randn(2, 50, 64, device="cuda")
+    first = init_sae_from_checkpoint(f"{tmp_path}/run/steps_20.pth", device="cuda")
+    with torch.no_grad():
+        assert float(loaded(x).fvu) < 1.0
+    assert torch.equal(loaded.W_dec.detach().cpu(), model.W_dec.detach().cpu())
+    assert not torch.equal(first.W_dec.cpu(), loaded.W_dec.cpu())
