@@ -243,6 +243,32 @@ def test_tail_wave_column_split_is_exact(shape, bias, monkeypatch):
         assert int((rv > 0).sum(-1).min()) < 32  # short rows are present
 
 
+@pytest.mark.parametrize("shape", [(300, 64, 200), (129, 64, 256), (77, 40, 64), (1000, 64, 257)])
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_fused_encoder_edge_shapes(shape, precision):
+    """Dictionaries of one column tile (set 1 never scans), exactly one tile, the minimum width, and a second tile
+    with a single valid column: selected sets equal a stable descending sort wherever the k-th gap is clear."""
+    from freud_b200 import ops
+    from freud_b200._lib import BF16, FP32
+
+    N, d, n = shape
+    prec = BF16 if precision == "bf16" else FP32
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, N, d, generator=g).cuda()
+    W = (torch.randn(n, d, generator=g) / d ** 0.5).cuda()
+    b_enc = (0.1 * torch.randn(n, generator=g)).cuda()
+    b_dec = (0.1 * torch.randn(d, generator=g)).cuda()
+    xc, xl, _ = ops.topk_prep_x(x, b_dec, prec)
+    w, wl = ops.split_operand(W, prec)
+    vals, idx = ops.topk_encode(xc, xl, w, wl, b_enc, prec)
+    pre = torch.relu(xc.float() @ w.float().T + b_enc) if prec == BF16 else torch.relu((x[0] - b_dec) @ W.T + b_enc)
+    srt, order = torch.sort(pre, dim=-1, descending=True, stable=True)
+    same = (torch.sort(idx.long(), -1).values == torch.sort(order[:, :32], -1).values).all(-1)
+    clear = (srt[:, 31] - srt[:, 32] > 1e-4 * srt[:, 31].abs().clamp_min(1e-3)) | (srt[:, 31] == 0)
+    assert bool(same[clear].all()) and float(clear.float().mean()) > 0.98
+    assert float((torch.sort(vals, -1, descending=True).values - srt[:, :32]).abs().max()) < 1e-5
+
+
 def test_row_topk_masked_exact():
     from freud_b200 import ops
 
