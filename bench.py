@@ -20,7 +20,6 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -137,9 +136,60 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- reference arm / CPU
+def reference_available():
+    from oracle import ref_shims
+
+    return ref_shims.reference_available()
+
+
+def reference_step_factory(w, device, use_autocast=True, seed=0):
+    """The UNMODIFIED reference (oracle/_ref, populated by oracle/make_ref.sh; /root/reference in the build
+    container): src.models.topkautoencoder.TopKAutoEncoder under torch autograd + clip_grad_norm_ + torch.optim.Adam +
+    transformers' linear warm-up, stepped by a verbatim restatement of the loop body train_sae.py:421-453 (that body is
+    not a function upstream, it sits inside train()).  Returns (model, step_fn)."""
+    from oracle import ref_shims
+
+    ref_shims.install()
+    from src.models.config import TopKAutoEncoderConfig
+    from src.models.topkautoencoder import TopKAutoEncoder
+    from torch.amp import autocast
+    from torch.optim import Adam
+    from transformers import get_linear_schedule_with_warmup
+    import contextlib
+
+    torch.manual_seed(seed)
+    autoencoder_config = {"n_dict_components": w["n"], "k": w["k"], "auxk_alpha": w["auxk_alpha"], "multi_topk": False,
+                          "normalize_decoder": True, "dead_feature_threshold": w["dead_feature_threshold"] or 1e30}
+    cfg = TopKAutoEncoderConfig.from_dict(autoencoder_config)
+    model = TopKAutoEncoder(activation_size=w["d"], cfg=cfg)
+    dist_model = model.to(device)
+    optimizer = Adam(dist_model.parameters(), lr=w["lr"])
+    scheduler = get_linear_schedule_with_warmup(optimizer, num_warmup_steps=w["warmup_steps"],
+                                                num_training_steps=100000)
+    num_frames_since_fired = torch.zeros(model.n_dict_components, device=device, dtype=torch.long)
+    dev_type = torch.device(device).type
+
+    def step(activations):
+        did_fire = torch.zeros(model.n_dict_components, device=device, dtype=torch.bool)
+        optimizer.zero_grad()
+        with (autocast(dev_type) if use_autocast else contextlib.nullcontext()):
+            dead_mask = num_frames_since_fired > autoencoder_config["dead_feature_threshold"]
+            out = dist_model(activations, dead_mask=dead_mask)
+            loss = out.fvu + out.auxk_loss + out.multi_topk_fvu / 8
+            did_fire[out.encoded.top_indices.flatten()] = True
+            num_frames_since_fired.add_(activations.shape[1] * activations.shape[0])
+            num_frames_since_fired[did_fire] = 0
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(dist_model.parameters(), 1.0)
+        optimizer.step()
+        scheduler.step()
+        return loss, out
+
+    return model, step
+
+
 def oracle_cpu_step_factory(w, B):
-    """One train step of the oracle port (oracle/sae.py + oracle/optim.py) on the host cores -- the CPU restatement
-    of the reference's own step, same workload shape with a bounded batch."""
+    """Fallback when oracle/_ref is absent: one train step of the oracle port (oracle/sae.py + oracle/optim.py)."""
     from oracle import optim as ooptim
     from oracle import sae as osae
 
@@ -171,8 +221,19 @@ def oracle_cpu_step_factory(w, B):
     return step, B * w["T"]
 
 
-def run_cpu_port(w, steps, warmup, B):
+def run_cpu_reference(w, steps, warmup, B):
+    """Times the reference's own CPU path on all host cores.  Returns (tokens/s, ms/step, threads, kind)."""
     torch.set_num_threads(os.cpu_count() or 1)
+    if reference_available():
+        _, step = reference_step_factory(w, "cpu", use_autocast=True)  # autocast('cpu') = bf16, as train_sae.py:431
+        xs = [synth_batch(B, w["T"], w["d"], 100 + i) for i in range(2)]
+        for i in range(warmup):
+            float(step(xs[i % 2])[0])
+        t0 = time.perf_counter()
+        for i in range(steps):
+            float(step(xs[i % 2])[0])  # loss.item() every step (train_sae.py:455)
+        dt = time.perf_counter() - t0
+        return B * w["T"] * steps / dt, dt / steps * 1e3, torch.get_num_threads(), "reference"
     step, tokens = oracle_cpu_step_factory(w, B)
     for _ in range(warmup):
         step()
@@ -180,23 +241,63 @@ def run_cpu_port(w, steps, warmup, B):
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    return tokens * steps / dt, dt / steps * 1e3, torch.get_num_threads()
+    return tokens * steps / dt, dt / steps * 1e3, torch.get_num_threads(), "port"
+
+
+def run_torch_eager_cuda(w, steps, warmup, device):
+    """The same unmodified reference modules on the B200 (stock PyTorch eager: cuBLAS GEMMs, torch.topk, dense
+    scatter decode, autograd, foreach Adam) under autocast('cuda') as train_sae.py:431 runs them -- the competitor
+    SURVEY.md 2.1 names.  Inputs resident in HBM, CUDA-event timed.  Returns dict or None if the reference is absent."""
+    if not reference_available():
+        return None
+    B, T, d = w["B"], w["T"], w["d"]
+    try:
+        _, step = reference_step_factory(w, device, use_autocast=True)
+        xs = [synth_batch(B, T, d, 1000 + i, device=device) for i in range(3)]
+        for i in range(warmup):
+            step(xs[i % 3])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            loss, _ = step(xs[i % 3])
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        res = {"value": B * T / (ms / 1e3), "unit": "tokens/s", "ms_per_step": ms, "steps": steps, "warmup": warmup,
+               "loss": float(loss), "what": "unmodified reference TopKAutoEncoder + autograd + clip_grad_norm_ + "
+               "torch.optim.Adam, stock PyTorch eager on this GPU under autocast('cuda') (fp16), inputs in HBM"}
+    except torch.cuda.OutOfMemoryError as ex:  # the dense [N,n] buffers of the eager path
+        res = {"value": None, "error": f"out of memory: {str(ex)[:80]}"}
+    finally:
+        step = xs = None
+        torch.cuda.empty_cache()
+    return res
 
 
 def reference_arm(args, w, rank, world):
+    """`--impl reference`: the reference's own CPU implementation of the step on this box's host cores, at the SAME
+    config as our arm (same B x T tokens per step, same shape, Adam + clip + warm-up), bounded to a few steps."""
     if rank != 0:
         return
-    B = 1 if args.workload == "c3" else 2
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
-    val, ms, cores = run_cpu_port(w, steps, warmup, B)
-    sample = f"{B}x{w['T']} tokens per step of the same shape (d={w['d']}, n={w['n']}, k={w['k']}), {steps} steps"
+    B = w["B"]
+    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    val, ms, cores, kind = run_cpu_reference(w, steps, warmup, B)
+    sample = (f"{B}x{w['T']} tokens per step (the bench batch; d={w['d']}, n={w['n']}, k={w['k']}), {steps} timed steps "
+              f"after {warmup} warm-up, {ms:.0f} ms/step")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "tokens/s", "n_gpus": args.gpus,
-            "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong" if w.get("sharded") else "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {w['desc']}", "note": "CPU port of the reference step (oracle/), "
-                       "bf16-operand mode as under the reference's autocast('cpu')"},
-            "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": f"{args.workload}: {w['desc']}", "global_batch_tokens": B * w["T"],
+                       "note": ("unmodified reference modules (oracle/_ref) under autocast('cpu') = bf16, "
+                                "torch.set_num_threads(all cores)") if kind == "reference" else
+                       "oracle/_ref absent: CPU port of the reference step (oracle/), bf16-operand mode"},
+            "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if torch.cuda.is_available() and not w.get("sharded"):
+        torch.cuda.set_device(0)
+        line["torch_eager_b200"] = run_torch_eager_cuda(w, 5, 2, torch.device("cuda", 0))
     print(json.dumps(line), flush=True)
 
 
@@ -228,6 +329,100 @@ def build_trainer(w, precision, dp, device):
                       dead_feature_threshold=w["dead_feature_threshold"], precision=precision, dp=dp)
 
 
+def _rel(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+def _rel_l2(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+_KEYS = ("encoder.weight", "encoder.bias", "W_dec", "b_dec")
+
+
+def parity_check(w, precision, dp, device, x_local, rank, world, sharded):
+    """Run BEFORE the timed region, on the bench workload's own shape and batch; the result rides in the JSON line.
+
+    world == 1 : one step of this build in fp32 mode and in `precision` mode against ONE step of the unmodified
+                 reference modules (oracle/_ref) in eager fp32 on this GPU, same init, same batch: fvu, selection
+                 flip rate, reconstruction and gradient error.  (Rigorous per-row gradient parity, with tie handling,
+                 lives in tests/test_gpu_bench_shapes.py; across 48 000 rows a handful of exact k-th/k+1-th ties flip
+                 and each moves one token's contribution between two dictionary rows, so the bench-level gradient
+                 check is an aggregate one.)
+    world > 1  : one N-rank step (data-parallel, or feature-sharded for c4) against the single-rank step of the same
+                 build on the concatenated (dp) / same (sharded) batch, on rank 0: loss, gradients, updated parameters.
+    """
+    import torch.distributed as dist
+
+    res = {}
+    if world == 1 and not sharded:
+        if not reference_available():
+            return {"ok": None, "skipped": "oracle/_ref absent (run oracle/make_ref.sh where /root/reference exists)"}
+        ref_model, ref_step = reference_step_factory(w, device, use_autocast=False)
+        ref_model.zero_grad()
+        out = ref_model(x_local)  # forward + backward of train_sae.py:433-448 without the optimiser step
+        (out.fvu + out.auxk_loss + out.multi_topk_fvu / 8).backward()
+        ref_g = {k: p.grad.detach().clone() for k, p in ref_model.named_parameters()}
+        ref_fvu, ref_out = out.fvu.detach().clone(), out.sae_out.detach().reshape(-1, w["d"]).clone()
+        ref_idx = torch.sort(out.encoded.top_indices.reshape(-1, w["k"]), -1).values
+        del out, ref_model, ref_step
+        torch.cuda.empty_cache()
+        ok = True
+        for mode, tol_fvu, tol_out in (("fp32", 1e-5, 1e-5), (precision, 2e-2, 2e-2)) if precision != "fp32" \
+                else (("fp32", 1e-5, 1e-5),):
+            tr = build_trainer(w, mode, None, device)
+            o = tr.step(x_local)
+            torch.cuda.synchronize()
+            flips = float((torch.sort(o["top_idx"].long(), -1).values != ref_idx).any(-1).float().mean())
+            r = {"fvu_rel": abs(float(o["fvu"]) - float(ref_fvu)) / float(ref_fvu), "selection_flip_rate": flips,
+                 "sae_out_rel_l2": _rel_l2(o["sae_out"], ref_out),
+                 "grad_rel_l2": max(_rel_l2(tr.params[k].grad, ref_g[k]) for k in _KEYS)}
+            good = r["fvu_rel"] < tol_fvu and (mode != "fp32" or (flips < 1e-3 and r["grad_rel_l2"] < 2e-2))
+            r["ok"] = bool(good)
+            ok = ok and good
+            res[mode + "_vs_reference_fp32"] = r
+            del tr, o
+            torch.cuda.empty_cache()
+        res["against"] = "unmodified reference modules (oracle/_ref), eager fp32 on this GPU, same init and batch"
+        res["ok"] = bool(ok)
+        return res
+    # ---- multi-rank: N-rank step vs the single-rank step on rank 0
+    tr = build_trainer(w, precision, dp, device)
+    o = tr.step(x_local)
+    torch.cuda.synchronize()
+    if sharded:
+        state = tr.gathered_state()
+        full_x = x_local
+        grads = None
+    else:
+        parts = [torch.empty_like(x_local) for _ in range(world)]
+        dist.all_gather(parts, x_local)
+        full_x = torch.cat(parts, 0) if rank == 0 else None
+        del parts
+        state = {k: tr.params[k].data for k in _KEYS}
+        grads = {k: tr.params[k].grad for k in _KEYS}
+    if rank == 0:
+        if sharded:
+            single = build_trainer({**w, "sharded": False}, precision, None, device)
+        else:
+            single = build_trainer(w, precision, None, device)
+        so = single.step(full_x)
+        torch.cuda.synchronize()
+        errs = {"loss_rel": abs(float(o["loss"]) - float(so["loss"])) / abs(float(so["loss"]))}
+        errs["param_rel"] = max(_rel(state[k], single.params[k].data) for k in _KEYS)
+        if grads is not None:
+            errs["grad_rel"] = max(_rel(grads[k], single.params[k].grad) for k in _KEYS)
+        errs["max_rel"] = max(errs.values())
+        errs["ok"] = bool(errs["max_rel"] < 1e-4)
+        errs["against"] = "single-rank step of this build on the " + ("same" if sharded else "concatenated") + " batch"
+        res = errs
+        del single, so
+    del tr, o, full_x
+    torch.cuda.empty_cache()
+    dist.barrier()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -237,6 +432,8 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the pre-timing parity check")
+    ap.add_argument("--no-eager", action="store_true", help="skip the stock-PyTorch-eager-on-this-GPU arm")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel share table (json) here")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
@@ -290,6 +487,10 @@ def main():
         t = torch.tensor([ms], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    parity = None
+    if not args.no_parity:
+        parity = parity_check(w, args.precision, dp, device, dev_x[0], rank, world, sharded)
 
     # ---------------- device-resident throughput (`value`) + live per-kernel timing
     sampler = ClockSampler(local_rank)
@@ -422,12 +623,21 @@ def main():
             dist.destroy_process_group()
         return
     cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline and not sharded:
-        Bc = 1 if args.workload == "c3" else 2
-        v, ms, cores = run_cpu_port(w, 3, 1, Bc)
-        cpu_baseline = {"value": v, "unit": "tokens/s", "cores": cores, "kind": "port",
-                        "sample": f"{Bc}x{T} tokens/step of the same shape, 3 timed steps after 1 warm-up, "
-                                  f"{ms:.0f} ms/step (oracle/ CPU port of the reference step)"}
+    eager = None
+    if world == 1 and not sharded:
+        # free this arm's trainers first: the eager reference materialises the dense [N,n] buffers
+        del tr, dev_x, stage
+        torch.cuda.empty_cache()
+        if not args.no_eager:
+            eager = run_torch_eager_cuda(w, 5, 2, device)
+        if not args.no_cpu_baseline:
+            Bc = 4 if args.workload == "c3" else 8
+            v, ms, cores, kind = run_cpu_reference(w, 2, 1, Bc)
+            what = ("unmodified reference modules (oracle/_ref) under autocast('cpu')" if kind == "reference"
+                    else "oracle/ CPU port of the reference step")
+            cpu_baseline = {"value": v, "unit": "tokens/s", "cores": cores, "kind": kind,
+                            "sample": f"{Bc}x{T} tokens/step of the same shape, 2 timed steps after 1 warm-up, "
+                                      f"{ms:.0f} ms/step ({what}); `--impl reference` times the full {B}x{T} batch"}
     line = {
         "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if sharded else "weak",
@@ -441,7 +651,8 @@ def main():
                 "d2h_bytes_per_step": 4 * world, "ms_per_step": e2e_ms / args.steps},
 
         "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-        "loss": last_loss, "kernel_shares": {k_: round(v["share"], 4) for k_, v in shares.items()},
+        "loss": last_loss, "parity_check": parity, "torch_eager_b200": eager,
+        "kernel_shares": {k_: round(v["share"], 4) for k_, v in shares.items()},
     }
     print(json.dumps(line), flush=True)
     if dist.is_initialized():

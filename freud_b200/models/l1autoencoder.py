@@ -99,6 +99,10 @@ class _L1ForwardFn(torch.autograd.Function):
 
 
 class L1AutoEncoder(nn.Module):
+    # class-level defaults: modules unpickled from reference-written files bypass __init__
+    precision = "auto"
+    dp = None  # freud_b200.parallel.DataParallel: losses over the concatenated batch (set by SAETrainer)
+
     def __init__(self, activation_size: int, cfg: L1AutoEncoderConfig):
         """Same construction order as the reference (:40-67): decoder Linear, zero bias, orthogonal init."""
         super(L1AutoEncoder, self).__init__()
@@ -112,8 +116,6 @@ class L1AutoEncoder(nn.Module):
         self.encoder_bias = nn.Parameter(torch.zeros(self.n_dict_components))
         nn.init.orthogonal_(self.decoder.weight)
         self.encoder = nn.Sequential(nn.ReLU())
-        self.precision = "auto"
-        self.dp = None  # freud_b200.parallel.DataParallel: losses over the concatenated batch (set by SAETrainer)
 
     def _check(self, x: Tensor):
         if not x.is_cuda:

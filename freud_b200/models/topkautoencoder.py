@@ -7,10 +7,11 @@ NamedTuple outputs; `forward` is a torch.autograd.Function over the C ABI, so `l
 Deviations, all documented in DESIGN.md:
   * CUDA only -- forward on CPU tensors raises (no CPU fallback).  Construction / load_state_dict happen on CPU
     exactly as in the reference (`model = TopKAutoEncoder(...); model.to(device)`, train_sae.py:358-362).
-  * autocast (any dtype) selects the bf16 tensor-core mode; selection is always done on fp32 accumulators and
-    top_acts are returned as fp32 (the reference returns the autocast dtype).
-  * only the scalar losses are differentiable outputs (what train_sae.py:441,448 uses); sae_out / top_acts are
-    returned detached.
+  * autocast (any dtype) selects the bf16 tensor-core mode; selection is always done on fp32 accumulators;
+    top_acts are returned in the autocast dtype like the reference's (fp32 outside autocast).
+  * differentiable outputs: the three loss scalars (what train_sae.py:441,448 uses), sae_out and top_acts (a
+    caller's own loss on the reconstruction / the activations back-propagates to the parameters through the generic
+    row-sparse route).  There is no gradient with respect to the input activations.
 """
 from typing import NamedTuple
 
@@ -67,30 +68,35 @@ def _precision(override: str) -> int:
 
 
 class _TopKForwardFn(torch.autograd.Function):
-    """(x, params) -> (sae_out, top_acts, top_idx, fvu, auxk_loss, multi_topk_fvu, mse); only the three loss
-    scalars carry gradient."""
+    """(x, params) -> (sae_out, top_acts, top_idx, fvu, auxk_loss, multi_topk_fvu, mse).  The loss scalars,
+    sae_out and top_acts carry gradient to the parameters; outputs the caller never used arrive as None in
+    backward (set_materialize_grads(False)), so the train-step case -- loss scalars only -- stays on the fused route."""
 
     @staticmethod
-    def forward(ctx, x, W_enc, b_enc, W_dec, b_dec, dead_mask, k, auxk_alpha, multi_topk, precision, holder):
+    def forward(ctx, x, W_enc, b_enc, W_dec, b_dec, dead_mask, k, auxk_alpha, multi_topk, precision):
         need_grad = any(ctx.needs_input_grad[1:5])
         res, st = topk_engine.topk_forward(x, W_enc, b_enc, W_dec, b_dec, k, precision=precision,
                                            dead_mask=dead_mask, auxk_alpha=auxk_alpha, multi_topk=multi_topk,
                                            need_grad=need_grad)
         ctx.st = st
-        ctx.holder = holder
-        holder["state"] = st
-        ctx.mark_non_differentiable(res.sae_out, res.top_acts, res.top_idx, res.mse)
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(res.top_idx, res.mse)
         return res.sae_out, res.top_acts, res.top_idx, res.fvu, res.auxk_loss, res.multi_topk_fvu, res.mse
 
     @staticmethod
     def backward(ctx, g_out, g_acts, g_idx, g_fvu, g_aux, g_multi, g_mse):
-        grads = topk_engine.topk_backward(ctx.st, g_fvu if g_fvu is not None else 0.0, g_aux, g_multi)
+        grads = topk_engine.topk_backward(ctx.st, g_fvu if g_fvu is not None else 0.0, g_aux, g_multi,
+                                          g_out=g_out, g_acts=g_acts)
         ctx.st = None
         return (None, grads["encoder.weight"], grads["encoder.bias"], grads["W_dec"], grads["b_dec"], None, None,
-                None, None, None, None)
+                None, None, None)
 
 
 class TopKAutoEncoder(nn.Module):
+    # class-level default so that modules unpickled from reference-written `torch.save(model)` files
+    # (train_sae.py:594-595; __init__ is bypassed) still resolve it
+    precision = "auto"  # "auto" (autocast -> bf16, else fp32) | "bf16" | "fp32"
+
     def __init__(self, activation_size: int, cfg: TopKAutoEncoderConfig, decoder: bool = True):
         """Same construction order as the reference (:45-70) so that a fixed torch seed yields the same init."""
         super().__init__()
@@ -106,8 +112,6 @@ class TopKAutoEncoder(nn.Module):
             self.set_decoder_norm_to_unit_norm()
 
         self.b_dec = nn.Parameter(torch.zeros(self.d_in))
-        self.precision = "auto"  # "auto" (autocast -> bf16, else fp32) | "bf16" | "fp32"
-        self._last = {}          # state of the most recent forward (used by freud_b200.trainer for did_fire)
 
     # ------------------------------------------------------------------ helpers
     def _check(self, x: Tensor):
@@ -118,11 +122,14 @@ class TopKAutoEncoder(nn.Module):
             x = x.float()
         return x.contiguous()
 
-    def _as3d(self, x: Tensor):
+    def _as3d(self, x: Tensor, variance_axis: bool = False):
+        """[B,T,d] as is.  A 2-D [T,d] input becomes [T,1,d] in forward (variance_axis) so that total_variance's
+        `x.mean(0)` (topkautoencoder.py:104) is the mean over T, exactly as the reference computes it for 2-D input;
+        encode / pre_acts have no variance and take it as one file [1,T,d]."""
         if x.dim() == 3:
             return x, None
         if x.dim() == 2:
-            return x.unsqueeze(0), 2
+            return (x.unsqueeze(1) if variance_axis else x.unsqueeze(0)), 2
         raise ValueError("expected [B, T, d] or [T, d] activations")
 
     # ------------------------------------------------------------------ reference API
@@ -170,11 +177,12 @@ class TopKAutoEncoder(nn.Module):
     def forward(self, x: Tensor, dead_mask: Tensor | None = None, return_mse: bool = False):
         assert self.W_dec is not None, "Decoder weight was not initialized."
         x = self._check(x)
-        x3, squeeze = self._as3d(x)
-        self._last = {}
+        x3, squeeze = self._as3d(x, variance_axis=True)
         sae_out, top_acts, top_idx, fvu, auxk, mfvu, mse = _TopKForwardFn.apply(
             x3, self.encoder.weight, self.encoder.bias, self.W_dec, self.b_dec, dead_mask, self.cfg.k,
-            float(self.cfg.auxk_alpha), bool(self.cfg.multi_topk), _precision(self.precision), self._last)
+            float(self.cfg.auxk_alpha), bool(self.cfg.multi_topk), _precision(self.precision))
+        if torch.is_autocast_enabled():  # the reference's top_acts come out of the autocast matmul (quirk 8)
+            top_acts = top_acts.to(torch.get_autocast_dtype("cuda"))
         lead = x.shape[:-1]
         out = TopKForwardOutput(
             sae_out.view(*lead, self.d_in),

@@ -197,8 +197,11 @@ def topk_forward(x, W_enc, b_enc, W_dec, b_dec, k, *, precision, dead_mask=None,
     return res, st
 
 
-def topk_backward(st: TopKState, g_fvu, g_aux=None, g_multi=None, *, out=None, on_offsets=None):
-    """Parameter gradients of g_fvu*fvu + g_aux*auxk_loss + g_multi*multi_topk_fvu.
+def topk_backward(st: TopKState, g_fvu, g_aux=None, g_multi=None, *, out=None, on_offsets=None, g_out=None,
+                  g_acts=None):
+    """Parameter gradients of g_fvu*fvu + g_aux*auxk_loss + g_multi*multi_topk_fvu (+ <g_out, sae_out> +
+    <g_acts, top_acts> when the caller built its own loss on the returned reconstruction / activations: those two
+    go through the generic row-sparse route and belong to the RETURNED encoding, i.e. the 4k one under multi-TopK).
     g_* are 0-d device tensors (or python floats).  Returns dict name -> gradient tensor.
     `out` may supply preallocated gradient buffers {name: tensor}.  on_offsets(offsets) is called as soon as the CSC
     offsets of the RETURNED encoding are enqueued (the did_fire bookkeeping can then run beside the rest of the
@@ -214,7 +217,8 @@ def topk_backward(st: TopKState, g_fvu, g_aux=None, g_multi=None, *, out=None, o
     xc = st.xc_hi if bf16 else st.x2
     two_over_tv = st.scal[2]
 
-    if not st.generic:
+    extra_seed = g_out is not None or g_acts is not None
+    if not st.generic and not extra_seed:
         if st.scal_ready is not None and not (isinstance(g_fvu, float) and g_fvu == 1.0):
             torch.cuda.current_stream().wait_event(st.scal_ready)  # the scale is about to be read by a torch kernel
             st.scal_ready = None
@@ -242,9 +246,15 @@ def topk_backward(st: TopKState, g_fvu, g_aux=None, g_multi=None, *, out=None, o
                 return torch.zeros((), dtype=torch.float32, device=dev)
             return g.to(torch.float32) if isinstance(g, torch.Tensor) else torch.tensor(float(g), device=dev)
 
+        if st.scal_ready is not None:
+            torch.cuda.current_stream().wait_event(st.scal_ready)
+            st.scal_ready = None
+        if st.e.dtype != torch.float32:  # fused forward kept the residual in bf16; this route seeds from fp32
+            st.e = st.e.float()
         gdt = torch.bfloat16 if bf16 else torch.float32
         c_main = as_t(g_fvu) * two_over_tv
         zero = torch.zeros((), dtype=torch.float32, device=dev)
+        one = torch.ones((), dtype=torch.float32, device=dev)
         decodes = []  # (tag, vals, idx, G)
         db_direct = c_main * st.colsum_e
         dense_aux = None
@@ -270,8 +280,16 @@ def topk_backward(st: TopKState, g_fvu, g_aux=None, g_multi=None, *, out=None, o
         ones = torch.ones(2, dtype=torch.float32, device=dev)
         first = True
         returned = "multi" if st.multi is not None else "main"
+        if g_out is not None:  # caller's own loss on sae_out: one more seed on the returned decode's output
+            g2 = g_out.reshape(-1, d).to(torch.float32).contiguous()
+            db_direct = db_direct + g2.sum(0)
+            decodes = [(tag, vals, idx, ops.axpby(G.float() if G.dtype != torch.float32 else G, g2,
+                                                  torch.stack((one, one)), gdt) if tag == returned else G)
+                       for tag, vals, idx, G in decodes]
         for tag, vals, idx, G in decodes:
             dacts = ops.topk_dacts(G, idx, st.wd)
+            if g_acts is not None and tag == returned:
+                dacts += g_acts.reshape(dacts.shape).to(torch.float32)
             offsets, entries = ops.csc_build(idx, n)
             if tag == returned:
                 st.offsets = offsets  # did_fire is taken from the RETURNED encoding (train_sae.py:442)

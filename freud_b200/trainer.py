@@ -71,12 +71,15 @@ class SAETrainer:
             self.params = {"encoder.weight": model.encoder.weight, "encoder.bias": model.encoder.bias,
                            "W_dec": model.W_dec, "b_dec": model.b_dec}
             # gradients are views of one flat fp32 buffer: data parallel reduces it in a single call, no copies
-            flat = torch.zeros(sum(p.numel() for p in self.params.values()), dtype=torch.float32, device=dev)
+            # (every segment starts on a 128-byte boundary: the float4 paths of the clip / Adam / sparse-gradient
+            # kernels need 16-byte-aligned tensors whatever n_dict_components is; the padding stays zero)
+            seg = {key: (self.params[key].numel() + 31) // 32 * 32 for key in _TOPK_KEYS}
+            flat = torch.zeros(sum(seg.values()), dtype=torch.float32, device=dev)
             off = 0
             for key in _TOPK_KEYS:
                 p = self.params[key]
                 p.grad = flat[off:off + p.numel()].view_as(p)
-                off += p.numel()
+                off += seg[key]
             self._flat_grad = flat
             # load torch's lazily-initialised kernels for the dead-mask read-back now, not in the first step that
             # crosses the threshold (a one-off ~60 ms module load otherwise lands inside the training loop)

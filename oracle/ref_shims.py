@@ -17,7 +17,19 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("FREUD_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root():
+    """The reference tree: $FREUD_REFERENCE_ROOT, else /root/reference (build container), else oracle/_ref -- the
+    copy oracle/make_ref.sh makes so that the unmodified reference travels to the GPU box."""
+    for cand in (os.environ.get("FREUD_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "src", "models")):
+            return cand
+    return os.path.join(_HERE, "_ref")
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def reference_available() -> bool:

@@ -97,10 +97,19 @@ def total_variance(x):
 
 
 def topk_forward(x, W_enc, b_enc, W_dec, b_dec, k, *, dead_mask=None, auxk_alpha=0.0,
-                 multi_topk=False, mode="fp32") -> TopKOut:
-    """topkautoencoder.py:93-151 (x is [B,T,d])."""
+                 multi_topk=False, mode="fp32", force_indices=None) -> TopKOut:
+    """topkautoencoder.py:93-151 (x is [B,T,d]).
+
+    force_indices ([..., k] int64): impose this main selection instead of the oracle's own (values are still the
+    oracle's pre-activations at those indices).  Parity tests use it on the few rows whose k-th / (k+1)-th
+    pre-activations tie within GEMM rounding, where either set is a valid top-k, so that sums over rows
+    (losses, gradients) can still be compared on every row."""
     pre = topk_pre_acts(x, W_enc, b_enc, b_dec, mode)
-    top_acts, top_idx = select_topk(pre, k)
+    if force_indices is not None:
+        top_idx = force_indices.reshape(*pre.shape[:-1], k).long()
+        top_acts = torch.gather(pre, -1, top_idx)
+    else:
+        top_acts, top_idx = select_topk(pre, k)
     sae_out = topk_decode(top_acts, top_idx, W_dec, b_dec, mode)
     e = sae_out - x
     tv = total_variance(x)

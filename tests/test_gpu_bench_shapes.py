@@ -1,0 +1,187 @@
+"""GPU parity at the shapes bench.py measures (BASELINE.json configs C1-C5): CUDA path through the C ABI vs the
+oracle on the same seeded inputs.
+
+Tolerances (north_star): fp32 mode 1e-5 relative; bf16 mode 2e-2 against the fp32 result and 4e-3 against the
+oracle evaluated on the same bf16-rounded operands.  "Relative" is reported two ways and both are asserted:
+`rel_err` = worst element error over the tensor's largest magnitude, `rel_l2` = ||a-b|| / ||b||.
+TopK index sets must be equal on every row, except rows whose disputed pre-activations tie with the k-th largest
+within GEMM rounding (`selection_report` asserts that and the flip rate is printed); sums over rows (losses,
+gradients) are then compared with the oracle evaluated at the CUDA path's selection on exactly those rows.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sae as osae
+from tests.util import rel_err, rel_l2, selection_report
+
+pytestmark = pytest.mark.gpu
+TOPK_KEYS = ["encoder.weight", "encoder.bias", "W_dec", "b_dec"]
+
+
+def topk_problem(B, T, d, n, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, T, d, generator=g) * (0.5 + torch.rand(T, 1, generator=g)) + 0.3 * torch.randn(d, generator=g)
+    W_enc = (torch.rand(n, d, generator=g) * 2 - 1) / d ** 0.5  # nn.Linear's kaiming-uniform range
+    W_dec = osae.set_decoder_norm_to_unit_norm(W_enc.clone() + 0.02 * torch.randn(n, d, generator=g))
+    b_enc = 0.02 * torch.randn(n, generator=g)
+    b_dec = 0.1 * torch.randn(d, generator=g)
+    return x, W_enc, b_enc, W_dec, b_dec
+
+
+def check_fused_step(shape, precision, tol, seed=5, min_clear=0.9):
+    """One fused k=32 forward + backward at `shape` against the oracle in the same precision mode."""
+    from freud_b200 import topk_engine
+    from freud_b200._lib import BF16, FP32
+
+    B, T, d, n = shape
+    k = 32
+    x, W_enc, b_enc, W_dec, b_dec = topk_problem(B, T, d, n, seed)
+    ref = osae.topk_forward(x, W_enc, b_enc, W_dec, b_dec, k, mode=precision)
+    cu = [v.cuda() for v in (x, W_enc, b_enc, W_dec, b_dec)]
+    res, st = topk_engine.topk_forward(*cu, k, precision=BF16 if precision == "bf16" else FP32)
+    assert not st.generic
+    grads = topk_engine.topk_backward(st, 1.0)
+    torch.cuda.synchronize()
+    idx = res.top_idx.cpu()
+    same, flip_rate, worst = selection_report(idx, ref.pre_acts, ref.top_indices, k, tie_tol=2e-5)
+    print(f"[{shape} {precision}] rows {B * T}, selection flip rate {flip_rate:.2e} (worst tie gap {worst:.1e})")
+    assert flip_rate < 5e-3
+    if flip_rate > 0:  # evaluate the oracle at the CUDA selection (tied rows only differ)
+        ref = osae.topk_forward(x, W_enc, b_enc, W_dec, b_dec, k, mode=precision, force_indices=idx)
+    rg = osae.topk_backward(x, W_enc, b_enc, W_dec, b_dec, ref, k, mode=precision)
+    # values: the selected pre-activations themselves
+    order = torch.argsort(idx.long(), -1)
+    ro = torch.argsort(ref.top_indices.reshape(-1, k), -1)
+    v_cu = torch.gather(res.top_acts.cpu(), -1, order)
+    v_ref = torch.gather(ref.top_acts.reshape(-1, k), -1, ro)
+    assert rel_err(v_cu, v_ref) < max(tol, 1e-5)
+    assert rel_err(res.fvu.cpu(), ref.fvu) < max(tol, 1e-5)
+    assert rel_err(res.sae_out.cpu(), ref.sae_out.reshape(-1, d)) < tol
+    assert rel_l2(res.sae_out.cpu(), ref.sae_out.reshape(-1, d)) < tol
+    for key in TOPK_KEYS:
+        assert rel_err(grads[key].cpu(), rg[key]) < tol, key
+        assert rel_l2(grads[key].cpu(), rg[key]) < tol, key
+    return res, ref
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 4e-3)])
+def test_c3_shape_step_vs_oracle(precision, tol):
+    """C3 (bench default): d=768, n=24576 -> 12 k-blocks x 96 column tiles per row block, 2 x 1500 tokens."""
+    check_fused_step((2, 1500, 768, 24576), precision, tol)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 4e-3)])
+def test_c2_shape_step_vs_oracle(precision, tol):
+    """C2 (configs/train/tiny_topk.json): d=384, n=6144, 4 x 1500 tokens."""
+    check_fused_step((4, 1500, 384, 6144), precision, tol)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 4e-3)])
+def test_c4_shape_step_vs_oracle(precision, tol):
+    """C4: d=1280, n=81920 (320 column tiles); 2 x 150 tokens = 3 row blocks, all in the split tail wave."""
+    from freud_b200 import ops
+
+    assert ops.topk_encode_workspace_bytes(300, 81920) > 0, "tail split not exercised"
+    check_fused_step((2, 150, 1280, 81920), precision, tol)
+
+
+def test_c3_bf16_mode_vs_fp32_oracle():
+    """north_star: bf16 mode within 2e-2 of the fp32 result (loss; selections legitimately differ near the k-th gap)."""
+    from freud_b200 import topk_engine
+    from freud_b200._lib import BF16
+
+    B, T, d, n, k = 2, 1500, 768, 24576, 32
+    x, W_enc, b_enc, W_dec, b_dec = topk_problem(B, T, d, n, 5)
+    ref = osae.topk_forward(x, W_enc, b_enc, W_dec, b_dec, k, mode="fp32")
+    res, _ = topk_engine.topk_forward(*[v.cuda() for v in (x, W_enc, b_enc, W_dec, b_dec)], k, precision=BF16)
+    assert rel_err(res.fvu.cpu(), ref.fvu) < 2e-2
+    assert rel_l2(res.sae_out.cpu(), ref.sae_out.reshape(-1, d)) < 2e-2
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 4e-3)])
+def test_c1_shape_l1_step_vs_oracle(precision, tol):
+    """C1 (configs/train/tiny_l1.json): L1 SAE d=384, n=200, recon_alpha=1e4 on 14 x 1500 = 21 000 tokens -- 165 row
+    blocks (persistent store-GEMM CTAs walk more than one), split-K weight gradient over K = 2 x 21 000, multi-CTA
+    loss reduction; a few exact -1.0 targets exercise the masked MSE."""
+    from freud_b200.models.config import L1AutoEncoderConfig
+    from freud_b200.models.l1autoencoder import L1AutoEncoder
+
+    B, T, d, n, alpha = 14, 1500, 384, 200, 1e4
+    torch.manual_seed(0)
+    model = L1AutoEncoder(d, L1AutoEncoderConfig.from_dict({"n_dict_components": n, "recon_alpha": alpha}))
+    g = torch.Generator().manual_seed(3)
+    model.encoder_bias.data = 0.05 * torch.randn(n, generator=g)
+    model.decoder.weight.data *= 1.0 + 0.3 * torch.rand(1, n, generator=g)  # columns off unit norm: colnorm matters
+    W0, b0 = model.decoder.weight.data.clone(), model.encoder_bias.data.clone()
+    x = 0.3 * torch.randn(B, T, d, generator=g)
+    x.view(-1)[torch.randint(0, x.numel(), (500,), generator=g)] = -1.0
+    ref = osae.l1_forward(x, W0, b0, alpha, mode=precision)
+    rg = osae.l1_backward(x, W0, b0, ref, alpha, mode=precision)
+    model = model.cuda()
+    model.precision = precision
+    out, mse = model(x.cuda(), return_mse=True)
+    (out.reconstruction_loss + out.l1_loss).backward()
+    torch.cuda.synchronize()
+    assert rel_err(model.decoder.weight.data.cpu(), ref.W_normed) < 1e-6
+    assert rel_err(out.l1_loss.detach().cpu(), ref.l1_loss) < max(tol, 1e-5)
+    assert rel_err(out.reconstruction_loss.detach().cpu(), ref.reconstruction_loss) < max(tol, 1e-5)
+    assert rel_err(mse.cpu(), ref.mse) < max(tol, 1e-5)
+    assert rel_err(out.encoded.latent.cpu(), ref.latent) < tol
+    assert rel_err(out.sae_out.cpu(), ref.sae_out) < tol
+    assert rel_l2(out.sae_out.cpu(), ref.sae_out) < tol
+    named = dict(model.named_parameters())
+    for key in ("decoder.weight", "encoder_bias"):
+        assert rel_err(named[key].grad.cpu(), rg[key]) < tol, key
+        assert rel_l2(named[key].grad.cpu(), rg[key]) < tol, key
+
+
+def test_c5_search_10k_files_exact_rankings():
+    """C5: 10 000 files x 1500 frames.  Dense store F=384 fp32 (23 GB, generated on the device in slabs) and an
+    indexed store k=32 (n=6144): per-file statistics, rankings and time markers exactly equal to the oracle's for
+    seeded queries x {plain, abs, min/max-filtered}."""
+    from freud_b200 import ops
+    from oracle import search as osearch
+
+    n_files, T, F, k, n = 10000, 1500, 384, 32, 6144
+    rng = np.random.default_rng(7)
+    n_frames = np.array([osearch.n_frames_from_samples(int(s)) for s in rng.integers(16000, 480001, n_files)])
+    nf_dev = torch.tensor(n_frames, dtype=torch.int32, device="cuda")
+    names = [str(i) for i in range(n_files)]
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    dense = torch.empty((n_files, T, F), dtype=torch.float32, device="cuda")
+    for lo in range(0, n_files, 500):
+        dense[lo:lo + 500].normal_(generator=gen)
+    modes = ((None, None, False), (None, None, True), (3.9, 0.5, False), (4.2, -4.0, True))
+    for feature in rng.integers(0, F, 6).tolist():
+        acts = dense[:, :, feature].contiguous().cpu().numpy()
+        vmax, amax, vabs, _ = ops.search_dense(dense, nf_dev, feature, False)
+        for mx, mn, ab in modes:
+            pq, mpf = osearch.top_activations(acts, names, n_frames, 20, mx, mn, ab, True)
+            files, cnt = ops.search_topn(vmax, vabs, ab, mn, mx, 20)
+            assert files[: int(cnt)].tolist() == [int(p[0]) for p in pq], (feature, mx, mn, ab)
+            stat = (vabs if ab else vmax).cpu().numpy().astype(np.float64)
+            assert np.array_equal(stat, np.array(mpf))
+            sel = files[: int(cnt)].long()
+            assert np.array_equal(amax[sel].cpu().numpy() * osearch.TIMESTEP_S, np.array([p[3] for p in pq]))
+    del dense
+    torch.cuda.empty_cache()
+    # indexed store: per frame k distinct indices out of n, |randn| values
+    vals = torch.empty((n_files, T, k), dtype=torch.float32, device="cuda").normal_(generator=gen).abs_()
+    idx = torch.empty((n_files, T, k), dtype=torch.int64, device="cuda")
+    for lo in range(0, n_files, 250):
+        r = torch.rand((min(250, n_files - lo), T, n), device="cuda", generator=gen)
+        idx[lo:lo + 250] = torch.topk(r, k, dim=-1).indices  # k distinct indices per frame
+    del r
+    for feature in rng.integers(0, n, 4).tolist():
+        hit = idx == feature
+        acts = torch.where(hit.any(-1), (vals * hit).sum(-1), torch.zeros((), device="cuda")).cpu().numpy()
+        vmax, amax, vabs, _ = ops.search_indexed(vals, idx, nf_dev, feature, False)
+        for mx, mn, ab in modes:
+            pq, mpf = osearch.top_activations(acts, names, n_frames, 20, mx, mn, ab, True)
+            files, cnt = ops.search_topn(vmax, vabs, ab, mn, mx, 20)
+            assert files[: int(cnt)].tolist() == [int(p[0]) for p in pq], (feature, mx, mn, ab)
+            stat = (vabs if ab else vmax).cpu().numpy().astype(np.float64)
+            assert np.array_equal(stat, np.array(mpf))
+            sel = files[: int(cnt)].long()
+            assert np.array_equal(amax[sel].cpu().numpy() * osearch.TIMESTEP_S, np.array([p[3] for p in pq]))
