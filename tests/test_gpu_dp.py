@@ -43,12 +43,27 @@ def _worker(rank, world, port, out):
               for _ in range(2)]
         kw = dict(lr=1e-3, steps=100, clip_thresh=1.0, optimizer="adam", scheduler="linear",
                   scheduler_params={"num_warmup_steps": 2}, dead_feature_threshold=1e9, precision="fp32")
-        tr = SAETrainer(_build(dev, "fp32"), dp=DataParallel(), **kw)
+        model = _build(dev, "fp32")
+        init = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+        tr = SAETrainer(model, dp=DataParallel(), **kw)
         per = B // world
+        g0 = None
         for x in xs:
             o = tr.step(x[rank * per:(rank + 1) * per].to(dev))
+            if g0 is None:
+                g0 = {k: p.grad.detach().cpu().clone() for k, p in tr.params.items()}
+                fvu0 = float(o["fvu"])
         torch.cuda.synchronize()
         if rank == 0:
+            # the N-rank step against the ORACLE on the concatenated batch (not only against this build's 1-rank step)
+            from oracle import sae as osae
+
+            ro = osae.topk_forward(xs[0], init["encoder.weight"], init["encoder.bias"], init["W_dec"], init["b_dec"], 32)
+            rgr = osae.topk_backward(xs[0], init["encoder.weight"], init["encoder.bias"], init["W_dec"], init["b_dec"],
+                                     ro, 32)
+            out["oracle.fvu"] = abs(fvu0 - float(ro.fvu)) / float(ro.fvu)
+            for k in g0:
+                out["oracle.grad." + k] = float((g0[k] - rgr[k]).abs().max() / rgr[k].abs().max())
             ref = SAETrainer(_build(dev, "fp32"), dp=None, **kw)
             for x in xs:
                 r = ref.step(x.to(dev))

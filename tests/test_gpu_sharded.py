@@ -39,10 +39,29 @@ def _worker(rank, world, port, out):
         kw = dict(lr=1e-3, steps=100, clip_thresh=1.0, scheduler="linear", scheduler_params={"num_warmup_steps": 2},
                   precision="fp32")
         sh = FeatureShardedTopKTrainer(state, 32, device=dev, **kw)
+        first = None
         for x in xs:
             o = sh.step(x.to(dev))
+            if first is None:
+                lo, hi = sh.lo, sh.lo + sh.n_local
+                first = {"fvu": float(o["fvu"]), "idx": o["top_idx"].cpu(), "sae_out": o["sae_out"].cpu(),
+                         "gW_dec": sh.plist[2].grad.cpu().clone(), "gW_enc": sh.plist[0].grad.cpu().clone()}
         full = sh.gathered_state()
         torch.cuda.synchronize()
+        # every rank: its slice of the step-0 gradients and the global selection against the ORACLE
+        from oracle import sae as osae
+
+        ro = osae.topk_forward(xs[0], state["encoder.weight"], state["encoder.bias"], state["W_dec"], state["b_dec"], 32)
+        rg = osae.topk_backward(xs[0], state["encoder.weight"], state["encoder.bias"], state["W_dec"], state["b_dec"],
+                                ro, 32)
+        oe = {"oracle.fvu": abs(first["fvu"] - float(ro.fvu)) / float(ro.fvu),
+              "oracle.sae_out": float((first["sae_out"] - ro.sae_out.reshape(-1, 64)).abs().max() / ro.sae_out.abs().max()),
+              "oracle.set_mismatch_frac": 1.0 - float((torch.sort(first["idx"].long(), -1).values ==
+                                                       torch.sort(ro.top_indices.reshape(-1, 32), -1).values).all(-1).float().mean()),
+              "oracle.gW_dec": float((first["gW_dec"] - rg["W_dec"][lo:hi]).abs().max() / rg["W_dec"].abs().max()),
+              "oracle.gW_enc": float((first["gW_enc"] - rg["encoder.weight"][lo:hi]).abs().max() / rg["encoder.weight"].abs().max())}
+        for k_, v_ in oe.items():
+            out[f"r{rank}.{k_}"] = v_
         if rank == 0:
             ref = SAETrainer(model.to(dev), optimizer="adam", dead_feature_threshold=1e9, **kw)
             for x in xs:
@@ -64,7 +83,7 @@ def test_feature_sharded_step_equals_single_gpu():
     mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     assert out, "rank 0 reported nothing"
     for k, v in out.items():
-        assert v < (0.01 if k == "set_mismatch_frac" else 3e-5), (k, v)
+        assert v < (0.01 if k.endswith("set_mismatch_frac") else 3e-5), (k, v)
 
 
 def _auxk_worker(rank, world, port, out):
