@@ -77,7 +77,7 @@ static int64_t tail_split_bytes(int num_mb, int S) {
   return S > 1 ? S * rows * 32 * 8 + rows * 4 : 0;
 }
 
-template <int BN, int STAGES, int EPI, bool TF32, int SETS, int CL, int NBUF = 2>
+template <int BN, int STAGES, int EPI, bool TF32, int SETS, int CL, int NBUF = 2, int CEV = 0>
 static int launch_gemm(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, GemmParams p,
                        int passes, cudaStream_t stream) {
   using L = GemmSmem<BN, STAGES, EPI, SETS, NBUF>;
@@ -93,7 +93,8 @@ static int launch_gemm(const void* a_hi, const void* a_lo, const void* b_hi, con
     mB1 = mB0;
   }
   p.passes = passes;
-  auto kern = sm100_gemm_kernel<BN, STAGES, EPI, TF32, SETS, CL, NBUF>;
+  auto kern = sm100_gemm_kernel<BN, STAGES, EPI, TF32, SETS, CL, NBUF, CEV>;
+  if (const char* e = getenv("FREUD_ENC_FLAGS")) p.flags = atoi(e);
   static bool attr_set = false;
   if (!attr_set) {
     FREUD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -199,6 +200,7 @@ extern "C" int freud_topk_encode(const void* xc_hi, const void* xc_lo, const voi
       // (a triple-buffered BN = 160 variant, launch_gemm<160, 4, EPI_TOPK, false, 2, 1, 3>, measured slower:
       //  2.02 vs 1.78 ms on C3 -- per-tile fixed costs outweigh the extra MMA/scan overlap)
       case 3: return launch_gemm<256, 3, EPI_TOPK, false, 1, 1>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
+      case 10: return launch_gemm<256, 3, EPI_TOPK, false, 2, 1, 2, 1>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
       case 6: p.out = top_vals; return launch_gemm<256, 3, EPI_NONE, false, 1, 1>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
       case 7: p.out = top_vals; return launch_gemm<256, 4, EPI_NONE, false, 1, 1>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
       case 8: p.out = top_vals; return launch_gemm<256, 3, EPI_NONE, false, 2, 1>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);

@@ -13,8 +13,11 @@
 //   EPI_NONE : discard the tile (mainloop-ceiling probe used by scripts/enc_variants.py)
 //
 // Roles: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warp 3 spare, then SETS x 4
-// epilogue warps (TMEM lane quarter == warp_idx % 4).  With SETS == 2, set s drains accumulator buffer s (tiles
-// s, s+2, ...) so every SM sub-partition hosts two epilogue warps that hide each other's latency.
+// epilogue warps (TMEM lane quarter == warp_idx % 4).  With SETS == 2 both sets drain EVERY tile, set s taking
+// columns [s*BN/2, (s+1)*BN/2) of it, so every SM sub-partition hosts two epilogue warps that hide each other's
+// latency and neither ever waits for "its" buffer while the MMA issuer fills it: the tile period is
+// max(MMA, scan / 2).  (Round 1 gave set s the tiles s, s+2, ... with one accumulator buffer each; a set then idled
+// for a whole MMA time per tile -- period (MMA + scan) / 2 -- and a single set, period max(MMA, scan), was faster.)
 // Pipelines: smem ring full/empty (TMA <-> MMA), TMEM accumulator double buffer full/empty (MMA <-> epilogue).
 //
 // Bias: each set stages the bias row of its next tile in shared memory two tiles ahead; the scan reads it with
@@ -44,7 +47,9 @@ constexpr int kTopK = 32;       // fused selection width
 constexpr int kNewSlots = 32;   // candidate slots per token between compactions
 constexpr int kChunk = 16;      // accumulator columns per TMEM load
 constexpr int kCheck = 8;       // columns between candidate-column occupancy checks
-constexpr int kSlotStride = 33 * 8;  // bytes between slots of one lane ([slot][33 lanes] x 8 B, conflict-free)
+constexpr int kSlotStride = 32 * 8;  // bytes between slots of one lane: [slot][32 lanes] x 8 B.  A lane's 8-byte word
+                                     // sits in banks {2*lane, 2*lane+1} whatever its slot (256 B == 0 mod 128 B), so the
+                                     // predicated appends of lanes at DIFFERENT fill levels never collide
 
 enum { EPI_TOPK = 0, EPI_STORE = 1, EPI_NONE = 2 };
 
@@ -81,6 +86,7 @@ struct GemmParams {
   // back, so the TMA / MMA of the next row block overlaps the store epilogue of the previous one (a one-tile-wide
   // product such as the L1 SAE's n = 200 otherwise pays the pipeline fill and drain once per 128 rows).
   int persistent;
+  int flags;  // experiments (FREUD_ENC_FLAGS): bit 0 = do not share 16th-largest values between the epilogue sets
 };
 
 template <int BN, int STAGES, int EPI, int SETS, int NBUF = 2>
@@ -93,8 +99,9 @@ struct GemmSmem {
   static constexpr int kRing = STAGES * kStageBytes;
   static constexpr int kBufPerWarp = kNewSlots * kSlotStride;
   static constexpr int kBuf = EPI == EPI_TOPK ? kEpiWarps * kBufPerWarp : 0;
-  static constexpr int kThr = 2 * kBM * 4 + 16;  // per-set published thresholds + per-set compaction generation
-  static constexpr int kBiasS = 2 * NBUF * BN * 4; // staged bias rows: [accumulator buffer][use parity][BN]
+  static constexpr int kThr = 2 * kBM * 4 + 16;  // per-set published 16th-largest values
+  static constexpr int kCols = BN / SETS;                   // columns of a tile one epilogue warp scans
+  static constexpr int kBiasS = kEpiWarps * 2 * kCols * 4;  // staged bias rows: [epilogue warp][use parity][kCols]
   static constexpr int kBars = (2 * STAGES + 2 * NBUF) * 8 + 16;
   static constexpr int kTotal = kRing + kBuf + kThr + kBiasS + kBars;
 };
@@ -107,7 +114,15 @@ struct GemmSmem {
 // sixteen independent exchanges of a network stage at ~3 in flight (measured: 12-14 k cycles per compaction, IPC
 // 0.2).  Keys are < 2^63 (value bits < 2^31), so the sign of the 64-bit difference is the comparison: one
 // subtract-with-borrow pair, one arithmetic shift to a mask, four LOP3 selects -- 7 instructions, carry flag only.
+template <int CEV = 0>
 __device__ __forceinline__ void cmp_exchange(uint64_t& hi, uint64_t& lo) {
+  if constexpr (CEV == 1) {  // experiment: one 64-bit compare (ISETP + ISETP.EX) and four predicated selects
+    const bool sw = hi < lo;
+    const uint64_t mx = sw ? lo : hi, mn = sw ? hi : lo;
+    hi = mx;
+    lo = mn;
+    return;
+  }
   const uint32_t al = static_cast<uint32_t>(hi), ah = static_cast<uint32_t>(hi >> 32);
   const uint32_t bl = static_cast<uint32_t>(lo), bh = static_cast<uint32_t>(lo >> 32);
   uint32_t m;  // all ones iff hi < lo
@@ -120,7 +135,7 @@ __device__ __forceinline__ void cmp_exchange(uint64_t& hi, uint64_t& lo) {
   lo = (static_cast<uint64_t>(nh) << 32) | nl;
 }
 
-template <int N>
+template <int N, int CEV = 0>
 __device__ __forceinline__ void bitonic_sort_desc(uint64_t (&a)[N]) {
 #pragma unroll
   for (int k = 2; k <= N; k <<= 1) {
@@ -131,23 +146,23 @@ __device__ __forceinline__ void bitonic_sort_desc(uint64_t (&a)[N]) {
         const int l = i ^ j;
         if (l > i) {
           if ((i & k) == 0)
-            cmp_exchange(a[i], a[l]);  // descending run: larger key first
+            cmp_exchange<CEV>(a[i], a[l]);  // descending run: larger key first
           else
-            cmp_exchange(a[l], a[i]);
+            cmp_exchange<CEV>(a[l], a[i]);
         }
       }
     }
   }
 }
 // Sort a bitonic sequence descending.
-template <int N>
+template <int N, int CEV = 0>
 __device__ __forceinline__ void bitonic_merge_desc(uint64_t (&a)[N]) {
 #pragma unroll
   for (int j = N >> 1; j > 0; j >>= 1) {
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       const int l = i ^ j;
-      if (l > i) cmp_exchange(a[i], a[l]);
+      if (l > i) cmp_exchange<CEV>(a[i], a[l]);
     }
   }
 }
@@ -164,29 +179,32 @@ __device__ __forceinline__ void sts64(uint32_t addr, uint64_t v) {
 }
 
 // Lock-step compaction: every lane merges the candidates of ITS OWN column (slots below `ptr`) into its sorted
-// survivors.  Returns the lane's new 32nd-best value (0 while fewer than 32 positives have been seen).
-__device__ __noinline__ float compact_rows(uint64_t (&surv)[kTopK], uint32_t my_base, uint32_t ptr) {
+// survivors.  Returns the lane's new 32nd-best value (0 while fewer than 32 positives have been seen) and, in t16,
+// its 16th-best.
+template <int CEV>
+__device__ __noinline__ float compact_rows(uint64_t (&surv)[kTopK], uint32_t my_base, uint32_t ptr, float& t16) {
   uint64_t fresh[kNewSlots];
 #pragma unroll
   for (int j = 0; j < kNewSlots; ++j) {
     const uint32_t addr = my_base + j * kSlotStride;
     fresh[j] = addr < ptr ? lds64(addr) : 0ull;
   }
-  bitonic_sort_desc<kNewSlots>(fresh);
+  bitonic_sort_desc<kNewSlots, CEV>(fresh);
   // max(descending, reversed descending) = the 32 largest of the union, as a bitonic sequence
 #pragma unroll
   for (int i = 0; i < kTopK; ++i) {
     uint64_t y = fresh[kNewSlots - 1 - i];
-    cmp_exchange(surv[i], y);  // keeps the larger; the smaller is dropped
+    cmp_exchange<CEV>(surv[i], y);  // keeps the larger; the smaller is dropped
   }
-  bitonic_merge_desc<kTopK>(surv);
+  bitonic_merge_desc<kTopK, CEV>(surv);
+  t16 = __uint_as_float(static_cast<uint32_t>(surv[kTopK / 2 - 1] >> 32));
   return __uint_as_float(static_cast<uint32_t>(surv[kTopK - 1] >> 32));
 }
 
 // NBUF accumulator buffers of BN columns live in TMEM (NBUF * BN <= 512).  With two epilogue sets scanning two
 // buffers, a THIRD buffer (BN = 160) lets the MMA issuer fill the next tile meanwhile: the tile rate becomes
 // min(1/M, 2/E) instead of 2/(M + E)  (M = MMA time, E = scan + bias pre-store time of one tile).
-template <int BN, int STAGES, int EPI, bool TF32, int SETS, int CL, int NBUF = 2>
+template <int BN, int STAGES, int EPI, bool TF32, int SETS, int CL, int NBUF = 2, int CEV = 0>
 __global__ void __launch_bounds__(128 + SETS * 128, 1)
 sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                   const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
@@ -257,7 +275,7 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     }
     for (int b = 0; b < NBUF; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], 4);  // the four lane-quarter warps that drain buffer b
+      mbar_init(&tempty_bar[b], 4 * SETS);  // every epilogue warp drains its column range of buffer b
     }
     fence_barrier_init();
   }
@@ -265,9 +283,7 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
-  if (threadIdx.x < 2 * kBM) thr_s[threadIdx.x] = 0.f;  // published per-set thresholds start at the ReLU floor
-  volatile int* gen_s = reinterpret_cast<volatile int*>(thr_s + 2 * kBM);  // [set]: compactions called so far
-  if (threadIdx.x < 2) gen_s[threadIdx.x] = 0;
+  if (threadIdx.x < 2 * kBM) thr_s[threadIdx.x] = 0.f;  // published per-set 16th-largest values start at the ReLU floor
   tc_fence_before();
   __syncthreads();
   if constexpr (CL > 1) cluster_sync_all();  // peers' barriers are initialised before anyone signals them
@@ -356,40 +372,40 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     const int stid = q * 32 + lane;  // thread index within the set == token row within the row block
     const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
 
-    // Bias row of local tile lt, staged in shared memory two tiles ahead (global-load latency off the critical path);
-    // the scan adds it to the accumulator values chunk by chunk.
-    auto fetch_bias = [&](int lt) {  // lt: CTA-local tile number
-      if (lt < num_lt) {
-        const int nt = static_cast<int>((g_begin + lt) % num_nt);
-        float* bs = bias_s + ((lt % NBUF) * 2 + ((lt / NBUF) & 1)) * BN;  // double-buffered per accumulator buffer
-        for (int c = stid; c < BN; c += 128) {
-          const int gc = nt * BN + c;
-          bs[c] = gc < p.N ? ((p.bias && split == 0) ? __ldg(p.bias + gc) : 0.f) : -INFINITY;
-        }
+    // Bias rows are staged PER WARP (two slots, filled one tile of this warp ahead): lane l fetches columns
+    // [8l, 8l+8) of the row its warp scans next while the current tile is scanned and stores them behind a
+    // __syncwarp.  No barrier ties the four warps of a set together, so a warp that has to compact does not hold
+    // its three peers at the next tile boundary; they only meet through the accumulator hand-off, which has a
+    // whole tile of slack.  The scan reads the row with broadcast loads and forms fl(accumulator + bias) per value.
+    constexpr int kCols = L::kCols;            // this warp scans columns [cb, cb + kCols) of every tile
+    constexpr int kPerLane = kCols / 32;       // bias columns a lane stages
+    static_assert(kCols % 32 == 0 && kPerLane <= 8 && kPerLane % 4 == 0, "bias staging layout");
+    const int cb = set * kCols;
+    float* bias_w = bias_s + ew * (2 * kCols);
+    float nb[kPerLane];
+    auto load_bias = [&](int lt) {  // lt: CTA-local tile number; out-of-range columns get -inf
+      const int nt = static_cast<int>((g_begin + lt) % num_nt);
+#pragma unroll
+      for (int j = 0; j < kPerLane; ++j) {
+        const int gc = nt * BN + cb + lane * kPerLane + j;
+        nb[j] = gc < p.N ? ((p.bias && split == 0) ? __ldg(p.bias + gc) : 0.f) : -INFINITY;
       }
     };
-    // The set's four warps fetched disjoint parts of a bias row: this barrier (at the start of every tile) makes the
-    // row of the tile about to be scanned visible, and orders the next fetch after the last reads of the slot it
-    // overwrites (the tile two uses back).
-    auto set_barrier = [&]() {
-      if (set == 0)
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-      else
-        asm volatile("bar.sync 2, 128;" ::: "memory");
+    auto store_bias = [&](int slot) {
+      float4* dst = reinterpret_cast<float4*>(bias_w + slot * kCols + lane * kPerLane);
+#pragma unroll
+      for (int j = 0; j < kPerLane; j += 4) dst[j / 4] = make_float4(nb[j], nb[j + 1], nb[j + 2], nb[j + 3]);
     };
 
-    int my_gen = 0;
     uint64_t surv[kTopK];
-    float thresh = 0.f;
+    float thresh = 0.f;  // candidates must be > thresh
+    float t16 = 0.f;     // this set's 16th largest value so far (0 while it holds fewer than 16)
     const uint32_t my_base = smem_u32(cand) + ew * L::kBufPerWarp + lane * 8;
     const uint32_t ptr_limit = my_base + (kNewSlots - kCheck) * kSlotStride;
     uint32_t ptr = my_base;
-    // bias rows of the first tile(s) this set will scan
-#pragma unroll
-    for (int t0 = 0; t0 < NBUF; ++t0)
-      if (SETS == 1 || (t0 & 1) == set) fetch_bias(t0);
-    // Segments: maximal runs of this CTA's local tiles inside one row block.  Both sets walk them in lock-step
-    // (a set may own no tile of a short segment): per-row state is reset at the start, merged and emitted at the end.
+    int bslot = 0;
+    // Segments: maximal runs of this CTA's local tiles inside one row block; per-row state is reset at the start,
+    // merged and emitted at the end.
     for (int lt0 = 0; lt0 < num_lt;) {
       const int mb = static_cast<int>((g_begin + lt0) / num_nt);
       const int nt0 = static_cast<int>(g_begin + lt0 - static_cast<int64_t>(mb) * num_nt);
@@ -400,43 +416,55 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
 #pragma unroll
         for (int s = 0; s < kTopK; ++s) surv[s] = 0ull;
         thresh = 0.f;
+        t16 = 0.f;
         ptr = my_base;
         if (lt0 > 0) {
-          // the thresholds published for the previous row block must not leak into this one, and set 0 must be done
+          // the values published for the previous row block must not leak into this one, and set 0 must be done
           // reading set 1's hand-off column before set 1 stages new candidates in it
           if constexpr (SETS == 2) thr_s[set * kBM + stid] = 0.f;
           asm volatile("bar.sync 3, %0;" ::"n"(kEpiWarps * 32) : "memory");
         }
       }
-      int lt = lt0 + ((set - lt0) & (SETS - 1));  // first tile of the segment owned by this set
-      for (; lt < seg_end; lt += SETS) {
+      {  // bias row of the segment's first tile
+        load_bias(lt0);
+        __syncwarp();
+        store_bias(bslot);
+        __syncwarp();
+      }
+      for (int lt = lt0; lt < seg_end; ++lt) {
       const int nt = nt0 + (lt - lt0);
       const int buf = lt % NBUF;
-      if constexpr (EPI == EPI_TOPK && SETS == 2) {
-        // any lower bound of the row's 32nd largest value is a valid filter: adopt the other set's if tighter
-        thresh = fmaxf(thresh, thr_s[(set ^ 1) * kBM + stid]);
+      if constexpr (EPI == EPI_TOPK) {
+        // Lower bounds of the row's final 32nd largest value, beyond this set's own 32nd largest:
+        //  * both sets see alike halves of the row (alternate 128-column runs), so min(own 16th, other's 16th) -- 16 + 16
+        //    distinct values at least that large -- sits near the 32nd largest of the UNION, far above either set's
+        //    own 32nd: the candidate count per row drops from 2 x 32(1 + ln(n/64)) towards 32(1 + ln(n/32));
+        //  * the 32nd largest another column piece of this row block has published (tail split).
+        // Values EQUAL to such a foreign bound may still win on the index tie-break, so the bound enters one ulp low.
+        float foreign = 0.f;
+        if constexpr (SETS == 2) {
+          if (!(p.flags & 1)) foreign = fminf(t16, thr_s[(set ^ 1) * kBM + stid]);
+        }
+        if (is_piece && row < p.M) foreign = fmaxf(foreign, __ldcg(p.part_thr + row));
+        if (foreign > 0.f) thresh = fmaxf(thresh, __uint_as_float(__float_as_uint(foreign) - 1u));
       }
-      float shared_thr = 0.f;  // ... and the one the other pieces of this row block have published (L2 load)
-      if (EPI == EPI_TOPK && is_piece && row < p.M) shared_thr = __ldcg(p.part_thr + row);
-      set_barrier();
-      fetch_bias(lt + NBUF);  // lands in shared memory while this tile is scanned
-      const uint32_t bs_addr = smem_u32(bias_s + ((lt % NBUF) * 2 + ((lt / NBUF) & 1)) * BN);
+      if (lt + 1 < seg_end) load_bias(lt + 1);  // lands in registers while this tile is scanned
+      const uint32_t bs_addr = smem_u32(bias_w + bslot * kCols);
       mbar_wait(&tfull_bar[buf], (lt / NBUF) & 1);
       tc_fence_after();
-      thresh = fmaxf(thresh, shared_thr);
-      const uint32_t t_addr = lane_taddr + buf * BN;
+      const uint32_t t_addr = lane_taddr + buf * BN + cb;
       uint32_t r[2][kChunk];
       tmem_ld_32x32b_x16(t_addr, r[0]);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 2 * kChunk) {
+      for (int c0 = 0; c0 < kCols; c0 += 2 * kChunk) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const int cc = c0 + h * kChunk;
+          const int cc = c0 + h * kChunk;  // column within this warp's range
           tmem_ld_wait();
-          if (cc + kChunk < BN) {
+          if (cc + kChunk < kCols) {
             tmem_ld_32x32b_x16(t_addr + cc + kChunk, r[h ^ 1]);  // prefetch the next chunk
           } else {
-            // the whole tile now sits in registers: hand the buffer back to the MMA issuer before scanning the rest
+            // this warp's columns now sit in registers: hand the buffer back to the MMA issuer before scanning the rest
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[buf]);
@@ -453,7 +481,7 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             v[j + 3] = __uint_as_float(r[h][j + 3]) + b4.w;
           }
           if constexpr (EPI == EPI_TOPK) {
-            const uint32_t nidx0 = ~static_cast<uint32_t>(nt * BN + cc);  // ~(col) == nidx0 - j
+            const uint32_t nidx0 = ~static_cast<uint32_t>(nt * BN + cb + cc);  // ~(col) == nidx0 - j
 #pragma unroll
             for (int g = 0; g < kChunk; g += kCheck) {
 #pragma unroll
@@ -473,30 +501,22 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                     : "memory");
                 ptr = next;
               }
-              // Compaction is called SET-wide: a buffer cycle ends when the slowest of the set's four warps is done, so
-              // a warp compacting alone delays its three peers by a whole compaction (with per-warp triggers ~3/4 of
-              // C3's tiles contained one); when one warp must compact, the others do it at their next check too --
-              // in parallel on the other three sub-partitions -- and their own trigger moves further away.
-              const int gen_seen = gen_s[set];
-              const bool need = __any_sync(0xffffffffu, ptr > ptr_limit);
-              if (need || gen_seen != my_gen) {
-                if (need && gen_seen == my_gen && lane == 0) gen_s[set] = my_gen + 1;
-                my_gen = need && gen_seen == my_gen ? my_gen + 1 : gen_seen;
-                // the next kCheck columns could overflow some lane's column: all lanes compact their own rows
-                const float t = compact_rows(surv, my_base, ptr);
+              // the next kCheck columns could overflow some lane's column: all lanes of the WARP compact their rows
+              if (__any_sync(0xffffffffu, ptr > ptr_limit)) {
+                const float t = compact_rows<CEV>(surv, my_base, ptr, t16);
                 thresh = fmaxf(thresh, t);
                 ptr = my_base;
-                if constexpr (SETS == 2) thr_s[set * kBM + stid] = thresh;
+                if constexpr (SETS == 2) thr_s[set * kBM + stid] = t16;
                 if (is_piece && row < p.M)  // non-negative floats order like their bit patterns
-                  atomicMax(reinterpret_cast<int*>(p.part_thr + row), __float_as_int(thresh));
+                  atomicMax(reinterpret_cast<int*>(p.part_thr + row), __float_as_int(t));
               }
             }
           } else if constexpr (EPI == EPI_NONE) {
             if (v[0] == 1.2345e38f) p.out[0] = 1.f;  // keep the loads alive
           } else {
             if (row < p.M) {
-              float* orow = p.out + split * p.split_stride + static_cast<int64_t>(row) * p.ldo + nt * BN + cc;
-              const bool full_chunk = (nt * BN + cc + kChunk <= p.N) && ((p.ldo & 3) == 0);
+              float* orow = p.out + split * p.split_stride + static_cast<int64_t>(row) * p.ldo + nt * BN + cb + cc;
+              const bool full_chunk = (nt * BN + cb + cc + kChunk <= p.N) && ((p.ldo & 3) == 0);
               if (full_chunk) {
 #pragma unroll
                 for (int j = 0; j < kChunk; j += 4) {
@@ -512,7 +532,7 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
               } else {
 #pragma unroll
                 for (int j = 0; j < kChunk; ++j) {
-                  if (nt * BN + cc + j < p.N) {
+                  if (nt * BN + cb + cc + j < p.N) {
                     float o = v[j];
                     if (p.relu) o = fmaxf(o, 0.f);
                     orow[j] = o;
@@ -523,13 +543,19 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           }
         }
       }
+      // the bias row of the next tile goes into the other slot (its last reader was this warp, one tile ago)
+      if (lt + 1 < seg_end) {
+        store_bias(bslot ^ 1);
+        __syncwarp();
+        bslot ^= 1;
+      }
       }
     if constexpr (EPI == EPI_TOPK) {
       // final compaction; with two sets, set 1 hands its survivors to set 0 through its (now idle) candidate
       // column and set 0 merges; then each thread emits its own row.  Short rows (fewer than 32 positive
       // pre-activations) are completed with zeros at the lowest indices not already chosen, which is the oracle's
       // (value desc, index asc) order for the all-zero tail after ReLU.
-      compact_rows(surv, my_base, ptr);
+      compact_rows<CEV>(surv, my_base, ptr, t16);
       if constexpr (SETS == 2) {
         if (set == 1) {
 #pragma unroll
@@ -541,9 +567,9 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
 #pragma unroll
           for (int i = 0; i < kTopK; ++i) {
             uint64_t y = lds64(peer + (kTopK - 1 - i) * kSlotStride);
-            cmp_exchange(surv[i], y);
+            cmp_exchange<CEV>(surv[i], y);
           }
-          bitonic_merge_desc<kTopK>(surv);
+          bitonic_merge_desc<kTopK, CEV>(surv);
         }
       }
       if (set == 0 && row < p.M) {

@@ -381,10 +381,15 @@ __global__ void __launch_bounds__(256) decode_kernel(const float* __restrict__ t
 // ------------------------------------------------------------------------------------------------ dacts
 // One warp per token: g row in registers, each gathered decoder row reduced to a per-lane partial dot;
 // 32 rows are reduced together with a 31-shuffle transposing reduction so lane j ends with row j's dot.
-template <typename GT, typename WT, int CH>
+// REFINE (fp32 mode of the fused encoder): g = x, `sub` = b_dec, W = W_enc, `bias` = b_enc and the output is
+// relu(dot + bias[idx]) -- the selected pre-activations recomputed with an fp32 FMA chain.  The tensor-core product
+// that SELECTS them accumulates 3 x d/8 partial sums in TMEM with truncating adds, good for ~1e-6 of a value; the
+// gradients (d act = e . W_dec[f] with e nearly orthogonal to the selected rows) need the values themselves to ~1e-7.
+template <typename GT, typename WT, int CH, bool REFINE = false>
 __global__ void __launch_bounds__(256) dacts_kernel(const GT* __restrict__ g, const int32_t* __restrict__ top_idx,
                                                     const WT* __restrict__ W, float* __restrict__ dacts, int64_t N,
-                                                    int d, int k) {
+                                                    int d, int k, const float* __restrict__ sub = nullptr,
+                                                    const float* __restrict__ bias = nullptr) {
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   for (int64_t t = static_cast<int64_t>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); t < N;
@@ -394,6 +399,12 @@ __global__ void __launch_bounds__(256) dacts_kernel(const GT* __restrict__ g, co
     for (int i = 0; i < CH; ++i) {
       const int c = lane * 4 + i * 128;
       gv[i] = c < d ? load4(g + t * d + c) : make_float4(0, 0, 0, 0);
+      if constexpr (REFINE) {
+        if (c < d) {
+          const float4 sb = load4(sub + c);
+          gv[i] = make_float4(gv[i].x - sb.x, gv[i].y - sb.y, gv[i].z - sb.z, gv[i].w - sb.w);
+        }
+      }
     }
     for (int j0 = 0; j0 < k; j0 += 32) {
       const int jn = min(32, k - j0);
@@ -420,7 +431,11 @@ __global__ void __launch_bounds__(256) dacts_kernel(const GT* __restrict__ g, co
         part[j] = s;
       }
       const float tot = warp_transpose_reduce32(part, lane);
-      if (lane < jn) dacts[t * k + j0 + lane] = tot;
+      if constexpr (REFINE) {
+        if (lane < jn && my_i >= 0) dacts[t * k + j0 + lane] = fmaxf(tot + __ldg(bias + my_i), 0.f);
+      } else {
+        if (lane < jn) dacts[t * k + j0 + lane] = tot;
+      }
     }
   }
 }
@@ -1249,6 +1264,23 @@ extern "C" int freud_topk_dacts(const void* g, int g_is_bf16, const int32_t* top
     if (w_is_bf16) launch_dacts<float, __nv_bfloat16>(g, top_idx, W_dec, dacts, N, (int)d, (int)k, STREAM);
     else launch_dacts<float, float>(g, top_idx, W_dec, dacts, N, (int)d, (int)k, STREAM);
   }
+  FREUD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int freud_topk_refine(const float* x, const float* b_dec, const float* W_enc, const float* b_enc,
+                                 const int32_t* top_idx, float* top_vals, int64_t N, int64_t d, int64_t k,
+                                 void* stream) {
+  FREUD_REQUIRE(N > 0 && k > 0 && d % 4 == 0 && d <= 2048, "refine needs d % 4 == 0 and d <= 2048");
+  const int grid = grid_for(N, 8, sm_count() * 8);
+#define LR(CH)                                                                                                     \
+  dacts_kernel<float, float, CH, true><<<grid, 256, 0, STREAM>>>(x, top_idx, W_enc, top_vals, N, (int)d, (int)k, \
+                                                                    b_dec, b_enc)
+  if (d <= 384) LR(3);
+  else if (d <= 768) LR(6);
+  else if (d <= 1280) LR(10);
+  else LR(16);
+#undef LR
   FREUD_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

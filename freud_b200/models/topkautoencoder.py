@@ -159,6 +159,9 @@ class TopKAutoEncoder(nn.Module):
             if self.cfg.k == ops.K_FUSED:
                 xc_hi, xc_lo, we_hi, we_lo, _ = topk_engine.encode_operands(x3, self.encoder.weight, self.b_dec, prec)
                 vals, idx = ops.topk_encode(xc_hi, xc_lo, we_hi, we_lo, self.encoder.bias, prec)
+                if prec == FP32:
+                    ops.topk_refine(x3.view(-1, self.d_in), self.b_dec.data, self.encoder.weight.data,
+                                    self.encoder.bias.data, idx, vals)
             else:
                 return self.select_topk(self.pre_acts(x))
         lead = x.shape[:-1]
@@ -201,6 +204,7 @@ class TopKAutoEncoder(nn.Module):
         eps = torch.finfo(self.W_dec.dtype).eps
         if self.W_dec.is_cuda:
             ops.rownorm_project(self.W_dec.data, eps)
+            self._weights_epoch = getattr(self, "_weights_epoch", 0) + 1  # SAETrainer rebuilds its bf16 copies
         else:
             # constructor-time only: the reference builds the module on the CPU and moves it afterwards
             # (train_sae.py:358-362); this is parameter initialisation, not the hot path.

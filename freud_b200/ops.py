@@ -84,6 +84,14 @@ def topk_encode(xc_hi, xc_lo, w_hi, w_lo, b_enc, precision: int):
     return vals, idx
 
 
+def topk_refine(x2, b_dec, W_enc, b_enc, idx, vals):
+    """fp32 mode: selected pre-activations recomputed in place with an fp32 FMA chain (see freud_topk_refine)."""
+    N, d = x2.shape
+    call("freud_topk_refine", _ptr(_f32(x2, "x")), _ptr(b_dec), _ptr(_f32(W_enc, "W_enc")), _ptr(b_enc), _ptr(idx),
+         _ptr(vals), N, d, idx.shape[1], _stream())
+    return vals
+
+
 def gemm_nt(a_hi, a_lo, b_hi, b_lo, bias, relu: bool, precision: int, out=None):
     """out[M,N] = act(A @ B^T + bias) on the tensor cores (operands as from split_operand / topk_prep_x)."""
     M, K = a_hi.shape

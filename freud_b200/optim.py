@@ -41,6 +41,11 @@ def clip_grad_norm_(parameters, max_norm: float) -> torch.Tensor:
 
 
 class _FusedBase(torch.optim.Optimizer):
+    def set_shadows(self, mapping):
+        """mapping: {parameter: bf16 tensor of the same shape}.  The update kernel then also writes the rounded new
+        value of that parameter there (2 B/param more traffic instead of a separate 6 B/param conversion pass)."""
+        self._shadows = {id(p): t for p, t in mapping.items()}
+
     def _prepare(self, group):
         ps = _collect(group["params"])
         for p in ps:
@@ -54,9 +59,11 @@ class _FusedBase(torch.optim.Optimizer):
     def _lists(self, ps):
         for i in range(0, len(ps), ops._lib.MAX_TENSORS):
             chunk = ps[i:i + ops._lib.MAX_TENSORS]
+            sh = getattr(self, "_shadows", None)
             yield chunk, ops.make_tensor_list([p.data for p in chunk], [p.grad for p in chunk],
                                               [self.state[p]["exp_avg"] for p in chunk],
-                                              [self.state[p]["exp_avg_sq"] for p in chunk])
+                                              [self.state[p]["exp_avg_sq"] for p in chunk],
+                                              [sh.get(id(p)) for p in chunk] if sh else None)
 
 
 class FusedAdam(_FusedBase):

@@ -42,6 +42,7 @@ class TopKState:
     offsets: Optional[torch.Tensor] = None  # CSC offsets of the returned encoding (did_fire bookkeeping)
     scal_ready: Optional[torch.cuda.Event] = None  # set when `scal` is still being produced on a side stream
     csc_ready: Optional[torch.cuda.Event] = None   # recorded once `offsets` is complete on the main stream
+    csc: Optional[tuple] = None  # (offsets, entries, event) of the main selection, built on the side stream
     extra: dict = field(default_factory=dict)
 
 
@@ -56,7 +57,22 @@ class TopKResult:
     mse: torch.Tensor
 
 
-def encode_operands(x, W_enc, b_dec, precision, dp=None):
+_aux_streams = {}
+
+
+def aux_stream(device):
+    """Side stream for work that depends only on the selected indices (the CSC index of the backward): it runs beside
+    the decode / activation-gradient kernels instead of between them."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    s = _aux_streams.get(key)
+    if s is None:
+        s = _aux_streams[key] = torch.cuda.Stream(torch.device("cuda", key))
+    return s
+
+
+def encode_operands(x, W_enc, b_dec, precision, dp=None, we_hi=None):
+    """we_hi: the bf16 copy of W_enc when the caller maintains one (the fused Adam kernel writes it next to the fp32
+    parameter, so the per-step conversion pass disappears); bf16 mode only."""
     if dp is None:
         xc_hi, xc_lo, tv = ops.topk_prep_x(x, b_dec, precision)
     else:
@@ -71,26 +87,34 @@ def encode_operands(x, W_enc, b_dec, precision, dp=None):
             colmean.record_stream(side)
             with torch.cuda.stream(side):
                 tv = dp.global_total_variance(tv, colmean, x.shape[0])
-    we_hi, we_lo = ops.split_operand(W_enc, precision)
+    if we_hi is not None and precision == BF16:
+        we_lo = None
+    else:
+        we_hi, we_lo = ops.split_operand(W_enc, precision)
     return xc_hi, xc_lo, we_hi, we_lo, tv
 
 
 def topk_forward(x, W_enc, b_enc, W_dec, b_dec, k, *, precision, dead_mask=None, auxk_alpha=0.0, multi_topk=False,
-                 need_grad=True, dp=None, defer_scal=False, num_dead=None):
+                 need_grad=True, dp=None, defer_scal=False, num_dead=None, shadows=None):
     """dp: optional freud_b200.parallel.DataParallel -- makes tv / sse (and with them every loss and gradient
     scale) those of the batch concatenated over ranks; gradients stay rank-local sums for the caller to allreduce.
     defer_scal (data parallel, fused main path only): the loss scalars are produced on dp's side stream and the
     main stream is NOT joined; st.scal_ready is the event to wait for before reading them (topk_backward does).
     num_dead: `int(dead_mask.sum())` when the caller already holds it (the trainer reads it back asynchronously during
-    the previous step); otherwise it is read here, which synchronises with the device like the reference (:109)."""
+    the previous step); otherwise it is read here, which synchronises with the device like the reference (:109).
+    shadows: {"encoder.weight": bf16 [n,d], "W_dec": bf16 [n,d]} up-to-date bf16 copies of the weights (bf16 mode)."""
     if x.dim() != 3:
         raise ValueError("x must be [B, T, d]")
     x = x.contiguous()
     B, T, d = x.shape
     N, n = B * T, W_enc.shape[0]
     x2 = x.view(N, d)
-    xc_hi, xc_lo, we_hi, we_lo, tv = encode_operands(x, W_enc, b_dec, precision, dp)
-    wd = ops.split_operand(W_dec, BF16)[0] if precision == BF16 else W_dec
+    shadows = shadows if (shadows and precision == BF16) else {}
+    xc_hi, xc_lo, we_hi, we_lo, tv = encode_operands(x, W_enc, b_dec, precision, dp, shadows.get("encoder.weight"))
+    if precision == BF16:
+        wd = shadows["W_dec"] if "W_dec" in shadows else ops.split_operand(W_dec, BF16)[0]
+    else:
+        wd = W_dec
     # reference: `int(dead_mask.sum())` (topkautoencoder.py:109) -- one 8-byte device->host read, as upstream
     if num_dead is None:
         num_dead = int(dead_mask.sum()) if dead_mask is not None else 0
@@ -101,9 +125,25 @@ def topk_forward(x, W_enc, b_enc, W_dec, b_dec, k, *, precision, dead_mask=None,
     pre = None
     if fused_main:
         vals, idx = ops.topk_encode(xc_hi, xc_lo, we_hi, we_lo, b_enc, precision)
+        if precision == FP32:
+            ops.topk_refine(x2, b_dec, W_enc, b_enc, idx, vals)
     else:
         pre = ops.gemm_nt(xc_hi, xc_lo, we_hi, we_lo, b_enc, True, precision)
         vals, idx = ops.row_topk(pre, k)
+
+    csc = None
+    if fused_main and need_grad and not generic:
+        # the feature-major (CSC) index of the backward depends on the indices alone: built on a side stream while
+        # the main stream decodes and forms the activation gradients
+        cur, side = torch.cuda.current_stream(), aux_stream(x.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            offsets, entries = ops.csc_build(idx, n)
+            csc_done = side.record_event()
+        idx.record_stream(side)
+        offsets.record_stream(cur)
+        entries.record_stream(cur)
+        csc = (offsets, entries, csc_done)
 
     resid_dtype = None
     if generic:
@@ -139,6 +179,7 @@ def topk_forward(x, W_enc, b_enc, W_dec, b_dec, k, *, precision, dead_mask=None,
     st = TopKState(precision, x2, xc_hi, wd, W_enc, b_dec, k, n, scal, generic, vals, idx, e, colsum_e,
                    auxk_alpha=auxk_alpha)
     st.scal_ready = scal_ready
+    st.csc = csc
 
     auxk = zero
     if num_dead > 0:
@@ -229,9 +270,14 @@ def topk_backward(st: TopKState, g_fvu, g_aux=None, g_multi=None, *, out=None, o
         else:
             scales = st.scal[2:4] * float(g_fvu)
         dacts = ops.topk_dacts(st.e, st.idx, st.wd)
-        offsets, entries = ops.csc_build(st.idx, n)
+        if st.csc is not None:
+            offsets, entries, csc_done = st.csc
+            torch.cuda.current_stream().wait_event(csc_done)
+            st.csc_ready = csc_done
+        else:
+            offsets, entries = ops.csc_build(st.idx, n)
+            st.csc_ready = torch.cuda.current_stream().record_event()
         st.offsets = offsets
-        st.csc_ready = torch.cuda.current_stream().record_event()
         if on_offsets is not None:
             on_offsets(offsets)
         if st.scal_ready is not None:  # gradient scale produced on the data-parallel side stream

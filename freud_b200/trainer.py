@@ -84,9 +84,31 @@ class SAETrainer:
             # load torch's lazily-initialised kernels for the dead-mask read-back now, not in the first step that
             # crosses the threshold (a one-off ~60 ms module load otherwise lands inside the training loop)
             int((self.num_frames_since_fired > (dead_feature_threshold or 0)).sum())
+            self._shadows, self._shadow_versions = {}, None
         self.last_state = None
         self._dead_next = None  # (mask, event, counter version) prefetched for the next step
         self._dead_pinned = torch.zeros(1, dtype=torch.int64).pin_memory() if dev.type == "cuda" else None
+
+    def _fresh_shadows(self):
+        """bf16 copies of W_enc / W_dec for the tensor-core and gather kernels.  Built once; afterwards the fused Adam
+        kernel rewrites them together with the fp32 parameters.  In-place torch writes to a parameter
+        (load_state_dict, `p.copy_`, `p.mul_` under no_grad) bump its version counter and the module's own
+        set_decoder_norm_to_unit_norm bumps `_weights_epoch`: either triggers a rebuild.  Writes through `p.data`
+        are invisible to both -- call `invalidate_weight_copies()` after editing weights that way."""
+        if self.precision != BF16:
+            return None
+        versions = tuple(self.params[k]._version for k in ("encoder.weight", "W_dec")) + \
+            tuple(self.params[k].data_ptr() for k in ("encoder.weight", "W_dec")) + \
+            (getattr(self.model, "_weights_epoch", 0),)
+        if self._shadow_versions != versions or not self._shadows:
+            for k in ("encoder.weight", "W_dec"):
+                self._shadows[k] = ops.split_operand(self.params[k].data, BF16)[0]
+            self.optimizer.set_shadows({self.params[k]: self._shadows[k] for k in self._shadows})
+            self._shadow_versions = versions
+        return self._shadows
+
+    def invalidate_weight_copies(self):
+        self._shadow_versions = None
 
     # ------------------------------------------------------------------------------------------ TopK
     def _topk_step(self, x):
@@ -113,7 +135,7 @@ class SAETrainer:
                                            m.b_dec.data, cfg.k, precision=self.precision, dead_mask=dead_mask,
                                            auxk_alpha=float(cfg.auxk_alpha), multi_topk=bool(cfg.multi_topk),
                                            need_grad=True, dp=self.dp, defer_scal=self.dp is not None,
-                                           num_dead=num_dead)
+                                           num_dead=num_dead, shadows=self._fresh_shadows())
         # loss = fvu + auxk_loss + multi_topk_fvu / 8   (train_sae.py:441)
         grads = {k: p.grad for k, p in self.params.items()}
         fired_early = []

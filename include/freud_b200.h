@@ -115,6 +115,12 @@ int freud_topk_decode(const float* top_vals, const int32_t* top_idx, const void*
 int freud_topk_dacts(const void* g, int g_is_bf16, const int32_t* top_idx, const void* W_dec, int w_is_bf16,
                      float* dacts, int64_t N, int64_t d, int64_t k, void* stream);
 
+/* fp32 mode: top_vals[t,j] <- relu((x[t] - b_dec) . W_enc[top_idx[t,j]] + b_enc[top_idx[t,j]]) with an fp32 FMA
+ * chain (topkautoencoder.py:72-77 restricted to the selected latents): the tensor-core product selects, this pass
+ * restores the selected values to fp32-GEMM accuracy.  Entries with index -1 are left untouched. */
+int freud_topk_refine(const float* x, const float* b_dec, const float* W_enc, const float* b_enc,
+                      const int32_t* top_idx, float* top_vals, int64_t N, int64_t d, int64_t k, void* stream);
+
 /* Elementwise AuxK / multi-TopK gradient seeds (autograd of topkautoencoder.py:126-138):
  *   out = alpha * a + beta * b   (b may be NULL), alpha/beta read from device scalars coef[0], coef[1];
  * written as bf16 or fp32. */
