@@ -394,6 +394,14 @@ def parity_check(w, precision, dp, device, x_local, rank, world, sharded):
         state = tr.gathered_state()
         full_x = x_local
         grads = None
+    elif getattr(tr, "fused_dp", False):
+        tr.consolidate()  # fp32 masters are sharded by the fused optimiser: gather them for the comparison
+        parts = [torch.empty_like(x_local) for _ in range(world)]
+        dist.all_gather(parts, x_local)
+        full_x = torch.cat(parts, 0) if rank == 0 else None
+        del parts
+        state = {k: tr.params[k].data for k in _KEYS}
+        grads = None  # each rank holds the summed gradient of its own slice only
     else:
         parts = [torch.empty_like(x_local) for _ in range(world)]
         dist.all_gather(parts, x_local)
@@ -423,6 +431,24 @@ def parity_check(w, precision, dp, device, x_local, rank, world, sharded):
     return res
 
 
+def symmetric_memory_ok(device):
+    """All ranks agree on whether torch's symmetric memory (NVLink peer mappings) works on this box."""
+    import torch.distributed as dist
+
+    ok = 1
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+
+        t = symm_mem.empty(1024, dtype=torch.float32, device=device)
+        symm_mem.rendezvous(t, dist.group.WORLD)
+    except Exception as ex:  # noqa: BLE001
+        print(f"[bench] symmetric memory unavailable ({ex!r}): falling back to the NCCL all-reduce path", file=sys.stderr)
+        ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return bool(flag.item())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -433,6 +459,8 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the pre-timing parity check")
+    ap.add_argument("--dp-mode", default="fused", choices=["fused", "nccl"],
+                    help="data parallel gradient exchange: fused peer-memory reduce-scatter + sharded Adam, or NCCL")
     ap.add_argument("--no-eager", action="store_true", help="skip the stock-PyTorch-eager-on-this-GPU arm")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel share table (json) here")
     args = ap.parse_args()
@@ -465,7 +493,8 @@ def main():
         if not sharded:
             from freud_b200.parallel import DataParallel
 
-            dp = DataParallel()
+            fused = world > 1 and args.dp_mode == "fused" and symmetric_memory_ok(device)
+            dp = DataParallel(fused=fused)
     # all work runs on an explicit non-blocking stream: the legacy default stream serialises with copy streams
     main_stream = torch.cuda.Stream(device)
     torch.cuda.set_stream(main_stream)
@@ -643,7 +672,11 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if sharded else "weak",
         "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
         "config": {"workload": f"{args.workload}: {w['desc']}", "global_batch_tokens": tokens_per_step,
-                   "parallelism": (f"feature-sharded x{world}" if sharded else f"dp{world}"), "optimizer": "adam+clip(1.0)+linear-warmup",
+                   "parallelism": (f"feature-sharded x{world}" if sharded else f"dp{world}"),
+                   "dp_exchange": (None if dp is None else ("fused peer-memory reduce-scatter + sharded Adam + bf16 all-gather"
+                                                            + (" (multimem)" if getattr(tr.optimizer, "multicast", False) else "")
+                                                            if getattr(tr, "fused_dp", False) else "NCCL all-reduce")),
+                   "optimizer": "adam+clip(1.0)+linear-warmup",
                    "l2": f"{n_bufs} rotating input batches of {B * T * d * 4 / 1e6:.0f} MB (> 126 MB L2)"
                    if B * T * d * 4 > 126e6 else f"{n_bufs} rotating input batches ({B * T * d * 4 / 1e6:.0f} MB each, "
                    f"{n_bufs * B * T * d * 4 / 1e6:.0f} MB total > 126 MB L2)"},

@@ -53,7 +53,7 @@ SIGNATURES = {
     "freud_csc_build": [_p, _i64, _i64, _i64, _p, _p, _p, _p],
     "freud_csc_meta": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _p],
     "freud_topk_sparse_grads": [_p, _p, _p, _i, _p, _i, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i, _p],
-    "freud_topk_bdec_grad": [_p, _p, _p, _p, _p, _i64, _i64, _i, _p],
+    "freud_topk_bdec_grad": [_p, _p, _p, _p, _i, _p, _i64, _i64, _i, _p],
     "freud_topk_loss_scalars": [_p, _p, _p, _i64, _p],
     "freud_dead_latent_update": [_p, _p, _i64, _i64, _p],
     "freud_rownorm_project": [_p, _i64, _i64, _f, _p],
@@ -67,6 +67,9 @@ SIGNATURES = {
     "freud_clip_grads": [C.POINTER(TensorList), _p, _f, _p, _p],
     "freud_adam_step": [C.POINTER(TensorList), _d, _d, _d, _d, _i64, _p, _f, _p],
     "freud_radam_step": [C.POINTER(TensorList), _d, _d, _d, _d, _d, _i64, _p, _f, _p],
+    "freud_dp_reduce_scatter": [_p, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _p],
+    "freud_dp_adam_allgather": [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _i64, _d, _d, _d, _d,
+                                _i64, _p, _f, _i, _p],
     "freud_feature_absmax": [_p, _p, _i, _i64, _p, _i64, _p],
     "freud_col_absmax": [_p, _i64, _i64, _p, _p],
     "freud_search_dense": [_p, _i, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p],
@@ -83,6 +86,7 @@ KERNELS_PER_CALL = {
     "freud_dead_latent_update": 1, "freud_rownorm_project": 1, "freud_remove_parallel_grad": 1,
     "freud_l1_colnorm": 1, "freud_l1_loss_reduce": 1, "freud_l1_dz": 1, "freud_l1_weight_grad": 1, "freud_l1_grad_operands": 1,
     "freud_grad_sumsq": 1, "freud_clip_grads": 1, "freud_adam_step": 1, "freud_radam_step": 1,
+    "freud_dp_reduce_scatter": 1, "freud_dp_adam_allgather": 1,
     "freud_feature_absmax": 1, "freud_col_absmax": 1,
     "freud_search_dense": 1, "freud_search_indexed": 1, "freud_search_topn": 1,
 }

@@ -1,5 +1,6 @@
 // Host launchers for the tcgen05 encoder GEMM kernels (freud_topk_encode, freud_gemm_nt).
 #include "gemm_sm100.cuh"
+#include "topk_sm100.cuh"
 #include "host_common.h"
 #include "../../include/freud_b200.h"
 
@@ -154,7 +155,64 @@ static int launch_gemm(const void* a_hi, const void* a_lo, const void* b_hi, con
   return 0;
 }
 
-// Encoder variant (epilogue sets / smem stages / multicast cluster); FREUD_ENC_VARIANT overrides for experiments.
+// Fused top-k encoder with specialised scanner / compactor epilogue warps (topk_sm100.cuh): one CTA per row block,
+// the row blocks of a partial last wave cut into column pieces exactly as in launch_gemm.
+template <int BN, int STAGES, bool TF32, int CEV = 0>
+static int launch_topk(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, GemmParams p, int passes,
+                       cudaStream_t stream) {
+  using L = TopkSmem<BN, STAGES>;
+  const int eb = TF32 ? 4 : 2;
+  CUtensorMap mA0, mA1, mB0, mB1;
+  if (make_tensor_map_2d(&mA0, a_hi, p.M, p.K, p.K, eb, kBM)) return 3;
+  if (make_tensor_map_2d(&mB0, b_hi, p.N, p.K, p.K, eb, BN)) return 3;
+  if (passes > 1) {
+    if (make_tensor_map_2d(&mA1, a_lo, p.M, p.K, p.K, eb, kBM)) return 3;
+    if (make_tensor_map_2d(&mB1, b_lo, p.N, p.K, p.K, eb, BN)) return 3;
+  } else {
+    mA1 = mA0;
+    mB1 = mB0;
+  }
+  p.passes = passes;
+  auto kern = sm100_topk_kernel<BN, STAGES, TF32, CEV>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FREUD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    attr_set = true;
+  }
+  const int num_mb = (p.M + kBM - 1) / kBM;
+  const int num_nt = (p.N + BN - 1) / BN;
+  int grid = num_mb;
+  if (p.part_vals != nullptr) {
+    int full = 0;
+    const int S = plan_tail_split(num_mb, num_nt, &full);
+    const int64_t stride = static_cast<int64_t>(num_mb) * kBM * 32;
+    if (S > 1 && tail_split_bytes(num_mb, S) <= p.part_stride) {  // part_stride carries the workspace size in
+      p.full_count = full;
+      p.tail_split = S;
+      p.part_stride = stride;
+      p.part_idx = reinterpret_cast<int32_t*>(p.part_vals + S * stride);
+      p.part_thr = reinterpret_cast<float*>(p.part_idx + S * stride);
+      FREUD_CHECK_CUDA(cudaMemsetAsync(p.part_thr, 0, static_cast<size_t>(num_mb) * kBM * sizeof(float), stream));
+      grid = full + (num_mb - full) * S;
+    } else {
+      p.part_vals = nullptr;
+    }
+  }
+  kern<<<grid, L::kThreads, L::kTotal, stream>>>(mA0, mA1, mB0, mB1, p);
+  FREUD_CHECK_CUDA(cudaGetLastError());
+  if (p.tail_split > 1) {
+    const int row0 = p.full_count * kBM;
+    topk_merge_pieces_kernel<<<(p.M - row0 + 7) / 8, 256, 0, stream>>>(p.part_vals, p.part_idx, p.part_stride, p.top_vals,
+                                                                       p.top_idx, p.M, row0, p.tail_split);
+    FREUD_CHECK_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+// Encoder variant (FREUD_ENC_VARIANT, experiments): 0 = specialised scanner / compactor warps, compare-exchange on the
+// keys as doubles (default; C2 0.49 ms); 4 / 5 = same with the borrow-mask / integer-predicate compare-exchange (0.58 /
+// 0.63 ms); 1 = generic kernel, two column-split epilogue sets compacting inline; 3 = generic kernel, one inline set
+// (0.68 ms); 6-8 = mainloop probes.
 static int encoder_variant() {
   static int v = -1;
   if (v < 0) {
@@ -196,18 +254,21 @@ extern "C" int freud_topk_encode(const void* xc_hi, const void* xc_lo, const voi
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (precision == FREUD_BF16) {
     switch (encoder_variant()) {
+      case 1: return launch_gemm<256, 3, EPI_TOPK, false, 2, 1>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
       case 2: return launch_gemm<256, 3, EPI_TOPK, false, 2, 2>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
-      // (a triple-buffered BN = 160 variant, launch_gemm<160, 4, EPI_TOPK, false, 2, 1, 3>, measured slower:
-      //  2.02 vs 1.78 ms on C3 -- per-tile fixed costs outweigh the extra MMA/scan overlap)
       case 3: return launch_gemm<256, 3, EPI_TOPK, false, 1, 1>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
-      case 10: return launch_gemm<256, 3, EPI_TOPK, false, 2, 1, 2, 1>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
+      case 4: return launch_topk<256, 3, false, 0>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
+      case 5: return launch_topk<256, 3, false, 1>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
       case 6: p.out = top_vals; return launch_gemm<256, 3, EPI_NONE, false, 1, 1>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
       case 7: p.out = top_vals; return launch_gemm<256, 4, EPI_NONE, false, 1, 1>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
       case 8: p.out = top_vals; return launch_gemm<256, 3, EPI_NONE, false, 2, 1>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
-      default: return launch_gemm<256, 3, EPI_TOPK, false, 2, 1>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
+      default: return launch_topk<256, 3, false, 2>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
     }
   }
-  if (precision == FREUD_FP32) return launch_gemm<256, 3, EPI_TOPK, true, 2, 1>(xc_hi, xc_lo, w_hi, w_lo, p, 3, s);
+  if (precision == FREUD_FP32) {
+    if (encoder_variant() == 1) return launch_gemm<256, 3, EPI_TOPK, true, 2, 1>(xc_hi, xc_lo, w_hi, w_lo, p, 3, s);
+    return launch_topk<256, 3, true, 2>(xc_hi, xc_lo, w_hi, w_lo, p, 3, s);
+  }
   FREUD_REQUIRE(false, "unknown precision");
 }
 

@@ -86,7 +86,8 @@ struct GemmParams {
   // back, so the TMA / MMA of the next row block overlaps the store epilogue of the previous one (a one-tile-wide
   // product such as the L1 SAE's n = 200 otherwise pays the pipeline fill and drain once per 128 rows).
   int persistent;
-  int flags;  // experiments (FREUD_ENC_FLAGS): bit 0 = do not share 16th-largest values between the epilogue sets
+  int flags;  // experiments (FREUD_ENC_FLAGS): bit 0 = do not share 16th-largest values between the epilogue sets;
+              // bits 1-4 = bare spin (no sleep between polls) in the producer / MMA-empty / MMA-full / epilogue waits
 };
 
 template <int BN, int STAGES, int EPI, int SETS, int NBUF = 2>
@@ -116,6 +117,14 @@ struct GemmSmem {
 // subtract-with-borrow pair, one arithmetic shift to a mask, four LOP3 selects -- 7 instructions, carry flag only.
 template <int CEV = 0>
 __device__ __forceinline__ void cmp_exchange(uint64_t& hi, uint64_t& lo) {
+  if constexpr (CEV == 2) {  // experiment: the keys as positive doubles (same order as their bit patterns: value
+                             // bits < 0x7f800000 never form a NaN / Inf exponent): one DSETP and four selects
+    const bool sw = __longlong_as_double(static_cast<long long>(hi)) < __longlong_as_double(static_cast<long long>(lo));
+    const uint64_t mx = sw ? lo : hi, mn = sw ? hi : lo;
+    hi = mx;
+    lo = mn;
+    return;
+  }
   if constexpr (CEV == 1) {  // experiment: one 64-bit compare (ISETP + ISETP.EX) and four predicated selects
     const bool sw = hi < lo;
     const uint64_t mx = sw ? lo : hi, mn = sw ? hi : lo;
@@ -204,7 +213,12 @@ __device__ __noinline__ float compact_rows(uint64_t (&surv)[kTopK], uint32_t my_
 // NBUF accumulator buffers of BN columns live in TMEM (NBUF * BN <= 512).  With two epilogue sets scanning two
 // buffers, a THIRD buffer (BN = 160) lets the MMA issuer fill the next tile meanwhile: the tile rate becomes
 // min(1/M, 2/E) instead of 2/(M + E)  (M = MMA time, E = scan + bias pre-store time of one tile).
-template <int BN, int STAGES, int EPI, bool TF32, int SETS, int CL, int NBUF = 2, int CEV = 0>
+// AMN / BMN: the operand is MN-major -- the global matrix is stored [K, M] (resp. [K, N]) row-major, e.g. a
+// [tokens, features] activation matrix used as the A^T of a weight-gradient product whose K axis is the token axis.
+// The TMA producer then fetches 64-column x 64-row boxes and the MMA reads them through MN-major descriptors, so no
+// physical transpose of the operand is ever made (bf16 only).
+template <int BN, int STAGES, int EPI, bool TF32, int SETS, int CL, int NBUF = 2, int CEV = 0, bool AMN = false,
+          bool BMN = false>
 __global__ void __launch_bounds__(128 + SETS * 128, 1)
 sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                   const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
@@ -217,6 +231,7 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                                  : NBUF * BN <= 256 ? 256 : 512;  // allocation granularity: power of two
   static_assert(NBUF * BN <= 512, "accumulator buffers exceed the 512 TMEM columns");
   static_assert(kNewSlots == kTopK, "the merge step pairs survivor i with candidate 31-i");
+  static_assert(!(AMN || BMN) || (!TF32 && CL == 1 && BN % 64 == 0), "MN-major operands: bf16, no multicast");
   const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0u;
 
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -305,12 +320,23 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           // pass order (3-pass split): hi*lo, lo*hi, then the dominant hi*hi term
           const CUtensorMap* ma = (p.passes == 1 || pass != 1) ? &mapA0 : &mapA1;
           const CUtensorMap* mb = (p.passes == 1 || pass != 0) ? &mapB0 : &mapB1;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (p.flags & 2) mbar_wait(&empty_bar[stage], phase ^ 1);
+          else mbar_wait_relaxed(&empty_bar[stage], phase ^ 1, 64);  // STAGES deep: nothing waits for this warp
           uint8_t* sa = ring + stage * L::kStageBytes;
           uint8_t* sb = sa + L::kABytes;
           mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
-          tma_load_2d(sa, ma, &full_bar[stage], (kb0 + kb) * kBKe, m0, kEvictNormal);
-          if constexpr (CL == 1) {
+          if constexpr (AMN) {  // two 64-wide MN atoms of 64 K-rows each
+#pragma unroll
+            for (int h = 0; h < kBM / 64; ++h)
+              tma_load_2d(sa + h * 8192, ma, &full_bar[stage], m0 + h * 64, (kb0 + kb) * kBKe, kEvictNormal);
+          } else {
+            tma_load_2d(sa, ma, &full_bar[stage], (kb0 + kb) * kBKe, m0, kEvictNormal);
+          }
+          if constexpr (BMN) {
+#pragma unroll
+            for (int h = 0; h < BN / 64; ++h)
+              tma_load_2d(sb + h * 8192, mb, &full_bar[stage], nt * BN + h * 64, (kb0 + kb) * kBKe, kEvictLast);
+          } else if constexpr (CL == 1) {
             tma_load_2d(sb, mb, &full_bar[stage], (kb0 + kb) * kBKe, nt * BN, kEvictLast);
           } else {
             // every CTA of the cluster walks the same weight tiles: fetch 1/CL of the tile, multicast it to all
@@ -328,24 +354,27 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   } else if (warp_idx == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(TF32 ? 2u : 1u, kBM, BN);
+      constexpr uint32_t idesc = make_idesc(TF32 ? 2u : 1u, kBM, BN, AMN, BMN);
       int stage = 0;
       uint32_t phase = 0;
       for (int lt = 0; lt < num_lt; ++lt) {
         const int buf = lt % NBUF;
         // the epilogue arrives once it has read the buffer's previous tile out of TMEM (fresh buffers pass at once)
-        mbar_wait(&tempty_bar[buf], ((lt / NBUF) & 1) ^ 1);
+        if (p.flags & 4) mbar_wait(&tempty_bar[buf], ((lt / NBUF) & 1) ^ 1);
+        else mbar_wait_relaxed(&tempty_bar[buf], ((lt / NBUF) & 1) ^ 1, 32);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * BN;
         for (int vk = 0; vk < num_vk; ++vk) {
-          mbar_wait(&full_bar[stage], phase);
+          if (p.flags & 8) mbar_wait(&full_bar[stage], phase);
+          else mbar_wait_relaxed(&full_bar[stage], phase, 20);
           tc_fence_after();
           const uint32_t sa = smem_u32(ring + stage * L::kStageBytes);
           const uint32_t sb = sa + L::kABytes;
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {  // 4 x 32-byte UMMA_K steps per 128-byte k-block
-            const uint64_t adesc = make_kmajor_sw128_desc(sa + k4 * 32);
-            const uint64_t bdesc = make_kmajor_sw128_desc(sb + k4 * 32);
+            // K-major: 32 bytes along the 128-byte row per K = 16 step; MN-major: 16 K-rows of 128 bytes = 2048 B
+            const uint64_t adesc = AMN ? make_mnmajor_sw128_desc(sa + k4 * 2048, 8192) : make_kmajor_sw128_desc(sa + k4 * 32);
+            const uint64_t bdesc = BMN ? make_mnmajor_sw128_desc(sb + k4 * 2048, 8192) : make_kmajor_sw128_desc(sb + k4 * 32);
             const uint32_t acc = (vk > 0 || k4 > 0) ? 1u : 0u;  // the tile's first MMA overwrites the buffer
             if constexpr (TF32)
               mma_tf32_ss(d_tmem, adesc, bdesc, idesc, acc);
@@ -450,7 +479,8 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       }
       if (lt + 1 < seg_end) load_bias(lt + 1);  // lands in registers while this tile is scanned
       const uint32_t bs_addr = smem_u32(bias_w + bslot * kCols);
-      mbar_wait(&tfull_bar[buf], (lt / NBUF) & 1);
+      if (p.flags & 16) mbar_wait(&tfull_bar[buf], (lt / NBUF) & 1);
+      else mbar_wait_relaxed(&tfull_bar[buf], (lt / NBUF) & 1, 32);
       tc_fence_after();
       const uint32_t t_addr = lane_taddr + buf * BN + cb;
       uint32_t r[2][kChunk];

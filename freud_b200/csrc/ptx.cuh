@@ -63,6 +63,41 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Wait of a warp that shares its SM sub-partition with busy warps (the TMA producer and the MMA issuer sit next to
+// the epilogue warps of lane quarters 0 and 1): a bare try_wait loop re-issues every ~20 cycles and was measured to
+// take ~10 % of all issued instructions each, i.e. about a third of the issue slots of "its" sub-partition -- and the
+// slowest quarter sets the tile period.  After a few immediate polls the warp sleeps between polls.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t sleep_ns) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > 4) {
+      asm volatile("nanosleep.u32 %0;" ::"r"(sleep_ns));
+      if (spins > (1u << 22)) __trap();
+    }
+  }
+}
+
+// Wait of a warp that is idle most of the time next to a busy one (the compactor beside its scanner): try_wait with
+// a suspend-time hint parks the warp in hardware until the phase completes (or the hint expires) instead of polling,
+// and a long sleep follows a miss.  Measured with 64 ns sleeps: the polling loop alone was 30 % of all instructions
+// the kernel issued, taken from the scanner's sub-partition.
+__device__ __forceinline__ void mbar_wait_suspended(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+        : "memory");
+    if (ok) return;
+    asm volatile("nanosleep.u32 %0;" ::"r"(400u));
+    if (++spins > (1u << 21)) __trap();
+  }
+}
+
 // ----------------------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -202,14 +237,33 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   return desc;
 }
 
-// Instruction descriptor, kind::f16 / kind::tf32, fp32 accumulator, both operands K-major.
+// Shared-memory matrix descriptor for an MN-major 16-bit operand tile: the M (or N) index is contiguous in memory.
+// What TMA boxes of {64 elements = 128 B, rows} with CU_TENSOR_MAP_SWIZZLE_128B produce when the GLOBAL matrix is
+// stored [K, M] row-major: each box is a run of K-rows of 128 bytes, i.e. canonical swizzle atoms of 64 (MN) x 8 (K)
+// elements, 1024 B each, stacked along K.  In 16-byte units the layout is ((8, n), (8, k)) : ((1, LBO), (8, SBO)):
+//   SBO = 1024 B between consecutive 8-row groups along K, LBO = distance between consecutive 64-wide atoms along MN
+//   (one whole box, `mn_atom_stride` bytes).  One MMA (K = 16) spans two K-atoms = 2048 B.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t mn_atom_stride) {
+  uint64_t desc = 0;
+  desc |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);           // bits [0,14)
+  desc |= static_cast<uint64_t>((mn_atom_stride >> 4) & 0x3FFF) << 16;  // leading byte offset [16,30)
+  desc |= static_cast<uint64_t>(1024 >> 4) << 32;                       // stride byte offset [32,46)
+  desc |= static_cast<uint64_t>(1) << 46;                               // descriptor version (Blackwell)
+  desc |= static_cast<uint64_t>(2) << 61;                               // layout type: SWIZZLE_128B
+  return desc;
+}
+
+// Instruction descriptor, kind::f16 / kind::tf32, fp32 accumulator; operands K-major unless a_mn / b_mn.
 //   fmt: 0 = f16, 1 = bf16, 2 = tf32
-__host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, uint32_t M, uint32_t N) {
-  return (1u << 4)            // c_format = F32
-         | (fmt << 7)         // a_format
-         | (fmt << 10)        // b_format
-         | ((N >> 3) << 17)   // n_dim
-         | ((M >> 4) << 24);  // m_dim
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, uint32_t M, uint32_t N, bool a_mn = false,
+                                                  bool b_mn = false) {
+  return (1u << 4)                   // c_format = F32
+         | (fmt << 7)                // a_format
+         | (fmt << 10)               // b_format
+         | ((a_mn ? 1u : 0u) << 15)  // a_major: 1 = MN-major
+         | ((b_mn ? 1u : 0u) << 16)  // b_major
+         | ((N >> 3) << 17)          // n_dim
+         | ((M >> 4) << 24);         // m_dim
 }
 
 }  // namespace freud

@@ -956,10 +956,15 @@ __global__ void __launch_bounds__(256) sparse_grads_kernel(
 }
 
 // db_dec[c] (+)= s*colsum[c] - sum_f db_enc[f] * W_enc[f,c]; grid over column chunks x feature slabs.
+__device__ __forceinline__ float ldw(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ldw(const __nv_bfloat16* p) {
+  return __uint_as_float(static_cast<uint32_t>(__ldg(reinterpret_cast<const unsigned short*>(p))) << 16);
+}
+template <typename WT>
 __global__ void __launch_bounds__(256) bdec_grad_kernel(const float* __restrict__ colsum,
                                                         const float* __restrict__ scales,
                                                         const float* __restrict__ db_enc,
-                                                        const float* __restrict__ W_enc, float* __restrict__ db_dec,
+                                                        const WT* __restrict__ W_enc, float* __restrict__ db_dec,
                                                         int n, int d, int slab) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= d) return;
@@ -971,9 +976,9 @@ __global__ void __launch_bounds__(256) bdec_grad_kernel(const float* __restrict_
     for (; f + 4 <= f1; f += 4) {
 #pragma unroll
       for (int u = 0; u < 4; ++u)
-        part[u] = fmaf(-__ldg(db_enc + f + u), __ldg(W_enc + static_cast<int64_t>(f + u) * d + c), part[u]);
+        part[u] = fmaf(-__ldg(db_enc + f + u), ldw(W_enc + static_cast<int64_t>(f + u) * d + c), part[u]);
     }
-    for (; f < f1; ++f) part[0] = fmaf(-__ldg(db_enc + f), __ldg(W_enc + static_cast<int64_t>(f) * d + c), part[0]);
+    for (; f < f1; ++f) part[0] = fmaf(-__ldg(db_enc + f), ldw(W_enc + static_cast<int64_t>(f) * d + c), part[0]);
     acc = (part[0] + part[1]) + (part[2] + part[3]);
   }
   if (blockIdx.y == 0 && colsum) acc = fmaf(scales[0], colsum[c], acc);
@@ -1442,15 +1447,20 @@ extern "C" int freud_topk_sparse_grads(const int32_t* offsets, const int32_t* me
   return 0;
 }
 
-extern "C" int freud_topk_bdec_grad(const float* colsum, const float* scales, const float* db_enc, const float* W_enc,
-                                    float* db_dec, int64_t n, int64_t d, int accumulate, void* stream) {
+extern "C" int freud_topk_bdec_grad(const float* colsum, const float* scales, const float* db_enc, const void* W_enc,
+                                    int w_is_bf16, float* db_dec, int64_t n, int64_t d, int accumulate, void* stream) {
   FREUD_REQUIRE(d > 0, "bdec_grad needs d > 0");
   FREUD_REQUIRE(db_enc == nullptr || W_enc != nullptr, "db_enc term needs W_enc");
   FREUD_REQUIRE(colsum == nullptr || scales != nullptr, "colsum term needs scales");
   if (!accumulate) FREUD_CHECK_CUDA(cudaMemsetAsync(db_dec, 0, d * sizeof(float), STREAM));
   const int slab = 64;  // n/64 x d/256 CTAs: enough of them in flight to stream W_enc at HBM rate
   dim3 grid((unsigned)((d + 255) / 256), (unsigned)(db_enc ? (n + slab - 1) / slab : 1));
-  bdec_grad_kernel<<<grid, 256, 0, STREAM>>>(colsum, scales, db_enc, W_enc, db_dec, (int)n, (int)d, slab);
+  if (w_is_bf16)
+    bdec_grad_kernel<<<grid, 256, 0, STREAM>>>(colsum, scales, db_enc, static_cast<const __nv_bfloat16*>(W_enc), db_dec,
+                                               (int)n, (int)d, slab);
+  else
+    bdec_grad_kernel<<<grid, 256, 0, STREAM>>>(colsum, scales, db_enc, static_cast<const float*>(W_enc), db_dec, (int)n,
+                                               (int)d, slab);
   FREUD_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

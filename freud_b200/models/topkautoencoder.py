@@ -118,6 +118,10 @@ class TopKAutoEncoder(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("freud_b200 TopKAutoEncoder runs on CUDA only (no CPU fallback); move the model and "
                                "the activations to a CUDA device")
+        opt = getattr(self, "_freud_sharded", None)
+        if opt is not None and opt() is not None and opt().stale:
+            raise RuntimeError("the fp32 weights of this model are sharded across ranks by the fused data-parallel "
+                               "optimiser; call trainer.consolidate() on every rank before using the module directly")
         if x.dtype != torch.float32:
             x = x.float()
         return x.contiguous()

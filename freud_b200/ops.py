@@ -263,8 +263,8 @@ def topk_sparse_grads(offsets, entries, top_vals, dacts, g, xc, b_dec, scales, d
 def topk_bdec_grad(colsum, scales, db_enc, W_enc, db_dec, accumulate: bool):
     d = db_dec.numel()
     n = db_enc.numel() if db_enc is not None else 0
-    call("freud_topk_bdec_grad", _ptr(colsum), _ptr(scales), _ptr(db_enc), _ptr(W_enc), _ptr(db_dec), n, d,
-         int(accumulate), _stream())
+    call("freud_topk_bdec_grad", _ptr(colsum), _ptr(scales), _ptr(db_enc), _ptr(W_enc),
+         int(W_enc is not None and W_enc.dtype == torch.bfloat16), _ptr(db_dec), n, d, int(accumulate), _stream())
 
 
 def topk_loss_scalars(sse, tv, numel: int):

@@ -9,9 +9,13 @@ import torch.distributed as dist
 
 
 class DataParallel:
-    def __init__(self, group=None):
+    def __init__(self, group=None, fused: bool = False):
+        """fused: exchange the gradients inside the optimiser step (freud_b200.fused_dp.FusedShardedAdam: reduce-scatter
+        over NVLink peer loads, Adam on a 1/G slice, updated weights stored to every rank) instead of one NCCL
+        all-reduce followed by the replicated update.  TopK trainer with Adam only; needs symmetric memory."""
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
+        self.fused = bool(fused)
         self.group = group
         self.world_size = dist.get_world_size(group)
         self.rank = dist.get_rank(group)

@@ -138,7 +138,7 @@ class FeatureShardedTopKTrainer:
             ops.topk_sparse_grads(offsets, entries, own_vals, dacts, e, xc, b_dec, scales, g["W_dec"],
                                   g["encoder.weight"], g["encoder.bias"], k, False)
             ops.topk_bdec_grad(colsum_e if self.rank == 0 else None, scales if self.rank == 0 else None,
-                               g["encoder.bias"], W_enc, g["b_dec"], False)
+                               g["encoder.bias"], we_hi if prec == BF16 else W_enc, g["b_dec"], False)
         else:
             e, sse, colsum_e = ops.residual(sae_out, x2, torch.float32)
             scal = ops.topk_loss_scalars(sse, tv, N * d)
@@ -153,7 +153,8 @@ class FeatureShardedTopKTrainer:
             auxk = (scale * sse_aux[0] / scal[4].double()).float() * self.auxk_alpha
             # ---- backward (rank-local) through the generic engine path: two decodes (main, aux) on this shard's rows;
             # replicated terms (the direct b_dec gradient) enter on rank 0 only, the sum over ranks completes them
-            st = topk_engine.TopKState(prec, x2, xc_hi, wd, W_enc, b_dec, k, self.n_local, scal, True, own_vals,
+            st = topk_engine.TopKState(prec, x2, xc_hi, wd, we_hi if prec == BF16 else W_enc, b_dec, k, self.n_local,
+                                       scal, True, own_vals,
                                        own_idx, e, colsum_e if self.rank == 0 else torch.zeros_like(colsum_e),
                                        auxk_alpha=self.auxk_alpha)
             st.aux = (a_own_vals, a_own_idx, r_aux, scale)

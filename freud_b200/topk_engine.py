@@ -25,7 +25,7 @@ class TopKState:
     x2: torch.Tensor            # [N,d] fp32 view of the input
     xc_hi: torch.Tensor         # encoder A operand (bf16, or tf32-hi)
     wd: torch.Tensor            # decoder weight as gathered (bf16 copy or the fp32 parameter)
-    W_enc: torch.Tensor
+    W_enc: torch.Tensor         # encoder weight as the db_dec term reads it (bf16 copy in bf16 mode, else fp32)
     b_dec: torch.Tensor
     k: int
     n: int
@@ -176,8 +176,10 @@ def topk_forward(x, W_enc, b_enc, W_dec, b_dec, k, *, precision, dead_mask=None,
         if not (defer_scal and not generic):
             cur.wait_event(scal_ready)
             scal_ready = None
-    st = TopKState(precision, x2, xc_hi, wd, W_enc, b_dec, k, n, scal, generic, vals, idx, e, colsum_e,
-                   auxk_alpha=auxk_alpha)
+    # the db_dec term back-propagates through the matmul operand: the bf16 copy in bf16 mode, as under the
+    # reference's autocast (and the only copy of W_enc that is current on every rank under the fused DP optimiser)
+    st = TopKState(precision, x2, xc_hi, wd, we_hi if precision == BF16 else W_enc, b_dec, k, n, scal, generic, vals,
+                   idx, e, colsum_e, auxk_alpha=auxk_alpha)
     st.scal_ready = scal_ready
     st.csc = csc
 

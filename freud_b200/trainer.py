@@ -58,9 +58,21 @@ class SAETrainer:
         self.precision = {"bf16": BF16, "fp32": FP32}[precision]
         model.precision = precision
         self.clip_thresh = clip_thresh
-        self.optimizer = build_optimizer(model, optimizer, lr, weight_decay, clip_thresh)
-        self.scheduler = build_scheduler(self.optimizer, scheduler, scheduler_params or {}, steps)
         self.dp = dp
+        self.fused_dp = bool(dp is not None and getattr(dp, "fused", False) and self.is_topk and optimizer == "adam")
+        if self.fused_dp:
+            from .fused_dp import FusedShardedAdam
+
+            named = {"encoder.weight": model.encoder.weight, "encoder.bias": model.encoder.bias,
+                     "W_dec": model.W_dec, "b_dec": model.b_dec}
+            self.optimizer = FusedShardedAdam(named, lr=lr, max_grad_norm=clip_thresh, group=dp.group,
+                                              weights=("encoder.weight", "W_dec") if precision == "bf16" else ())
+            import weakref
+
+            model._freud_sharded = weakref.ref(self.optimizer)  # module forward refuses stale fp32 weights
+        else:
+            self.optimizer = build_optimizer(model, optimizer, lr, weight_decay, clip_thresh)
+        self.scheduler = build_scheduler(self.optimizer, scheduler, scheduler_params or {}, steps)
         self.step_count = 0
         self.tokens_seen = 0
         self.dead_feature_threshold = dead_feature_threshold
@@ -70,6 +82,14 @@ class SAETrainer:
             self.num_frames_since_fired = torch.zeros(model.n_dict_components, device=dev, dtype=torch.long)
             self.params = {"encoder.weight": model.encoder.weight, "encoder.bias": model.encoder.bias,
                            "W_dec": model.W_dec, "b_dec": model.b_dec}
+            if self.fused_dp:  # parameters and gradients already are views of the optimiser's symmetric flat buffers
+                self._flat_grad = self.optimizer.flat_grad
+                self._shadows, self._shadow_versions = self.optimizer.shadows, None
+                self.last_state = None
+                self._dead_next = None
+                self._dead_pinned = torch.zeros(1, dtype=torch.int64).pin_memory()
+                int((self.num_frames_since_fired > (dead_feature_threshold or 0)).sum())
+                return
             # gradients are views of one flat fp32 buffer: data parallel reduces it in a single call, no copies
             # (every segment starts on a 128-byte boundary: the float4 paths of the clip / Adam / sparse-gradient
             # kernels need 16-byte-aligned tensors whatever n_dict_components is; the padding stays zero)
@@ -97,6 +117,8 @@ class SAETrainer:
         are invisible to both -- call `invalidate_weight_copies()` after editing weights that way."""
         if self.precision != BF16:
             return None
+        if self.fused_dp:
+            return self._shadows  # written by the fused optimiser step on every rank
         versions = tuple(self.params[k]._version for k in ("encoder.weight", "W_dec")) + \
             tuple(self.params[k].data_ptr() for k in ("encoder.weight", "W_dec")) + \
             (getattr(self.model, "_weights_epoch", 0),)
@@ -109,6 +131,12 @@ class SAETrainer:
 
     def invalidate_weight_copies(self):
         self._shadow_versions = None
+
+    def consolidate(self):
+        """Fused data-parallel mode keeps the fp32 master weights current only inside each rank's slice; this
+        all-gathers them (collective: call on every rank) before the model is evaluated, saved or edited."""
+        if self.fused_dp:
+            self.optimizer.consolidate()
 
     # ------------------------------------------------------------------------------------------ TopK
     def _topk_step(self, x):
@@ -164,10 +192,16 @@ class SAETrainer:
                     if self._dead_next is not None:
                         self._dead_next[0].record_stream(main)  # the mask is consumed on the main stream next step
                     fired_done = side.record_event()
-            self.dp.all_reduce_grads(glist, flat=self._flat_grad)
-        tl = ops.make_tensor_list([self.params[k].data for k in _TOPK_KEYS], glist)
-        sumsq = ops.grad_sumsq(tl, x.device)
-        self.optimizer.step(grad_sumsq=sumsq)  # clip_grad_norm_ + optimizer.step (train_sae.py:449-450), fused
+            if not self.fused_dp:
+                self.dp.all_reduce_grads(glist, flat=self._flat_grad)
+        if self.fused_dp:
+            # gradient exchange + clip_grad_norm_ + optimizer.step (train_sae.py:449-450) in two peer-memory kernels
+            self.optimizer.step()
+            sumsq = self.optimizer.grad_sumsq().view(1)
+        else:
+            tl = ops.make_tensor_list([self.params[k].data for k in _TOPK_KEYS], glist)
+            sumsq = ops.grad_sumsq(tl, x.device)
+            self.optimizer.step(grad_sumsq=sumsq)  # clip_grad_norm_ + optimizer.step, fused
         self.scheduler.step()
         # did_fire / num_frames_since_fired (train_sae.py:442-446), from the CSC index of the returned encoding
         offsets = st.offsets

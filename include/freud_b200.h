@@ -170,9 +170,10 @@ int freud_topk_sparse_grads(const int32_t* offsets, const int32_t* meta, const v
                             int accumulate, void* stream);
 
 /* db_dec[c] (+)= s * colsum[c] - sum_f db_enc_part[f] * W_enc[f,c]   (s = scales[0]; either term may be
- * skipped with a NULL pointer).  Autograd of `x - b_dec` (:74) and `+ b_dec` (:91). */
-int freud_topk_bdec_grad(const float* colsum, const float* scales, const float* db_enc, const float* W_enc,
-                         float* db_dec, int64_t n, int64_t d, int accumulate, void* stream);
+ * skipped with a NULL pointer).  Autograd of `x - b_dec` (:74) and `+ b_dec` (:91).  W_enc fp32, or its bf16 copy
+ * (bf16 mode: under autocast the reference back-propagates through the bf16 matmul operand). */
+int freud_topk_bdec_grad(const float* colsum, const float* scales, const float* db_enc, const void* W_enc,
+                         int w_is_bf16, float* db_dec, int64_t n, int64_t d, int accumulate, void* stream);
 
 /* Loss scalars (topkautoencoder.py:104-106,126-132,138,150), all on device:
  *   tv' = tv == 0 ? 1 : tv;  out[0] = fvu = sse/tv';  out[1] = mse = sse/numel;
@@ -245,6 +246,31 @@ int freud_adam_step(const freud_tensor_list* host_list, double lr, double beta1,
 /* RAdam with non-decoupled weight decay (torch/optim/radam.py:256-361). */
 int freud_radam_step(const freud_tensor_list* host_list, double lr, double beta1, double beta2, double eps,
                      double weight_decay, int64_t step, const double* sumsq, float max_norm, void* stream);
+
+/* ------------------------------------------------------------------ fused data-parallel optimiser step
+ * (N ranks == the single-GPU step of train_sae.py:448-450 on the concatenated batch.)
+ * The flat parameter space [W_enc | b_enc | W_dec | b_dec] (each padded to 32 elements) is cut into one contiguous
+ * slice [lo, hi) per rank.  peer_* are HOST arrays of `world` device pointers, one per rank, to the ranks' flat
+ * buffers in NVLink peer-mapped (symmetric) memory; mc_* the NVSwitch multicast address of the same buffer or NULL.
+ *
+ * freud_dp_reduce_scatter: this rank's gradient buffer [lo, hi) <- sum over ranks of peer_grads[r][lo, hi) (fixed
+ *   rank order, or multimem.ld_reduce when mc_grad != NULL); the slice's sum of squares is accumulated in *partial
+ *   (device double, zero on entry, re-zeroed on exit together with *done_ctr) and posted to slot `rank` of every
+ *   peer's slot buffer peer_slots[r] (>= world doubles).  A cross-rank barrier must separate it from the ranks'
+ *   backward kernels before and from freud_dp_adam_allgather after.
+ * freud_dp_adam_allgather: clip coefficient from the `world` posted partials (if clip), Adam (torch/optim/adam.py:347)
+ *   on [lo, hi) with exp_avg / exp_avg_sq holding ONLY the slice (index e - lo), fp32 master updated in
+ *   peer_params[rank]; the updated values of a region go to every rank: is_weight regions as bf16 into
+ *   peer_shadows[r] (what the tensor-core and gather kernels read), other regions as fp32 into peer_params[r].
+ *   A cross-rank barrier must follow before any rank reads them. */
+int freud_dp_reduce_scatter(void* const* peer_grads, const float* mc_grad, int64_t world, int64_t rank, int64_t lo,
+                            int64_t hi, double* partial, unsigned int* done_ctr, void* const* peer_slots,
+                            void* stream);
+int freud_dp_adam_allgather(void* const* peer_params, void* const* peer_shadows, float* mc_param, void* mc_shadow,
+                            const float* grad, float* exp_avg, float* exp_avg_sq, int64_t world, int64_t rank,
+                            int64_t lo, int64_t hi, const int64_t* region_begin, const int64_t* region_end,
+                            const int32_t* region_is_weight, int64_t n_regions, double lr, double beta1, double beta2,
+                            double eps, int64_t step, const double* slots, float max_norm, int clip, void* stream);
 
 /* ------------------------------------------------------------------ validation feature statistics
  * (src/scripts/train_sae.py:70-118,175-178)

@@ -135,3 +135,88 @@ def test_two_rank_l1_step_equals_single_rank_on_concatenated_batch():
     assert out, "rank 0 reported nothing"
     for k, v in out.items():
         assert v < 2e-5, (k, v)
+
+
+def _fused_worker(rank, world, port, precision, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from freud_b200.parallel import DataParallel
+        from freud_b200.trainer import SAETrainer
+
+        g = torch.Generator().manual_seed(7)
+        B, T, d = 8, 96, 64
+        xs = [torch.randn(B, T, d, generator=g) * (0.5 + torch.rand(T, 1, generator=g)) + 0.2 * torch.randn(d, generator=g)
+              for _ in range(3)]
+        kw = dict(lr=1e-3, steps=100, clip_thresh=1.0, optimizer="adam", scheduler="linear",
+                  scheduler_params={"num_warmup_steps": 2}, dead_feature_threshold=1e9, precision=precision)
+        model = _build(dev, precision)
+        init = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+        tr = SAETrainer(model, dp=DataParallel(fused=True), **kw)
+        assert tr.fused_dp
+        per = B // world
+        fvu0 = norm0 = None
+        for x in xs:
+            o = tr.step(x[rank * per:(rank + 1) * per].to(dev))
+            if fvu0 is None:
+                fvu0, norm0 = float(o["fvu"]), float(o["grad_sumsq"].sqrt())
+        # the module refuses to run on the sharded (stale) fp32 weights ...
+        if precision == "bf16":
+            try:
+                model(xs[0][:1].to(dev))
+                out[f"r{rank}.stale_guard"] = 1.0
+            except RuntimeError:
+                out[f"r{rank}.stale_guard"] = 0.0
+        tr.consolidate()  # ... until they are gathered
+        sd = tr.optimizer.state_dict()
+        torch.cuda.synchronize()
+        if rank == 0:
+            from oracle import optim as ooptim
+            from oracle import sae as osae
+
+            ro = osae.topk_forward(xs[0], init["encoder.weight"], init["encoder.bias"], init["W_dec"], init["b_dec"], 32,
+                                   mode=precision)
+            rgr = osae.topk_backward(xs[0], init["encoder.weight"], init["encoder.bias"], init["W_dec"], init["b_dec"],
+                                     ro, 32, mode=precision)
+            keys = ["encoder.weight", "encoder.bias", "W_dec", "b_dec"]
+            _, total = ooptim.clip_grad_norm([rgr[k] for k in keys], 1.0)
+            tol = 1e-5 if precision == "fp32" else 4e-3
+            out["oracle.fvu"] = abs(fvu0 - float(ro.fvu)) / float(ro.fvu) / tol
+            out["oracle.grad_norm"] = abs(norm0 - float(total)) / float(total) / tol
+            ref = SAETrainer(_build(dev, precision), dp=None, **kw)
+            for x in xs:
+                r = ref.step(x.to(dev))
+            torch.cuda.synchronize()
+            ptol = 2e-5 if precision == "fp32" else 2e-4
+            for k in tr.params:
+                out["param." + k] = float((tr.params[k].data - ref.params[k].data).abs().max() /
+                                          ref.params[k].data.abs().max()) / ptol
+            out["fvu"] = abs(float(o["fvu"]) - float(r["fvu"])) / float(r["fvu"]) / ptol
+            rsd = ref.optimizer.state_dict()
+            for i in range(4):
+                for key in ("exp_avg", "exp_avg_sq"):
+                    a, b = sd["state"][i][key].cpu(), rsd["state"][i][key].cpu()
+                    out[f"state.{i}.{key}"] = float((a - b).abs().max() / b.abs().max().clamp_min(1e-30)) / (10 * ptol)
+            if precision == "bf16":  # every rank's bf16 copies are the rounded masters
+                for k in ("encoder.weight", "W_dec"):
+                    out["shadow." + k] = float((tr.optimizer.shadows[k].float() -
+                                                tr.params[k].data.to(torch.bfloat16).float()).abs().max())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_two_rank_fused_optimizer_step_equals_single_rank(precision):
+    """Fused peer-memory gradient exchange + sharded Adam (csrc/collective.cu) == single-rank step on the concatenated
+    batch (parameters, optimiser state, loss) and == the oracle (loss, clipped-norm) at step 0; values are normalised by
+    their tolerance, so every entry must be < 1."""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_fused_worker, args=(2, _free_port(), precision, out), nprocs=2, join=True)
+    assert out and "fvu" in out, "rank 0 reported nothing"
+    for k, v in out.items():
+        assert v < 1.0, (k, v)
