@@ -37,12 +37,18 @@ SIGNATURES = {
     "freud_row_topk": [_p, _p, _p, _p, _i64, _i64, _i64, _p],
     "freud_gather_rows": [_p, _p, _p, _i64, _i64, _p],
     "freud_index_map": [_p, _p, _p, _i64, _p],
-    "freud_row_topk_mask": [_p, _p, _i64, _i64, _i64, _i64, _p],
+    "freud_row_topk_mask": [_p, _p, _i64, _i64, _i64, _i64, _i64, _i, _p],
+    "freud_col_sum_bf16": [_p, _p, _i64, _i64, _i64, _p],
     "freud_transpose_bf16": [_p, _p, _i64, _i64, _i64, _i64, _p],
     "freud_mask_grad": [_p, _p, _p, _p, _i64, _i64, _i64, _p],
     "freud_scatter_add_rows": [_p, _p, _p, _i64, _i64, _p],
     "freud_gemm_nt_splitk": [_p, _p, _p, _i64, _i64, _i64, _i64, _p],
     "freud_sum_splits": [_p, _p, _i64, _i64, _p],
+    "freud_gemm_nt_mask": [_p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _p],
+    "freud_l1_encode_fused": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _p],
+    "freud_l1_decode_fused": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p],
+    "freud_gemm_tn_splitk": [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _p],
+    "freud_gemm_nn": [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i, _p],
     "freud_topk_decode": [_p, _p, _p, _i, _p, _p, _p, _p, _i, _p, _p, _i64, _i64, _i64, _p],
     "freud_topk_dacts": [_p, _i, _p, _p, _i, _p, _i64, _i64, _i64, _p],
     "freud_topk_refine": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _p],
@@ -74,13 +80,14 @@ SIGNATURES = {
     "freud_col_absmax": [_p, _i64, _i64, _p, _p],
     "freud_search_dense": [_p, _i, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p],
     "freud_search_indexed": [_p, _p, _i, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p],
+    "freud_search_table_dense": [_p, _i, _p, _i64, _i64, _i64, _p, _p, _p, _p],
     "freud_search_topn": [_p, _p, _i64, _i, _i, _d, _i, _d, _i64, _p, _p, _p],
 }
 
 # CUDA kernels each entry point enqueues (memsets not counted); bench.py sums these into `gpu_launches`
 KERNELS_PER_CALL = {
     "freud_topk_prep_x": 1, "freud_split_operand": 1, "freud_topk_encode_workspace": 0, "freud_topk_encode": 2, "freud_gemm_nt": 1,
-    "freud_row_topk": 1, "freud_gather_rows": 1, "freud_index_map": 1, "freud_row_topk_mask": 1, "freud_transpose_bf16": 1, "freud_mask_grad": 1, "freud_scatter_add_rows": 1, "freud_gemm_nt_splitk": 1, "freud_sum_splits": 1,
+    "freud_row_topk": 1, "freud_gather_rows": 1, "freud_index_map": 1, "freud_row_topk_mask": 1, "freud_col_sum_bf16": 1, "freud_transpose_bf16": 1, "freud_mask_grad": 1, "freud_scatter_add_rows": 1, "freud_gemm_nt_splitk": 1, "freud_sum_splits": 1, "freud_gemm_nt_mask": 1, "freud_l1_encode_fused": 1, "freud_l1_decode_fused": 1, "freud_gemm_tn_splitk": 1, "freud_gemm_nn": 1,
     "freud_topk_decode": 1, "freud_topk_dacts": 1, "freud_topk_refine": 1, "freud_axpby": 1, "freud_shard_merge": 1, "freud_shard_localize": 1, "freud_residual": 1, "freud_csc_build": 5,
     "freud_csc_meta": 1, "freud_topk_sparse_grads": 3, "freud_topk_bdec_grad": 1, "freud_topk_loss_scalars": 1,
     "freud_dead_latent_update": 1, "freud_rownorm_project": 1, "freud_remove_parallel_grad": 1,
@@ -88,7 +95,7 @@ KERNELS_PER_CALL = {
     "freud_grad_sumsq": 1, "freud_clip_grads": 1, "freud_adam_step": 1, "freud_radam_step": 1,
     "freud_dp_reduce_scatter": 1, "freud_dp_adam_allgather": 1,
     "freud_feature_absmax": 1, "freud_col_absmax": 1,
-    "freud_search_dense": 1, "freud_search_indexed": 1, "freud_search_topn": 1,
+    "freud_search_dense": 1, "freud_search_indexed": 1, "freud_search_table_dense": 1, "freud_search_topn": 1,
 }
 
 _lib = None

@@ -78,23 +78,33 @@ static int64_t tail_split_bytes(int num_mb, int S) {
   return S > 1 ? S * rows * 32 * 8 + rows * 4 : 0;
 }
 
-template <int BN, int STAGES, int EPI, bool TF32, int SETS, int CL, int NBUF = 2, int CEV = 0>
+template <int BN, int STAGES, int EPI, bool TF32, int SETS, int CL, int NBUF = 2, int CEV = 0, bool AMN = false,
+          bool BMN = false>
 static int launch_gemm(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, GemmParams p,
                        int passes, cudaStream_t stream) {
   using L = GemmSmem<BN, STAGES, EPI, SETS, NBUF>;
   const int eb = TF32 ? 4 : 2;
   CUtensorMap mA0, mA1, mB0, mB1;
-  if (make_tensor_map_2d(&mA0, a_hi, p.M, p.K, p.K, eb, kBM)) return 3;
-  if (make_tensor_map_2d(&mB0, b_hi, p.N, p.K, p.K, eb, BN / CL)) return 3;
+  // K-major operand: stored [M or N, K], boxes of {128 B of K, rows}; MN-major: stored [K, M or N], boxes {64, 64}
+  auto map_a = [&](CUtensorMap* m, const void* base) {
+    if (AMN) return make_tensor_map_2d(m, base, p.K, p.M, p.lda ? p.lda : p.M, eb, 64);
+    return make_tensor_map_2d(m, base, p.M, p.K, p.lda ? p.lda : p.K, eb, kBM);
+  };
+  auto map_b = [&](CUtensorMap* m, const void* base) {
+    if (BMN) return make_tensor_map_2d(m, base, p.K, p.N, p.ldb ? p.ldb : p.N, eb, 64);
+    return make_tensor_map_2d(m, base, p.N, p.K, p.ldb ? p.ldb : p.K, eb, BN / CL);
+  };
+  if (map_a(&mA0, a_hi)) return 3;
+  if (map_b(&mB0, b_hi)) return 3;
   if (passes > 1) {
-    if (make_tensor_map_2d(&mA1, a_lo, p.M, p.K, p.K, eb, kBM)) return 3;
-    if (make_tensor_map_2d(&mB1, b_lo, p.N, p.K, p.K, eb, BN / CL)) return 3;
+    if (map_a(&mA1, a_lo)) return 3;
+    if (map_b(&mB1, b_lo)) return 3;
   } else {
     mA1 = mA0;
     mB1 = mB0;
   }
   p.passes = passes;
-  auto kern = sm100_gemm_kernel<BN, STAGES, EPI, TF32, SETS, CL, NBUF, CEV>;
+  auto kern = sm100_gemm_kernel<BN, STAGES, EPI, TF32, SETS, CL, NBUF, CEV, AMN, BMN>;
   if (const char* e = getenv("FREUD_ENC_FLAGS")) p.flags = atoi(e);
   static bool attr_set = false;
   if (!attr_set) {
@@ -103,7 +113,9 @@ static int launch_gemm(const void* a_hi, const void* a_lo, const void* b_hi, con
   }
   int grid = (p.M + kBM - 1) / kBM;
   grid = (grid + CL - 1) / CL * CL;  // whole clusters; surplus CTAs run the protocol on out-of-range rows
-  if (EPI == EPI_STORE && CL == 1 && p.kb_per_split == 0 && grid > sm_count() && !getenv("FREUD_NO_PERSISTENT")) {
+  if ((EPI == EPI_STORE || EPI == EPI_MASK || EPI == EPI_RELU16 || EPI == EPI_RESID) && CL == 1 &&
+      p.kb_per_split == 0 && grid > sm_count() &&
+      !getenv("FREUD_NO_PERSISTENT")) {
     p.persistent = 1;  // one CTA per SM, each a contiguous run of row blocks
     grid = sm_count();
   }
@@ -317,4 +329,120 @@ extern "C" int freud_gemm_nt_splitk(const void* a_hi, const void* b_hi, float* w
                 "splits must equal ceil(k_blocks / ceil(k_blocks / splits)) so that no partial is left unwritten");
   p.split_stride = M * N;
   return launch_gemm<256, 4, EPI_STORE, false, 2, 1>(a_hi, nullptr, b_hi, nullptr, p, 1, static_cast<cudaStream_t>(stream));
+}
+
+// Products whose operands are stored "the other way round" (MN-major operands, see sm100_gemm_kernel):
+//   freud_gemm_tn_splitk : out[M, N] = A^T B with A stored [K, lda >= M] and B stored [K, ldb >= N], both bf16 and
+//                          row-major -- the weight-gradient shape (K = tokens); `splits` fp32 partials go to
+//                          workspace [splits, M, N] for freud_sum_splits.  No operand is transposed in memory.
+//   freud_gemm_nn        : out[M, ldo] = act(A B + bias) with A stored [M, K] and B stored [K, ldb >= N], bf16.
+extern "C" int freud_gemm_tn_splitk(const void* a, const void* b, float* workspace, int64_t M, int64_t N, int64_t K,
+                                    int64_t lda, int64_t ldb, int64_t splits, void* stream) {
+  FREUD_REQUIRE(M > 0 && N > 0 && K > 0 && splits >= 1, "empty split-K GEMM");
+  FREUD_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "sizes exceed int32");
+  FREUD_REQUIRE(lda >= M && ldb >= N && lda % 8 == 0 && ldb % 8 == 0, "row pitches must be multiples of 8 elements");
+  GemmParams p{};
+  p.M = static_cast<int>(M);
+  p.N = static_cast<int>(N);
+  p.K = static_cast<int>(K);
+  p.lda = lda;
+  p.ldb = ldb;
+  p.out = workspace;
+  p.ldo = N;
+  const int total_kb = static_cast<int>((K + 63) / 64);
+  p.kb_per_split = static_cast<int>((total_kb + splits - 1) / splits);
+  FREUD_REQUIRE((total_kb + p.kb_per_split - 1) / p.kb_per_split == splits,
+                "splits must equal ceil(k_blocks / ceil(k_blocks / splits)) so that no partial is left unwritten");
+  p.split_stride = M * N;
+  return launch_gemm<256, 4, EPI_STORE, false, 2, 1, 2, 0, true, true>(a, nullptr, b, nullptr, p, 1,
+                                                                       static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int freud_gemm_nn(const void* a, const void* b, const float* bias, float* out, int64_t M, int64_t N,
+                             int64_t K, int64_t lda, int64_t ldb, int64_t ldo, int relu, void* stream) {
+  FREUD_REQUIRE(M > 0 && N > 0 && K > 0, "empty GEMM");
+  FREUD_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "sizes exceed int32");
+  FREUD_REQUIRE(lda >= K && ldb >= N && lda % 8 == 0 && ldb % 8 == 0 && ldo >= N, "bad row pitches");
+  GemmParams p{};
+  p.M = static_cast<int>(M);
+  p.N = static_cast<int>(N);
+  p.K = static_cast<int>(K);
+  p.lda = lda;
+  p.ldb = ldb;
+  p.bias = bias;
+  p.relu = relu;
+  p.out = out;
+  p.ldo = ldo;
+  return launch_gemm<256, 4, EPI_STORE, false, 2, 1, 2, 0, false, true>(a, nullptr, b, nullptr, p, 1,
+                                                                        static_cast<cudaStream_t>(stream));
+}
+
+// dpre[M, ld16] (bf16) = (act > 0) ? A B^T : 0 -- activation gradient of the dense AuxK branch with the ReLU / top-k
+// mask applied in the GEMM epilogue (autograd of relu + topk on the dead subset, topkautoencoder.py:118-123).
+extern "C" int freud_gemm_nt_mask(const void* a, const void* b, const void* act_bf16, void* out_bf16,
+                                  const float* affine, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ld16,
+                                  void* stream) {
+  FREUD_REQUIRE(M > 0 && N > 0 && K > 0 && K % 8 == 0, "gemm_nt_mask: bad sizes");
+  FREUD_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "sizes exceed int32");
+  FREUD_REQUIRE(ld16 >= N && ld16 % 8 == 0, "ld16 must be a multiple of 8 and >= N");
+  GemmParams p{};
+  p.M = static_cast<int>(M);
+  p.N = static_cast<int>(N);
+  p.K = static_cast<int>(K);
+  p.mask_src = static_cast<const __nv_bfloat16*>(act_bf16);
+  p.out16 = static_cast<__nv_bfloat16*>(out_bf16);
+  p.ld16 = ld16;
+  p.affine = affine;
+  p.lda = lda;
+  return launch_gemm<256, 4, EPI_MASK, false, 2, 1>(a, nullptr, b, nullptr, p, 1, static_cast<cudaStream_t>(stream));
+}
+
+// L1 SAE forward on bf16 operands (l1autoencoder.py:69-95):
+//   freud_l1_encode_fused: c = relu(x W + b) -> bf16 [M, ld16] (the decode GEMM's operand), sums[0] += sum(c); optional
+//                          fp32 copy `latent` [M, N].   a = x bf16 [M, K = d], b = W^T bf16 [N = n, K = d].
+//   freud_l1_decode_fused: x_hat = c W^T; against target x: sums[0] += masked sse, sums[1] += count(x != -1),
+//                          sums[2] += sse; e * [x != -1] -> bf16 [M, ld16] (unscaled gradient seed); optional fp32 copy
+//                          `x_hat` [M, N].   a = c bf16 [M, lda] (K = n valid columns), b = W bf16 [N = d, K = n].
+extern "C" int freud_l1_encode_fused(const void* x_bf16, const void* wt_bf16, const float* bias, void* c_bf16,
+                                     float* latent, double* sums, int64_t M, int64_t N, int64_t K, int64_t ld16,
+                                     void* stream) {
+  FREUD_REQUIRE(M > 0 && N > 0 && K > 0 && K % 8 == 0, "l1_encode_fused: bad sizes");
+  FREUD_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "sizes exceed int32");
+  FREUD_REQUIRE(ld16 >= N && ld16 % 8 == 0, "ld16 must be a multiple of 8 and >= N");
+  GemmParams p{};
+  p.M = static_cast<int>(M);
+  p.N = static_cast<int>(N);
+  p.K = static_cast<int>(K);
+  p.bias = bias;
+  p.out16 = static_cast<__nv_bfloat16*>(c_bf16);
+  p.ld16 = ld16;
+  p.out = latent;
+  p.ldo = N;
+  p.sums = sums;
+  return launch_gemm<256, 4, EPI_RELU16, false, 2, 1>(x_bf16, nullptr, wt_bf16, nullptr, p, 1,
+                                                      static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int freud_l1_decode_fused(const void* c_bf16, const void* w_bf16, const float* target, void* resid_bf16,
+                                     float* x_hat, double* sums, int64_t M, int64_t N, int64_t K, int64_t lda,
+                                     int64_t ldb, int64_t ld16, void* stream) {
+  FREUD_REQUIRE(M > 0 && N > 0 && K > 0, "l1_decode_fused: bad sizes");
+  FREUD_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "sizes exceed int32");
+  FREUD_REQUIRE(lda >= K && lda % 8 == 0 && ldb >= K && ldb % 8 == 0, "operand pitches must be multiples of 8");
+  FREUD_REQUIRE(ld16 >= N && ld16 % 8 == 0, "ld16 must be a multiple of 8 and >= N");
+  GemmParams p{};
+  p.M = static_cast<int>(M);
+  p.N = static_cast<int>(N);
+  p.K = static_cast<int>(K);
+  p.lda = lda;
+  p.ldb = ldb;
+  p.target = target;
+  p.ldt = N;
+  p.out16 = static_cast<__nv_bfloat16*>(resid_bf16);
+  p.ld16 = ld16;
+  p.out = x_hat;
+  p.ldo = N;
+  p.sums = sums;
+  return launch_gemm<256, 4, EPI_RESID, false, 2, 1>(c_bf16, nullptr, w_bf16, nullptr, p, 1,
+                                                     static_cast<cudaStream_t>(stream));
 }

@@ -11,6 +11,13 @@
 //              (reference: TopKAutoEncoder.pre_acts + select_topk, topkautoencoder.py:72-85)
 //   EPI_STORE: (ReLU and) store fp32 [M, N]  (reference: pre_acts / L1 encode + decode GEMMs)
 //   EPI_NONE : discard the tile (mainloop-ceiling probe used by scripts/enc_variants.py)
+//   EPI_MASK : store bf16 (act[row, col] > 0 ? scale * acc + shift : 0) -- the ReLU / top-k mask of a dense backward
+//              applied to the activation gradient without materialising the fp32 product (dense AuxK; L1 SAE dz)
+//   EPI_RELU16: c = relu(acc + bias) stored as bf16 (the next GEMM's operand) with sum(c) accumulated -- the L1 SAE's
+//              encode + L1 penalty (l1autoencoder.py:74-75,85); optional fp32 copy
+//   EPI_RESID: e = acc - target; masked / unmasked squared error and count accumulated, e * [target != -1] stored as
+//              bf16 -- the L1 SAE's decode + masked MSE (l1autoencoder.py:78,86,29-36) and its gradient seed; optional
+//              fp32 copy of acc
 //
 // Roles: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warp 3 spare, then SETS x 4
 // epilogue warps (TMEM lane quarter == warp_idx % 4).  With SETS == 2 both sets drain EVERY tile, set s taking
@@ -51,7 +58,7 @@ constexpr int kSlotStride = 32 * 8;  // bytes between slots of one lane: [slot][
                                      // sits in banks {2*lane, 2*lane+1} whatever its slot (256 B == 0 mod 128 B), so the
                                      // predicated appends of lanes at DIFFERENT fill levels never collide
 
-enum { EPI_TOPK = 0, EPI_STORE = 1, EPI_NONE = 2 };
+enum { EPI_TOPK = 0, EPI_STORE = 1, EPI_NONE = 2, EPI_MASK = 3, EPI_RELU16 = 4, EPI_RESID = 5 };
 
 struct GemmParams {
   int M, N, K;          // K in elements
@@ -86,9 +93,24 @@ struct GemmParams {
   // back, so the TMA / MMA of the next row block overlaps the store epilogue of the previous one (a one-tile-wide
   // product such as the L1 SAE's n = 200 otherwise pays the pipeline fill and drain once per 128 rows).
   int persistent;
+  // EPI_MASK
+  const __nv_bfloat16* mask_src;  // [M, ld16] activations whose positivity gates the output
+  __nv_bfloat16* out16;           // [M, ld16]
+  int64_t ld16;                   // multiple of 8
+  const float* affine;            // EPI_MASK: device (scale, shift) or nullptr for (1, 0)
+  const float* target;            // EPI_RESID: fp32 [M, ldt]
+  int64_t ldt;
+  double* sums;                   // EPI_RELU16: [sum c]; EPI_RESID: [masked sse, count, sse]
+  int64_t lda, ldb;  // host side only: row pitch (elements) of the A / B matrix as stored; 0 = dense
   int flags;  // experiments (FREUD_ENC_FLAGS): bit 0 = do not share 16th-largest values between the epilogue sets;
               // bits 1-4 = bare spin (no sleep between polls) in the producer / MMA-empty / MMA-full / epilogue waits
 };
+
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 
 template <int BN, int STAGES, int EPI, int SETS, int NBUF = 2>
 struct GemmSmem {
@@ -426,6 +448,14 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       for (int j = 0; j < kPerLane; j += 4) dst[j / 4] = make_float4(nb[j], nb[j + 1], nb[j + 2], nb[j + 3]);
     };
 
+    double acc_sum[3] = {0.0, 0.0, 0.0};  // EPI_RELU16 / EPI_RESID running sums of this thread's rows
+    float aff_scale = 1.f, aff_shift = 0.f;
+    if constexpr (EPI == EPI_MASK) {
+      if (p.affine != nullptr) {
+        aff_scale = __ldg(p.affine);
+        aff_shift = __ldg(p.affine + 1);
+      }
+    }
     uint64_t surv[kTopK];
     float thresh = 0.f;  // candidates must be > thresh
     float t16 = 0.f;     // this set's 16th largest value so far (0 while it holds fewer than 16)
@@ -543,6 +573,107 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             }
           } else if constexpr (EPI == EPI_NONE) {
             if (v[0] == 1.2345e38f) p.out[0] = 1.f;  // keep the loads alive
+          } else if constexpr (EPI == EPI_RELU16) {
+            if (row < p.M) {
+              const int64_t col0 = static_cast<int64_t>(nt) * BN + cb + cc;
+#pragma unroll
+              for (int j = 0; j < kChunk; ++j) {
+                v[j] = fmaxf(v[j], 0.f);  // columns past N carry a -inf bias: they come out as 0
+                acc_sum[0] += v[j];
+              }
+#pragma unroll
+              for (int h8 = 0; h8 < kChunk; h8 += 8) {
+                if (col0 + h8 < p.ld16) {
+                  uint4 q;
+                  uint32_t* qw = reinterpret_cast<uint32_t*>(&q);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const __nv_bfloat162 h = __floats2bfloat162_rn(v[h8 + 2 * j], v[h8 + 2 * j + 1]);
+                    qw[j] = *reinterpret_cast<const uint32_t*>(&h);
+                  }
+                  *reinterpret_cast<uint4*>(p.out16 + static_cast<int64_t>(row) * p.ld16 + col0 + h8) = q;
+                }
+              }
+              if (p.out != nullptr) {
+#pragma unroll
+                for (int j = 0; j < kChunk; ++j)
+                  if (col0 + j < p.N) p.out[static_cast<int64_t>(row) * p.ldo + col0 + j] = v[j];
+              }
+            }
+          } else if constexpr (EPI == EPI_RESID) {
+            if (row < p.M) {
+              const int64_t col0 = static_cast<int64_t>(nt) * BN + cb + cc;
+              float e[kChunk], xt[kChunk];
+              const float* trow = p.target + static_cast<int64_t>(row) * p.ldt + col0;
+              if (col0 + kChunk <= p.N && (p.ldt & 3) == 0) {  // 16-byte loads: 4 per chunk instead of 16 scalar ones
+#pragma unroll
+                for (int j = 0; j < kChunk; j += 4) {
+                  const float4 t4 = __ldg(reinterpret_cast<const float4*>(trow + j));
+                  xt[j] = t4.x; xt[j + 1] = t4.y; xt[j + 2] = t4.z; xt[j + 3] = t4.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < kChunk; ++j) xt[j] = col0 + j < p.N ? __ldg(trow + j) : 0.f;
+              }
+#pragma unroll
+              for (int j = 0; j < kChunk; ++j) {
+                float ev = 0.f;
+                if (col0 + j < p.N) {
+                  const float xv = xt[j];
+                  const float d0 = v[j] - xv;
+                  const float d2 = d0 * d0;
+                  acc_sum[2] += d2;
+                  if (xv != -1.0f) {  // mse_loss(..., ignored_index=-1): exact comparison, as the reference (:31)
+                    acc_sum[0] += d2;
+                    acc_sum[1] += 1.0;
+                    ev = d0;
+                  }
+                }
+                e[j] = ev;
+              }
+#pragma unroll
+              for (int h8 = 0; h8 < kChunk; h8 += 8) {
+                if (col0 + h8 < p.ld16) {
+                  uint4 q;
+                  uint32_t* qw = reinterpret_cast<uint32_t*>(&q);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const __nv_bfloat162 h = __floats2bfloat162_rn(e[h8 + 2 * j], e[h8 + 2 * j + 1]);
+                    qw[j] = *reinterpret_cast<const uint32_t*>(&h);
+                  }
+                  *reinterpret_cast<uint4*>(p.out16 + static_cast<int64_t>(row) * p.ld16 + col0 + h8) = q;
+                }
+              }
+              if (p.out != nullptr) {
+#pragma unroll
+                for (int j = 0; j < kChunk; ++j)
+                  if (col0 + j < p.N) p.out[static_cast<int64_t>(row) * p.ldo + col0 + j] = v[j];
+              }
+            }
+          } else if constexpr (EPI == EPI_MASK) {
+            if (row < p.M) {
+              const int64_t col0 = static_cast<int64_t>(nt) * BN + cb + cc;
+#pragma unroll
+              for (int h8 = 0; h8 < kChunk; h8 += 8) {
+                if (col0 + h8 < p.ld16) {  // ld16 % 8 == 0: a group of 8 is either inside the pitch or outside
+                  const int64_t o = static_cast<int64_t>(row) * p.ld16 + col0 + h8;
+                  const uint4 a8 = __ldg(reinterpret_cast<const uint4*>(p.mask_src + o));
+                  const uint32_t aw[4] = {a8.x, a8.y, a8.z, a8.w};
+                  uint4 q;
+                  uint32_t* qw = reinterpret_cast<uint32_t*>(&q);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    // bf16 > 0  <=>  sign clear and not zero
+                    const bool p0 = (aw[j] & 0x8000u) == 0 && (aw[j] & 0x7fffu) != 0;
+                    const bool p1 = (aw[j] & 0x80000000u) == 0 && (aw[j] & 0x7fff0000u) != 0;
+                    const __nv_bfloat162 h = __floats2bfloat162_rn(p0 ? fmaf(aff_scale, v[h8 + 2 * j], aff_shift) : 0.f,
+                                                                   p1 ? fmaf(aff_scale, v[h8 + 2 * j + 1], aff_shift) : 0.f);
+                    qw[j] = *reinterpret_cast<const uint32_t*>(&h);
+                  }
+                  *reinterpret_cast<uint4*>(p.out16 + o) = q;
+                }
+              }
+            }
           } else {
             if (row < p.M) {
               float* orow = p.out + split * p.split_stride + static_cast<int64_t>(row) * p.ldo + nt * BN + cb + cc;
@@ -654,6 +785,14 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       }
     }
       lt0 = seg_end;
+    }
+    if constexpr (EPI == EPI_RELU16 || EPI == EPI_RESID) {
+      constexpr int kSums = EPI == EPI_RELU16 ? 1 : 3;
+#pragma unroll
+      for (int i = 0; i < kSums; ++i) {
+        const double t = warp_sum_f64(acc_sum[i]);
+        if (lane == 0 && t != 0.0) atomicAdd(p.sums + i, t);
+      }
     }
   }
 

@@ -7,20 +7,32 @@
 
 namespace freud {
 
-// One thread per dictionary column j (coalesced across j for every row i).
-__global__ void __launch_bounds__(128) l1_colnorm_kernel(float* __restrict__ W, float* __restrict__ Wt, int d, int n) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
+// One CTA of 8 warps per group of 32 dictionary columns: thread (w, lane) walks rows w, w+8, ... of column j0 + lane
+// (coalesced across the lanes), the 8 row-partials of a column meet in shared memory.  (One thread per column walked
+// all d rows twice by itself: 0.09 ms of pure latency for the 384 x 200 matrix of C1, every encode() call.)
+__global__ void __launch_bounds__(256) l1_colnorm_kernel(float* __restrict__ W, float* __restrict__ Wt, int d, int n) {
+  __shared__ float part[8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + lane;
   float s = 0.f;
-  for (int i = 0; i < d; ++i) {
-    const float w = W[static_cast<int64_t>(i) * n + j];
-    s = fmaf(w, w, s);
+  if (j < n) {
+    for (int i = w; i < d; i += 8) {
+      const float v = W[static_cast<int64_t>(i) * n + j];
+      s = fmaf(v, v, s);
+    }
   }
-  const float inv = 1.f / fmaxf(sqrtf(s), 1e-12f);  // F.normalize eps
-  for (int i = 0; i < d; ++i) {
-    const float w = W[static_cast<int64_t>(i) * n + j] * inv;
-    W[static_cast<int64_t>(i) * n + j] = w;
-    Wt[static_cast<int64_t>(j) * d + i] = w;
+  part[w][lane] = s;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) tot += part[k][lane];
+  const float inv = 1.f / fmaxf(sqrtf(tot), 1e-12f);  // F.normalize eps
+  if (j < n) {
+    for (int i = w; i < d; i += 8) {
+      const float v = W[static_cast<int64_t>(i) * n + j] * inv;
+      W[static_cast<int64_t>(i) * n + j] = v;
+      Wt[static_cast<int64_t>(j) * d + i] = v;
+    }
   }
 }
 
@@ -241,7 +253,7 @@ using namespace freud;
 
 extern "C" int freud_l1_colnorm(float* W, float* Wt, int64_t d, int64_t n, void* stream) {
   FREUD_REQUIRE(d > 0 && n > 0, "colnorm needs d, n > 0");
-  l1_colnorm_kernel<<<(int)((n + 127) / 128), 128, 0, STREAM>>>(W, Wt, (int)d, (int)n);
+  l1_colnorm_kernel<<<(int)((n + 31) / 32), 256, 0, STREAM>>>(W, Wt, (int)d, (int)n);
   FREUD_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 
 namespace freud {
 

@@ -219,6 +219,159 @@ __global__ void __launch_bounds__(kSelThreads) row_topk_mask_kernel(const float*
   }
 }
 
+// Warp-per-row version for NON-NEGATIVE rows (post-ReLU pre-activations) that fit in registers (n <= 64 * PAIRS):
+// lane l holds the column pairs {2l + 64i, 2l + 64i + 1}, read once with coalesced 8-byte loads.  Only the strictly
+// positive values compete (a zero is written as zero whether selected or not, and with fewer than k positives all of
+// them are kept), so their raw bit patterns order like the values.  The k-th largest is bracketed by bisection on the
+// bit patterns, starting from the row's own [min, max] and counting with register compares + one warp reduction per
+// step (no shared-memory atomics: the histogram versions serialised on the few exponent bins a row occupies), until
+// at most 32 values remain in the bracket; those are gathered one per lane and ranked with shuffles.  The masked
+// row goes out as coalesced bf16x2 stores.  Ties at the k-th value are resolved towards the lower column index, as
+// in row_topk_mask_kernel.
+template <int PAIRS>
+__global__ void __launch_bounds__(256) row_topk_mask_warp_kernel(const float* __restrict__ latents,
+                                                                 __nv_bfloat16* __restrict__ out, int64_t rows, int n,
+                                                                 int k, int ld_in, int ld_out) {
+  __shared__ uint32_t gather_s[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t* gat = gather_s[w];
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + w; row < rows; row += static_cast<int64_t>(gridDim.x) * 8) {
+    const float* __restrict__ x = latents + row * ld_in;
+    uint32_t u[PAIRS][2];  // raw bits of the strictly positive values, 0 for everything else
+    int npos = 0;
+    uint32_t umax = 0u, umin = 0xffffffffu;
+    // all loads of the row first (the pitch is even, so a pair that starts inside it lies inside it): written with
+    // per-element branches the compiler issued load -> use -> load ..., 40 serial memory round trips per row
+    float2 raw[PAIRS];
+#pragma unroll
+    for (int i = 0; i < PAIRS; ++i) {
+      const int c = 2 * lane + 64 * i;
+      raw[i] = c < ld_in ? __ldcs(reinterpret_cast<const float2*>(x + c)) : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < PAIRS; ++i) {
+      const int c = 2 * lane + 64 * i;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float tv = (c + e < n) ? (e == 0 ? raw[i].x : raw[i].y) : 0.f;
+        const uint32_t b = tv > 0.f ? __float_as_uint(tv) : 0u;
+        u[i][e] = b;
+        npos += b != 0u;
+        umax = max(umax, b);
+        umin = min(umin, b != 0u ? b : 0xffffffffu);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      npos += __shfl_xor_sync(0xffffffffu, npos, o);
+      umax = max(umax, __shfl_xor_sync(0xffffffffu, umax, o));
+      umin = min(umin, __shfl_xor_sync(0xffffffffu, umin, o));
+    }
+    uint32_t kth = 1u;  // smallest positive pattern: with fewer than k positives every positive value is kept
+    int need_eq = 0x7fffffff;
+    if (npos >= k) {  // warp-uniform
+      // invariants: count(u >= lo) = c_lo >= k,  count(u >= hi) = c_hi < k
+      uint32_t lo = umin, hi = umax + 1u;
+      int c_lo = npos, c_hi = 0;
+      while (hi - lo > 1u && c_lo - c_hi > 32) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        int c = 0;
+#pragma unroll
+        for (int i = 0; i < PAIRS; ++i) c += (u[i][0] >= mid) + (u[i][1] >= mid);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (c >= k) {
+          lo = mid;
+          c_lo = c;
+        } else {
+          hi = mid;
+          c_hi = c;
+        }
+      }
+      if (hi - lo == 1u) {
+        kth = lo;
+        need_eq = k - c_hi;  // count(u > lo) == count(u >= hi)
+      } else {
+        // gather the c_lo - c_hi <= 32 values of [lo, hi), one per lane (any order), and rank them
+        int mine = 0;
+#pragma unroll
+        for (int i = 0; i < PAIRS; ++i) mine += (u[i][0] >= lo && u[i][0] < hi) + (u[i][1] >= lo && u[i][1] < hi);
+        int base = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v2 = __shfl_up_sync(0xffffffffu, base, o);
+          if (lane >= o) base += v2;
+        }
+        base -= mine;  // exclusive prefix
+#pragma unroll
+        for (int i = 0; i < PAIRS; ++i) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+            if (u[i][e] >= lo && u[i][e] < hi) gat[base++] = u[i][e];
+        }
+        __syncwarp();
+        const int m = c_lo - c_hi;
+        const uint32_t el = lane < m ? gat[lane] : 0u;
+        int gt = 0, ge = 0;
+        for (int j = 0; j < m; ++j) {
+          const uint32_t o2 = __shfl_sync(0xffffffffu, el, j);
+          gt += o2 > el;
+          ge += o2 >= el;
+        }
+        const int r = k - c_hi;  // the r-th largest of the gathered values is the k-th largest of the row
+        const uint32_t hit = __ballot_sync(0xffffffffu, lane < m && gt < r && r <= ge);
+        const int src = __ffs(hit) - 1;  // every hit lane holds the same value
+        kth = __shfl_sync(0xffffffffu, el, src);
+        need_eq = r - __shfl_sync(0xffffffffu, gt, src);
+        __syncwarp();
+      }
+    }
+    int eq_before = 0;
+    __nv_bfloat16* __restrict__ o = out + row * ld_out;
+#pragma unroll
+    for (int i = 0; i < PAIRS; ++i) {
+      const int c = 2 * lane + 64 * i;
+      const bool g0 = u[i][0] > kth, g1 = u[i][1] > kth;
+      const bool e0 = u[i][0] == kth, e1 = u[i][1] == kth;
+      const uint32_t b0 = __ballot_sync(0xffffffffu, e0), b1 = __ballot_sync(0xffffffffu, e1);
+      const int before = eq_before + __popc(b0 & lt_mask) + __popc(b1 & lt_mask);
+      const bool t0 = g0 || (e0 && before < need_eq);
+      const bool t1 = g1 || (e1 && before + (e0 ? 1 : 0) < need_eq);
+      eq_before += __popc(b0) + __popc(b1);
+      if (c < ld_out) {
+        const __nv_bfloat162 q =
+            __floats2bfloat162_rn(t0 ? __uint_as_float(u[i][0]) : 0.f, t1 ? __uint_as_float(u[i][1]) : 0.f);
+        if (c + 1 < ld_out)
+          *reinterpret_cast<__nv_bfloat162*>(o + c) = q;
+        else
+          o[c] = __low2bfloat16(q);
+      }
+    }
+    // columns of the output pitch beyond what this lane's pairs cover
+    for (int c = 64 * PAIRS + 2 * lane; c < ld_out; c += 64) {
+      o[c] = __float2bfloat16_rn(0.f);
+      if (c + 1 < ld_out) o[c + 1] = __float2bfloat16_rn(0.f);
+    }
+  }
+}
+
+// colsum[j] = sum_r x[r, j] for a bf16 matrix [rows, ld] (first n columns), fp32 accumulation; caller zeroes colsum.
+__global__ void __launch_bounds__(256) col_sum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ colsum,
+                                                           int64_t rows, int n, int ld, int slab) {
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (j >= n) return;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * slab, r1 = min(rows, r0 + slab);
+  float a0 = 0.f, a1 = 0.f;
+  for (int64_t r = r0; r < r1; ++r) {
+    const __nv_bfloat162 q = *reinterpret_cast<const __nv_bfloat162*>(x + r * ld + j);
+    a0 += __low2float(q);
+    a1 += __high2float(q);
+  }
+  atomicAdd(colsum + j, a0);
+  if (j + 1 < n) atomicAdd(colsum + j + 1, a1);
+}
+
 // out[c, r] = in[r, c] for a bf16 matrix in [rows, ld_in] -> [cols, ld_out]; columns [rows, ld_out) of out zeroed.
 __global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in,
                                                              __nv_bfloat16* __restrict__ out, int64_t rows, int64_t cols,
@@ -284,11 +437,42 @@ extern "C" int freud_row_topk(const float* latents, const uint8_t* col_mask, flo
   return 0;
 }
 
-extern "C" int freud_row_topk_mask(const float* latents, void* out_bf16, int64_t rows, int64_t n, int64_t k, int64_t ld,
-                                   void* stream) {
-  FREUD_REQUIRE(rows > 0 && n > 0 && k > 0 && k <= n && ld >= n, "row_topk_mask needs 0 < k <= n <= ld");
-  row_topk_mask_kernel<<<(unsigned)rows, kSelThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      latents, static_cast<__nv_bfloat16*>(out_bf16), (int)n, (int)k, (int)ld);
+extern "C" int freud_row_topk_mask(const float* latents, void* out_bf16, int64_t rows, int64_t n, int64_t k,
+                                   int64_t ld_in, int64_t ld, int nonneg, void* stream) {
+  FREUD_REQUIRE(rows > 0 && n > 0 && k > 0 && k <= n && ld >= n && ld_in >= n, "row_topk_mask needs 0 < k <= n <= ld");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(out_bf16);
+  const bool warp_ok = nonneg && n <= 64 * 64 && ld_in % 2 == 0 && ld % 2 == 0 &&
+                       (reinterpret_cast<uintptr_t>(latents) & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0;
+  if (warp_ok) {
+    int64_t grid = (rows + 7) / 8;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 6;
+    if (grid > cap) grid = cap;
+#define LW(P) \
+  row_topk_mask_warp_kernel<P><<<(unsigned)grid, 256, 0, st>>>(latents, out, rows, (int)n, (int)k, (int)ld_in, (int)ld)
+    if (n <= 64 * 8) LW(8);
+    else if (n <= 64 * 16) LW(16);
+    else if (n <= 64 * 24) LW(24);
+    else if (n <= 64 * 32) LW(32);
+    else if (n <= 64 * 40) LW(40);
+    else if (n <= 64 * 48) LW(48);
+    else LW(64);
+#undef LW
+  } else {
+    FREUD_REQUIRE(ld_in == n, "the CTA-per-row kernel reads dense rows");
+    row_topk_mask_kernel<<<(unsigned)rows, kSelThreads, 0, st>>>(latents, out, (int)n, (int)k, (int)ld);
+  }
+  FREUD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int freud_col_sum_bf16(const void* x_bf16, float* colsum, int64_t rows, int64_t n, int64_t ld, void* stream) {
+  FREUD_REQUIRE(rows > 0 && n > 0 && ld >= n && ld % 2 == 0, "col_sum_bf16: bad sizes");
+  FREUD_CHECK_CUDA(cudaMemsetAsync(colsum, 0, n * sizeof(float), static_cast<cudaStream_t>(stream)));
+  const int slab = 512;
+  dim3 grid((unsigned)((n / 2 + 1 + 255) / 256), (unsigned)((rows + slab - 1) / slab));
+  col_sum_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x_bf16), colsum,
+                                                                          rows, (int)n, (int)ld, slab);
   FREUD_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

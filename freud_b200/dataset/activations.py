@@ -147,23 +147,27 @@ class DeviceActivationStore:
             for s in range(0, n, chunk_files):
                 blk = torch.from_numpy(np.ascontiguousarray(mm[self.lo + s:self.lo + min(n, s + chunk_files)]))
                 blk = blk.view(-1, T, F)
-                out[s:s + blk.shape[0]].copy_(blk.pin_memory(), non_blocking=True)
+                if dtype_out is not None and blk.dtype != dtype_out:
+                    out[s:s + blk.shape[0]].copy_(blk.pin_memory().to(dev, non_blocking=True))  # converts on the device
+                else:
+                    out[s:s + blk.shape[0]].copy_(blk.pin_memory(), non_blocking=True)
             torch.cuda.synchronize(dev)
             return out
 
+        self.acts_fm = None
+        self._table = None
         if self.activation_type == "indexed":
             self.vals = upload(dataset.act_mmap).float()
-            self.idx = upload(dataset.idx_mmap)
+            # the .npy holds int64 indices (torch.topk); a dictionary never has 2^31 features, so they are narrowed
+            # chunk by chunk on the way in: the per-query index scan reads half the bytes
+            self.idx = upload(dataset.idx_mmap, torch.int32)
         else:
             acts = upload(dataset.mmap)
             self.acts = acts if acts.dtype in (torch.float32, torch.float16) else acts.float()
-            # Feature-major copy [F, N_files, T]: a single-feature query then streams N_files*T contiguous values
-            # (60 MB at C5) instead of one 32-byte sector per frame of the row-major store.
-            # Built once at load time (a layout change, like the upload); kept when both copies fit comfortably.
-            if feature_major is None:
-                free, _ = torch.cuda.mem_get_info(dev)
-                feature_major = self.acts.numel() * self.acts.element_size() * 1.2 < free
-            self.acts_fm = self.acts.permute(2, 0, 1).contiguous() if feature_major else None
+            # (feature_major=True keeps a second, [F, N_files, T] copy so that a single-feature scan is contiguous; the
+            #  all-feature table below makes scans unnecessary, so it is no longer built by default)
+            if feature_major:
+                self.acts_fm = self.acts.permute(2, 0, 1).contiguous()
         if frames_fn is None:
             if num_samples is not None:
                 frames_fn = lambda f: n_frames_from_samples(num_samples[f])  # noqa: E731
@@ -173,6 +177,16 @@ class DeviceActivationStore:
                     return n_frames_from_samples(ns, sr)
         self.n_frames_host = [min(int(frames_fn(f)), T) for f in self.filenames]
         self.n_frames = torch.tensor(self.n_frames_host[self.lo:self.hi], dtype=torch.int32, device=dev)
+
+
+    def feature_table(self):
+        """(vmax, amax, vabs) [n_files_local, F] of EVERY feature of a dense store, built by one pass over it on first
+        use (freud_search_table_dense); every later query is a column gather + the ranking kernel."""
+        if self._table is None:
+            from .. import ops
+
+            self._table = ops.search_table_dense(self.acts, self.n_frames)
+        return self._table
 
 
 class DeviceResidentActivationLoader:

@@ -47,22 +47,51 @@ def _gemm_operands(t: Tensor, precision: int):
     return ops.split_operand(t, precision)
 
 
+def _pad_cols_bf16(t: Tensor, mult: int = 8) -> Tensor:
+    """bf16 copy of a small fp32 matrix with the row pitch rounded up to `mult` elements (TMA rows are 16-byte multiples)."""
+    r, c = t.shape
+    ld = (c + mult - 1) // mult * mult
+    if ld == c:
+        return ops.split_operand(t, BF16)[0]
+    out = torch.zeros((r, ld), dtype=torch.bfloat16, device=t.device)
+    out[:, :c] = t.to(torch.bfloat16)
+    return out
+
+
 class _L1ForwardFn(torch.autograd.Function):
-    """(x, W, b) -> (x_hat, latent, l1_loss, reconstruction_loss, mse); losses carry gradient to W and b."""
+    """(x, W, b) -> (x_hat, latent, l1_loss, reconstruction_loss, mse); losses carry gradient to W and b.
+
+    bf16 mode runs the step in five tensor-core launches and no elementwise passes over [N, n] / [N, d] matrices:
+      encode GEMM  -> epilogue relu + bf16 latent (next GEMM's operand) + sum|c|
+      decode GEMM  -> epilogue residual against x, masked / unmasked SSE, count, bf16 masked residual
+      dz GEMM      -> epilogue (c > 0) ? s_recon * (dxhat W) + s_l1 : 0 as bf16
+      two products over the token axis (x^T dz, dxhat^T c) reading their operands through MN-major descriptors.
+    fp32 outputs (x_hat, latent) are only materialised when `want_outputs` (the module API returns them; the trainer
+    does not need them).  fp32 mode keeps the 3-pass split-TF32 GEMMs and separate reduction kernels."""
 
     @staticmethod
-    def forward(ctx, x2, W, b, recon_alpha, precision, dp=None):
+    def forward(ctx, x2, W, b, recon_alpha, precision, dp=None, want_outputs=True):
         N, d = x2.shape
         n = W.shape[1]
         Wt = ops.l1_colnorm(W.data)  # in place on decoder.weight.data + K-major transposed copy
-        x_ops = _gemm_operands(x2, precision)
-        wt_ops = _gemm_operands(Wt, precision)
-        w_ops = _gemm_operands(W.data, precision)
-        latent = ops.gemm_nt(x_ops[0], x_ops[1], wt_ops[0], wt_ops[1], b, True, precision)       # relu(x @ W + b)
-        c_ops = _gemm_operands(latent, precision)
-        x_hat = ops.gemm_nt(c_ops[0], c_ops[1], w_ops[0], w_ops[1], None, False, precision)      # c @ W.T
         need_grad = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
-        acc, dxhat = ops.l1_loss_reduce(latent, x_hat, x2, need_grad)
+        if precision == BF16:
+            x16 = ops.split_operand(x2, BF16)[0]
+            wt16 = ops.split_operand(Wt, BF16)[0]                                   # [n, d]
+            w16 = _pad_cols_bf16(W.data)                                            # [d, ceil8(n)]
+            c16, l1sum, latent = ops.l1_encode_fused(x16, wt16, b, want_outputs)    # relu(x @ W + b)
+            dxh16, sums, x_hat = ops.l1_decode_fused(c16, w16, n, x2, want_outputs)  # c @ W.T vs x
+            acc = torch.cat((l1sum, sums))
+            saved = (x16, c16, dxh16, wt16)
+        else:
+            x_ops = _gemm_operands(x2, precision)
+            wt_ops = _gemm_operands(Wt, precision)
+            w_ops = _gemm_operands(W.data, precision)
+            latent = ops.gemm_nt(x_ops[0], x_ops[1], wt_ops[0], wt_ops[1], b, True, precision)   # relu(x @ W + b)
+            c_ops = _gemm_operands(latent, precision)
+            x_hat = ops.gemm_nt(c_ops[0], c_ops[1], w_ops[0], w_ops[1], None, False, precision)  # c @ W.T
+            acc, dxhat = ops.l1_loss_reduce(latent, x_hat, x2, need_grad)
+            saved = (x2, latent, dxhat, wt_ops)
         n_glob = N
         if dp is not None:  # losses (and with them the gradient scales) of the batch concatenated over ranks
             acc = dp.all_reduce_sum(acc)
@@ -70,38 +99,43 @@ class _L1ForwardFn(torch.autograd.Function):
         l1 = (acc[0] / n_glob).float()
         recon = (recon_alpha * acc[1] / acc[2]).float()
         mse = (acc[3] / (n_glob * d)).float()
-        ctx.saved = (x2, latent, dxhat, acc, wt_ops, Wt, precision, recon_alpha, n_glob)
-        ctx.mark_non_differentiable(x_hat, latent, mse)
+        ctx.saved = saved + (acc, precision, recon_alpha, n_glob, n, d)
+        outs = [t for t in (x_hat, latent, mse) if t is not None]
+        ctx.mark_non_differentiable(*outs)
         return x_hat, latent, l1, recon, mse
 
     @staticmethod
     def backward(ctx, g_xhat, g_latent, g_l1, g_recon, g_mse):
-        x2, latent, dxhat, acc, wt_ops, Wt, precision, recon_alpha, n_glob = ctx.saved
-        N, d = x2.shape
-        dev = x2.device
+        a0, a1, a2, a3, acc, precision, recon_alpha, n_glob, n, d = ctx.saved
+        dev = a0.device
         zero = torch.zeros((), dtype=torch.float32, device=dev)
         g_l1 = zero if g_l1 is None else g_l1.float()
         g_recon = zero if g_recon is None else g_recon.float()
         s_recon = (g_recon.double() * (2.0 * recon_alpha) / acc[2]).float()   # d recon / d x_hat = 2*alpha*(x_hat-x)/N_unmasked
         s_l1 = g_l1 / n_glob                                                  # d l1 / d c = 1[c>0]/N
-        # dc (unscaled) = dxhat_raw @ W  as  A = dxhat [N, K=d], B = W^T [n, K=d]
-        dx_ops = _gemm_operands(dxhat, precision)
-        dc = ops.gemm_nt(dx_ops[0], dx_ops[1], wt_ops[0], wt_ops[1], None, False, precision)
         if precision == BF16:
-            # tensor-core path: dz formed while packing the K-major operands, dW = [x^T | s dxhat^T] @ [dz | c]
-            dW, db = ops.l1_weight_grad_tc(x2, dxhat, dc, latent,
-                                           torch.stack((s_recon, s_l1, torch.ones_like(s_recon), s_recon)))
+            x16, c16, dxh16, wt16 = a0, a1, a2, a3
+            dz16 = ops.gemm_nt_mask(dxh16, wt16, c16, torch.stack((s_recon, s_l1)))  # (c>0) ? s_recon*(dxhat W) + s_l1 : 0
+            db = ops.col_sum_bf16(dz16, n)
+            Ga = ops.gemm_tn_splitk(x16, dz16, M=d, N=n)                             # x^T dz
+            Gb = ops.gemm_tn_splitk(dxh16, c16, M=d, N=n)                            # dxhat^T c   (dxhat unscaled)
+            dW = torch.addcmul(Ga, Gb, s_recon)
         else:
+            x2, latent, dxhat, wt_ops = a0, a1, a2, a3
+            # dc (unscaled) = dxhat_raw @ W  as  A = dxhat [N, K=d], B = W^T [n, K=d]
+            dx_ops = _gemm_operands(dxhat, precision)
+            dc = ops.gemm_nt(dx_ops[0], dx_ops[1], wt_ops[0], wt_ops[1], None, False, precision)
             db = ops.l1_dz(dc, latent, torch.stack((s_recon, s_l1)))          # dc becomes dz in place
             dW = ops.l1_weight_grad(x2, dc, dxhat, latent, torch.stack((torch.ones_like(s_recon), s_recon)))
         ctx.saved = None
-        return None, dW, db, None, None, None
+        return None, dW, db, None, None, None, None
 
 
 class L1AutoEncoder(nn.Module):
     # class-level defaults: modules unpickled from reference-written files bypass __init__
     precision = "auto"
     dp = None  # freud_b200.parallel.DataParallel: losses over the concatenated batch (set by SAETrainer)
+    materialize_outputs = True  # False (set by SAETrainer): bf16 mode skips the fp32 sae_out / latent copies
 
     def __init__(self, activation_size: int, cfg: L1AutoEncoderConfig):
         """Same construction order as the reference (:40-67): decoder Linear, zero bias, orthogonal init."""
@@ -149,11 +183,11 @@ class L1AutoEncoder(nn.Module):
         d = x.shape[-1]
         x_hat, latent, l1, recon, mse = _L1ForwardFn.apply(x.view(-1, d), self.decoder.weight, self.encoder_bias,
                                                            float(self.recon_alpha), _precision(self.precision),
-                                                           self.dp)
+                                                           self.dp, bool(self.materialize_outputs))
         lead = x.shape[:-1]
-        c = latent.view(*lead, self.n_dict_components)
+        c = latent.view(*lead, self.n_dict_components) if latent is not None else None
         forward_output = L1ForwardOutput(
-            sae_out=x_hat.view(*lead, d),
+            sae_out=x_hat.view(*lead, d) if x_hat is not None else None,
             encoded=L1EncoderOutput(c),
             l1_loss=l1,
             reconstruction_loss=recon,

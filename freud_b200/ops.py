@@ -130,11 +130,22 @@ def index_map(table: torch.Tensor, idx: torch.Tensor):
     return out
 
 
-def row_topk_mask(latents: torch.Tensor, k: int, ld: int):
-    """Dense bf16 [rows, ld] with each row's exact top-k kept and everything else zero."""
-    rows, n = latents.shape
+def row_topk_mask(latents: torch.Tensor, k: int, ld: int, n: int = None, nonneg: bool = False):
+    """Dense bf16 [rows, ld] with each row's exact top-k (among the first n columns) kept and everything else zero.
+    `latents` may carry a padded row pitch (latents.shape[1] >= n).  nonneg: the caller guarantees latents >= 0
+    (post-ReLU pre-activations), which allows the streaming warp-per-row kernel."""
+    rows, ld_in = latents.shape
+    n = ld_in if n is None else n
     out = torch.empty((rows, ld), dtype=torch.bfloat16, device=latents.device)
-    call("freud_row_topk_mask", _ptr(_f32(latents, "latents")), _ptr(out), rows, n, k, ld, _stream())
+    call("freud_row_topk_mask", _ptr(_f32(latents, "latents")), _ptr(out), rows, n, k, ld_in, ld, int(nonneg),
+         _stream())
+    return out
+
+
+def col_sum_bf16(x: torch.Tensor, n: int):
+    rows, ld = x.shape
+    out = torch.empty(n, dtype=torch.float32, device=x.device)
+    call("freud_col_sum_bf16", _ptr(x), _ptr(out), rows, n, ld, _stream())
     return out
 
 
@@ -174,6 +185,81 @@ def gemm_nt_splitk(a: torch.Tensor, b: torch.Tensor, splits: int):
     call("freud_gemm_nt_splitk", _ptr(a), _ptr(b), _ptr(ws), M, Nn, K, splits, _stream())
     call("freud_sum_splits", _ptr(ws), _ptr(out), splits, M * Nn, _stream())
     return out
+
+
+def gemm_nt_mask(a: torch.Tensor, b: torch.Tensor, act: torch.Tensor, affine: torch.Tensor = None):
+    """bf16 [M, ld] = (act > 0) ? scale * (a[:, :K] @ b^T) + shift : 0 with a [M, lda], b [N, K] bf16, act bf16
+    [M, ld >= N]; (scale, shift) = `affine` (2 device floats) or (1, 0)."""
+    M, lda = a.shape
+    N, K = b.shape
+    out = torch.empty_like(act)
+    call("freud_gemm_nt_mask", _ptr(a), _ptr(b), _ptr(act), _ptr(out), _ptr(affine), M, N, K, lda, act.shape[1],
+         _stream())
+    return out
+
+
+def l1_encode_fused(x16: torch.Tensor, wt16: torch.Tensor, bias: torch.Tensor, want_latent: bool):
+    """c = relu(x W + b) as bf16 [M, ceil8(n)] + sum(c) (double[1]) [+ fp32 latent]."""
+    M, K = x16.shape
+    n = wt16.shape[0]
+    ld = (n + 7) // 8 * 8
+    c16 = torch.empty((M, ld), dtype=torch.bfloat16, device=x16.device)
+    latent = torch.empty((M, n), dtype=torch.float32, device=x16.device) if want_latent else None
+    sums = torch.zeros(1, dtype=torch.float64, device=x16.device)
+    call("freud_l1_encode_fused", _ptr(x16), _ptr(wt16), _ptr(bias), _ptr(c16), _ptr(latent), _ptr(sums), M, n, K, ld,
+         _stream())
+    return c16, sums, latent
+
+
+def l1_decode_fused(c16: torch.Tensor, w16: torch.Tensor, n: int, target: torch.Tensor, want_xhat: bool):
+    """x_hat = c W^T against `target`: (dxhat16 bf16 [M, ceil8(d)] unscaled masked residual, sums double[3] =
+    (masked sse, count, sse) [, fp32 x_hat]).  c16 [M, lda] with n valid columns, w16 [d, ldb >= n]."""
+    M, lda = c16.shape
+    d, ldb = w16.shape
+    ld = (d + 7) // 8 * 8
+    r16 = torch.empty((M, ld), dtype=torch.bfloat16, device=c16.device)
+    x_hat = torch.empty((M, d), dtype=torch.float32, device=c16.device) if want_xhat else None
+    sums = torch.zeros(3, dtype=torch.float64, device=c16.device)
+    call("freud_l1_decode_fused", _ptr(c16), _ptr(w16), _ptr(_f32(target, "target")), _ptr(r16), _ptr(x_hat),
+         _ptr(sums), M, d, n, lda, ldb, ld, _stream())
+    return r16, sums, x_hat
+
+
+def _splits_for(M: int, K: int, splits=None):
+    total_kb = (K + 63) // 64
+    if splits is None:
+        splits = max(1, min(total_kb, -(-148 // max(1, (M + 127) // 128))))  # about one CTA per SM
+    per = (total_kb + splits - 1) // splits
+    return (total_kb + per - 1) // per  # the split count the kernel will actually run (no empty partials)
+
+
+def gemm_tn_splitk(a: torch.Tensor, b: torch.Tensor, M: int = None, N: int = None, splits: int = None):
+    """a^T @ b for bf16 a [K, lda], b [K, ldb] stored row-major (K = tokens), first M / N columns used: fp32 [M, N].
+    The operands are read through MN-major tensor-core descriptors -- nothing is transposed in memory."""
+    K, lda = a.shape
+    ldb = b.shape[1]
+    M = lda if M is None else M
+    N = ldb if N is None else N
+    splits = _splits_for(M, K, splits)
+    ws = torch.empty((splits, M, N), dtype=torch.float32, device=a.device)
+    call("freud_gemm_tn_splitk", _ptr(a), _ptr(b), _ptr(ws), M, N, K, lda, ldb, splits, _stream())
+    if splits == 1:
+        return ws[0]
+    out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    call("freud_sum_splits", _ptr(ws), _ptr(out), splits, M * N, _stream())
+    return out
+
+
+def gemm_nn(a: torch.Tensor, b: torch.Tensor, bias=None, relu: bool = False, K: int = None, N: int = None):
+    """act(a[:, :K] @ b[:K, :N] + bias) for bf16 a [M, lda] and b [K', ldb] stored row-major: fp32 [M, N]."""
+    M, lda = a.shape
+    ldb = b.shape[1]
+    K = lda if K is None else K
+    N = ldb if N is None else N
+    ldo = (N + 3) // 4 * 4
+    out = torch.empty((M, ldo), dtype=torch.float32, device=a.device)
+    call("freud_gemm_nn", _ptr(a), _ptr(b), _ptr(bias), _ptr(out), M, N, K, lda, ldb, ldo, int(relu), _stream())
+    return out[:, :N] if ldo != N else out
 
 
 def topk_decode(top_vals, top_idx, W_dec, b_dec, target=None, *, resid_dtype=None, want_sse=False,
@@ -406,6 +492,20 @@ def search_dense(acts, n_frames, feature: int, want_trace: bool):
     call("freud_search_dense", _ptr(acts), int(acts.dtype == torch.float16), _ptr(n_frames), n_files, T, F, feature,
          _ptr(vmax), _ptr(amax), _ptr(vabs), _ptr(trace), _stream())
     return vmax, amax, vabs, trace
+
+
+def search_table_dense(acts, n_frames):
+    """(vmax, amax, vabs) tables [n_files, F] for every feature column in one pass over the store."""
+    n_files, T, F = acts.shape
+    dev = acts.device
+    vmax = torch.empty((n_files, F), dtype=torch.float32, device=dev)
+    amax = torch.empty((n_files, F), dtype=torch.int32, device=dev)
+    vabs = torch.empty((n_files, F), dtype=torch.float32, device=dev)
+    if acts.dtype not in (torch.float32, torch.float16):
+        raise TypeError("dense activations must be float32 or float16")
+    call("freud_search_table_dense", _ptr(acts), int(acts.dtype == torch.float16), _ptr(n_frames), n_files, T, F,
+         _ptr(vmax), _ptr(amax), _ptr(vabs), _stream())
+    return vmax, amax, vabs
 
 
 def search_indexed(vals, idx, n_frames, feature: int, want_trace: bool):

@@ -193,17 +193,19 @@ def topk_forward(x, W_enc, b_enc, W_dec, b_dec, k, *, precision, dead_mask=None,
         elif precision == BF16:
             # Dense AuxK on the compacted dead-latent subset (S columns): k_aux = d/2 selections per token make
             # the row-sparse kernels ~12x the main path's work, but as dense [N,S] x [S,d] products it is cheap.
-            dead_idx = torch.nonzero(dead_mask).squeeze(1).to(torch.int32)
-            S = dead_idx.numel()
+            # No operand is transposed in memory: products over the token axis read their operands through
+            # MN-major tensor-core descriptors (gemm_nn / gemm_tn_splitk).
+            dead_idx = torch.nonzero_static(dead_mask, size=num_dead).squeeze(1).to(torch.int32)  # no host sync
+            S = num_dead
             Sp = (S + 7) // 8 * 8
             ws = ops.gather_rows(we_hi, dead_idx)
             bs = ops.gather_rows(b_enc, dead_idx)
-            pre_dead = ops.gemm_nt(xc_hi, None, ws, None, bs, True, precision)          # [N,S] fp32
-            A = ops.row_topk_mask(pre_dead, k_aux, Sp)                                   # [N,Sp] bf16, top-k_aux kept
+            pre_dead = torch.empty((N, Sp), dtype=torch.float32, device=x.device)          # row pitch Sp, S valid columns
+            ops.gemm_nt(xc_hi, None, ws, None, bs, True, precision, out=pre_dead)
+            A = ops.row_topk_mask(pre_dead, k_aux, Sp, n=S, nonneg=True)                              # [N,Sp] bf16, top-k_aux kept
             del pre_dead
             wd_sub = ops.gather_rows(wd, dead_idx)                                       # [S,d] bf16
-            wd_sub_T = ops.transpose_bf16(wd_sub, d, Sp)                                 # [d,Sp]
-            e_hat = ops.gemm_nt(A, None, wd_sub_T, None, b_dec, False, precision)        # A @ W_dec[dead] + b_dec
+            e_hat = ops.gemm_nn(A, wd_sub, b_dec, False, K=S)                            # A @ W_dec[dead] + b_dec
             r_aux, sse_aux, _ = ops.residual(e_hat, e, torch.float32, want_colsum=False)
             st.aux_dense = (dead_idx, S, Sp, A, wd_sub, r_aux, scale)
             a_vals = a_idx = None
@@ -348,21 +350,12 @@ def topk_backward(st: TopKState, g_fvu, g_aux=None, g_multi=None, *, out=None, o
                                   idx.shape[1], not first)
             first = False
         if dense_aux is not None:
-            # dense backward of the AuxK branch on the dead subset: four tensor-core products, then a row scatter
+            # dense backward of the AuxK branch on the dead subset: three tensor-core products, then a row scatter
             dead_idx, S, Sp, A, wd_sub, G_hat = dense_aux
-            N = st.x2.shape[0]
-            Np = (N + 7) // 8 * 8
-            gA = ops.gemm_nt(G_hat, None, wd_sub, None, None, False, BF16)               # [N,S] = G_hat @ W_dec[dead]^T
-            dpre, db_sub = ops.mask_grad(gA, A)                                          # relu/top-k mask, bf16 [N,Sp]
-            del gA
-            splits = max(1, min(16, (148 * 2) // max(1, (S + 127) // 128)))
-            A_T = ops.transpose_bf16(A, S, Np)                                           # [S,Np]
-            G_T = ops.transpose_bf16(G_hat, d, Np)                                       # [d,Np]
-            dWdec_sub = ops.gemm_nt_splitk(A_T, G_T, splits)                             # A^T @ G_hat       [S,d]
-            del A_T, G_T
-            P_T = ops.transpose_bf16(dpre, S, Np)
-            X_T = ops.transpose_bf16(st.xc_hi, d, Np)
-            dWenc_sub = ops.gemm_nt_splitk(P_T, X_T, splits)                             # dpre^T @ (x - b_dec)
+            dpre = ops.gemm_nt_mask(G_hat, wd_sub, A)               # (A > 0) ? G_hat @ W_dec[dead]^T : 0   bf16 [N,Sp]
+            db_sub = ops.col_sum_bf16(dpre, S)
+            dWdec_sub = ops.gemm_tn_splitk(A, G_hat, M=S, N=d)      # A^T @ G_hat            [S,d]
+            dWenc_sub = ops.gemm_tn_splitk(dpre, st.xc_hi, M=S, N=d)  # dpre^T @ (x - b_dec)   [S,d]
             ops.scatter_add_rows(dWdec_sub, dead_idx, dW_dec)
             ops.scatter_add_rows(dWenc_sub, dead_idx, dW_enc)
             ops.scatter_add_rows(db_sub, dead_idx, db_enc)

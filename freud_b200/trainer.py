@@ -50,7 +50,11 @@ def build_scheduler(opt, scheduler: str, scheduler_params: dict, steps: int):
 
 class SAETrainer:
     def __init__(self, model, *, lr, steps, clip_thresh=1.0, weight_decay=0.0, optimizer="adam", scheduler="linear",
-                 scheduler_params=None, dead_feature_threshold=None, precision="bf16", dp=None):
+                 scheduler_params=None, dead_feature_threshold=None, precision="bf16", dp=None,
+                 materialize_outputs=True):
+        """materialize_outputs (L1 SAE, bf16 mode): False skips the fp32 sae_out / latent copies the train loop does
+        not need (step() then returns None for them)."""
+        self.materialize_outputs = materialize_outputs
         if not next(model.parameters()).is_cuda:
             raise RuntimeError("SAETrainer needs the model on a CUDA device (no CPU fallback)")
         self.model = model
@@ -63,8 +67,9 @@ class SAETrainer:
         if self.fused_dp:
             from .fused_dp import FusedShardedAdam
 
-            named = {"encoder.weight": model.encoder.weight, "encoder.bias": model.encoder.bias,
-                     "W_dec": model.W_dec, "b_dec": model.b_dec}
+            # model.parameters() order, so that optimizer.state_dict() indexes the parameters exactly like the
+            # reference's Adam(model.parameters()) does (checkpoint layout, train_sae.py:232-248)
+            named = dict(model.named_parameters())
             self.optimizer = FusedShardedAdam(named, lr=lr, max_grad_norm=clip_thresh, group=dp.group,
                                               weights=("encoder.weight", "W_dec") if precision == "bf16" else ())
             import weakref
@@ -247,6 +252,7 @@ class SAETrainer:
     def _l1_step(self, x):
         self.optimizer.zero_grad(set_to_none=True)
         self.model.dp = self.dp
+        self.model.materialize_outputs = self.materialize_outputs
         out = self.model(x)
         loss = out.reconstruction_loss + out.l1_loss  # train_sae.py:433-434
         loss.backward()
@@ -255,7 +261,7 @@ class SAETrainer:
         self.optimizer.step()
         self.scheduler.step()
         return {"loss": loss.detach(), "loss_recon": out.reconstruction_loss.detach(), "loss_l1": out.l1_loss.detach(),
-                "sae_out": out.sae_out, "latent": out.encoded.latent}
+                "sae_out": out.sae_out, "latent": out.encoded.latent}  # None when materialize_outputs is False
 
     def step(self, activations: torch.Tensor):
         """One optimisation step on a [B, T, d] fp32 CUDA batch.  Returns device tensors (no host sync)."""

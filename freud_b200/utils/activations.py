@@ -50,7 +50,15 @@ def top_activations(dataloader, feature_idx: int, n_files: int, max_val: Optiona
                     absolute_magnitude: bool, return_max_per_file: bool):
     store = get_store(dataloader)
     if store.activation_type == "tensor":
-        if getattr(store, "acts_fm", None) is not None:
+        F = store.acts.shape[-1]
+        if not 0 <= int(feature_idx) < F:
+            raise IndexError(f"feature_idx {feature_idx} out of range for {F} features")
+        if F % 4 == 0:
+            # all-feature table (one pass over the store, first query only): this query is a column of it
+            tv, ta, tb = store.feature_table()
+            f = int(feature_idx)
+            vmax, amax, vabs = tv[:, f].contiguous(), ta[:, f].contiguous(), tb[:, f].contiguous()
+        elif getattr(store, "acts_fm", None) is not None:
             # contiguous [N_files, T] slab of this feature: the same kernel with a unit column stride
             vmax, amax, vabs, _ = ops.search_dense(store.acts_fm[int(feature_idx)].unsqueeze(-1), store.n_frames, 0, False)
         else:

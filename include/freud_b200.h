@@ -81,12 +81,17 @@ int freud_index_map(const int32_t* table, const int32_t* in, int32_t* out, int64
 
 /* Dense AuxK branch on the compacted dead-latent subset (bf16 mode).  k_aux = d/2 selected latents per token make
  * the row-sparse kernels 12x the main path's work, while a dense GEMM over the S dead latents is cheap:
- *   freud_row_topk_mask   : out[r,j] = latents[r,j] if j is in row r's top-k else 0 (bf16, row pitch ld >= n)
+ *   freud_row_topk_mask   : out[r,j] = latents[r,j] if j is in row r's top-k else 0 (bf16, row pitch ld >= n;
+ *                           latents fp32 with row pitch ld_in >= n; nonneg != 0 promises
+ *                           latents >= 0 (post-ReLU), which selects the streaming warp-per-row kernel)
  *   freud_transpose_bf16  : out[c,r] = in[r,c] (pitches ld_in / ld_out, padding zeroed) -- K-major GEMM operands
  *   freud_mask_grad       : dpre = (act > 0) ? g : 0 (bf16) with fp32 column sums (autograd of relu + topk)
  *   freud_scatter_add_rows: dst[rows_idx[r],:] += src[r,:] (subset gradients back into the full matrices) */
-int freud_row_topk_mask(const float* latents, void* out_bf16, int64_t rows, int64_t n, int64_t k, int64_t ld,
-                        void* stream);
+int freud_row_topk_mask(const float* latents, void* out_bf16, int64_t rows, int64_t n, int64_t k, int64_t ld_in,
+                        int64_t ld, int nonneg, void* stream);
+/* colsum[j] = sum_r x[r,j] over a bf16 matrix [rows, ld] (first n columns): the bias gradient of the dense AuxK
+ * branch (db_enc[dead] = sum_t dpre[t,:]). */
+int freud_col_sum_bf16(const void* x_bf16, float* colsum, int64_t rows, int64_t n, int64_t ld, void* stream);
 int freud_transpose_bf16(const void* in, void* out, int64_t rows, int64_t cols, int64_t ld_in, int64_t ld_out,
                          void* stream);
 int freud_mask_grad(const float* g, const void* act_bf16, void* dpre_bf16, float* colsum, int64_t rows, int64_t n,
@@ -97,6 +102,39 @@ int freud_scatter_add_rows(const float* src, const int32_t* rows_idx, float* dst
  * workspace [splits, M, N] receives partial A[M,K] @ B[N,K]^T products (bf16 operands), freud_sum_splits adds them. */
 int freud_gemm_nt_splitk(const void* a_bf16, const void* b_bf16, float* workspace, int64_t M, int64_t N, int64_t K,
                          int64_t splits, void* stream);
+/* Products with operands stored "the other way round" (read through MN-major tensor-core descriptors; nothing is
+ * transposed in memory).  bf16 operands, fp32 accumulation / output.
+ *   freud_gemm_tn_splitk: out[M,N] = A^T B, A stored [K, lda >= M], B stored [K, ldb >= N] (K = tokens: the
+ *                         weight-gradient shape, e.g. dW_dec[dead] = A^T g_hat, autograd of topkautoencoder.py:17-18,
+ *                         or the L1 SAE's X^T dZ, l1autoencoder.py:74,78); `splits` partials in workspace
+ *                         [splits,M,N], summed by freud_sum_splits.
+ *   freud_gemm_nn       : out[M,ldo] = act(A B + bias), A stored [M, lda >= K], B stored [K, ldb >= N]. */
+/* out_bf16[M, ld16] = (act_bf16[M, ld16] > 0) ? scale * (A B^T) + shift : 0, A [M, lda >= K], B [N,K] bf16 K-major,
+ * (scale, shift) = affine[0..1] on the device or (1, 0) if NULL: the activation gradient of the dense AuxK branch with
+ * the ReLU / top-k mask applied in the GEMM epilogue (topkautoencoder.py:118-123). */
+int freud_gemm_nt_mask(const void* a, const void* b, const void* act_bf16, void* out_bf16, const float* affine,
+                       int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ld16, void* stream);
+/* L1 SAE forward fused into the two tensor-core GEMMs (bf16 operands; l1autoencoder.py:69-95):
+ *   freud_l1_encode_fused: c = relu(x W + b) stored as bf16 [M, ld16] (zero padded), sums[0] += sum(c) (= the L1
+ *                          penalty's numerator, c >= 0); `latent` (fp32 [M,N]) optional.  x bf16 [M,K=d], wt = W^T
+ *                          bf16 [N=n, K=d].
+ *   freud_l1_decode_fused: x_hat = c W^T compared with target x [M,N=d] fp32: sums[0] += sum over x != -1 of e^2,
+ *                          sums[1] += count(x != -1), sums[2] += sum e^2  (mse_loss with ignored_index=-1, :29-36, and
+ *                          the return_mse value, :94); e * [x != -1] stored as bf16 [M, ld16] (the UNSCALED gradient of
+ *                          the reconstruction loss w.r.t. x_hat); `x_hat` (fp32 [M,N]) optional.  c bf16 [M, lda],
+ *                          w bf16 [N=d, ldb] with K = n valid columns.
+ *   freud_gemm_nt_mask with affine = device (scale, shift): dz = (c > 0) ? scale * (dxhat W) + shift : 0, the
+ *                          gradient through ReLU with the L1 term added (SURVEY.md M3'). */
+int freud_l1_encode_fused(const void* x_bf16, const void* wt_bf16, const float* bias, void* c_bf16, float* latent,
+                          double* sums, int64_t M, int64_t N, int64_t K, int64_t ld16, void* stream);
+int freud_l1_decode_fused(const void* c_bf16, const void* w_bf16, const float* target, void* resid_bf16, float* x_hat,
+                          double* sums, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ld16,
+                          void* stream);
+int freud_gemm_tn_splitk(const void* a, const void* b, float* workspace, int64_t M, int64_t N, int64_t K, int64_t lda,
+                         int64_t ldb, int64_t splits, void* stream);
+int freud_gemm_nn(const void* a, const void* b, const float* bias, float* out, int64_t M, int64_t N, int64_t K,
+                  int64_t lda, int64_t ldb, int64_t ldo, int relu, void* stream);
+
 int freud_sum_splits(const float* parts, float* out, int64_t splits, int64_t numel, void* stream);
 
 /* Sparse decode + residual (eager_decode + decode, topkautoencoder.py:15-18,87-91,101):
@@ -295,6 +333,12 @@ int freud_search_dense(const void* acts, int acts_is_fp16, const int32_t* n_fram
 int freud_search_indexed(const float* vals, const void* idx, int idx_is_int64, const int32_t* n_frames,
                          int64_t n_files, int64_t T, int64_t k, int64_t feature, float* vmax, int32_t* amax,
                          float* vabs, float* trace, void* stream);
+/* The same three statistics for EVERY feature column in one pass over the dense store (utils/activations.py:94-130
+ * loops over files per query; here one scan serves all later queries): tables [N_files, F], column `f` equal to what
+ * freud_search_dense returns for feature f.  F % 4 == 0. */
+int freud_search_table_dense(const void* acts, int acts_is_fp16, const int32_t* n_frames, int64_t n_files, int64_t T,
+                             int64_t F, float* vmax_tab, int32_t* amax_tab, float* vabs_tab, void* stream);
+
 /* Ranking of utils/activations.py:88-93,121-130: among files passing the min/max filter (applied to the
  * signed statistic), the n_top largest keys (vmax, or |vabs| when absolute != 0), ties broken by lower file
  * index (stable sort).  use_min/use_max select the optional bounds.  out_files int32 [n_top] (-1 padded),

@@ -60,7 +60,8 @@ from freud_b200.trainer import SAETrainer  # noqa: E402
 for prec in ("bf16", "fp32"):
     torch.manual_seed(0)
     m = L1AutoEncoder(384, L1AutoEncoderConfig.from_dict({"n_dict_components": 200, "recon_alpha": 1e4})).to(dev)
-    tr = SAETrainer(m, lr=4e-4, steps=100000, clip_thresh=1.0, optimizer="radam", scheduler="cosine", precision=prec)
+    tr = SAETrainer(m, lr=4e-4, steps=100000, clip_thresh=1.0, optimizer="radam", scheduler="cosine", precision=prec,
+                    materialize_outputs=False)
     xs = [bench.synth_batch(100, 1500, 384, 70 + i).to(dev) for i in range(3)]
     ms = timed(lambda i: tr.step(xs[i % 3]), 8)
     out[f"l1_step.c1.{prec}"] = {"ms_per_step": ms, "tokens_per_s": 150000 / ms * 1e3}

@@ -17,7 +17,8 @@ n_feat = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 for prec in ("bf16", "fp32"):
     torch.manual_seed(0)
     m = L1AutoEncoder(384, L1AutoEncoderConfig.from_dict({"n_dict_components": n_feat, "recon_alpha": 1e4})).to(dev)
-    tr = SAETrainer(m, lr=4e-4, steps=100000, clip_thresh=1.0, optimizer="radam", scheduler="cosine", precision=prec)
+    tr = SAETrainer(m, lr=4e-4, steps=100000, clip_thresh=1.0, optimizer="radam", scheduler="cosine", precision=prec,
+                    materialize_outputs=False)
     xs = [bench.synth_batch(100, 1500, 384, 70 + i).to(dev) for i in range(3)]
     for i in range(4):
         tr.step(xs[i % 3])

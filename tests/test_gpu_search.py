@@ -135,3 +135,38 @@ def test_file_sharded_search_matches_reference(tmp_path):
     out = mgr.dict()
     mp.spawn(_sharded_search_worker, args=(2, port, str(tmp_path), out), nprocs=2, join=True)
     assert dict(out) == {0: [], 1: []}
+
+
+def test_all_feature_table_equals_per_feature_scans():
+    """freud_search_table_dense: column f of the one-pass tables == freud_search_dense(feature=f), for fp32 and fp16
+    stores, F that needs several frame groups (F=48), exactly one (F=384) and more quads than threads (F=1280)."""
+    from freud_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for n_files, T, F, dt in ((300, 333, 48, torch.float32), (200, 1500, 384, torch.float32),
+                              (64, 200, 1280, torch.float16), (50, 97, 200, torch.float32)):
+        acts = torch.randn((n_files, T, F), device="cuda", generator=g).to(dt)
+        acts[:, ::7, :] = acts[:, 1::7, :][:, : acts[:, ::7, :].shape[1]]  # repeated values: arg-max ties
+        nf = torch.randint(0, T + 1, (n_files,), device="cuda", generator=g, dtype=torch.int32)
+        tv, ta, tb = ops.search_table_dense(acts, nf)
+        for f in (0, 1, F // 2, F - 1):
+            vmax, amax, vabs, _ = ops.search_dense(acts, nf, f, False)
+            assert torch.equal(tv[:, f], vmax) and torch.equal(ta[:, f], amax)
+            assert torch.equal(tb[:, f].nan_to_num(nan=-7.0), vabs.nan_to_num(nan=-7.0))
+
+
+def test_indexed_scan_int32_equals_int64():
+    """The narrowed-index scan (4 frames per load instruction, no shuffles on the hit path) == the int64 kernel."""
+    from freud_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(6)
+    n_files, T, k, n = 500, 700, 32, 300
+    r = torch.rand((n_files, T, n), device="cuda", generator=g)
+    idx = torch.topk(r, k, dim=-1).indices  # distinct indices per frame
+    vals = torch.randn((n_files, T, k), device="cuda", generator=g)  # signed values: abs statistics differ from max
+    nf = torch.randint(0, T + 1, (n_files,), device="cuda", generator=g, dtype=torch.int32)
+    for f in (0, 5, 150, 299):
+        a = ops.search_indexed(vals, idx, nf, f, False)
+        b = ops.search_indexed(vals, idx.to(torch.int32), nf, f, False)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+        assert torch.equal(a[2].nan_to_num(nan=-7.0), b[2].nan_to_num(nan=-7.0))
