@@ -449,6 +449,134 @@ def symmetric_memory_ok(device):
     return bool(flag.item())
 
 
+# ---------------------------------------------------------------------------------------------- secondary workloads
+def _timed(fn, iters, warm=3):
+    for i in range(warm):
+        fn(i)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for i in range(iters):
+        fn(i)
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters
+
+
+def extras_single_gpu(device, peaks):
+    """The other BASELINE.json configurations, measured briefly on this GPU so that they ride in the driver's BENCH
+    line (the headline workload above is C3): C2 (bf16), C3 with AuxK live, C1 (L1 SAE), C5 (feature search)."""
+    from freud_b200 import ops
+    from freud_b200.models.config import L1AutoEncoderConfig
+    from freud_b200.models.l1autoencoder import L1AutoEncoder
+    from freud_b200.trainer import SAETrainer
+
+    out = {}
+
+    def guarded(name, fn):
+        try:
+            out[name] = fn()
+        except Exception as ex:  # noqa: BLE001 -- a secondary measurement must never take the headline line down
+            out[name] = {"error": repr(ex)[:200]}
+        torch.cuda.empty_cache()
+
+    def topk_case(wl, dead_frac):
+        w = WORKLOADS[wl]
+        tr = build_trainer(w, "bf16", None, device)
+        xs = [synth_batch(w["B"], w["T"], w["d"], 50 + i, device=device) for i in range(3)]
+        if dead_frac:
+            dead = torch.randperm(w["n"], device=device)[: int(w["n"] * dead_frac)]
+            tr.tokens_seen = 10 ** 12
+
+            def step(i):
+                tr.num_frames_since_fired[dead] = 10 ** 9  # a fixed share of the latents stays dead: AuxK every step
+                tr.step(xs[i % 3])
+        else:
+            def step(i):
+                tr.step(xs[i % 3])
+        ms = _timed(step, 10)
+        return {"ms_per_step": ms, "tokens_per_s": w["B"] * w["T"] / ms * 1e3, "workload": w["desc"]}
+
+    guarded("c2_bf16", lambda: topk_case("c2", 0.0))
+    guarded("c3_auxk_live_10pct_dead", lambda: topk_case("c3", 0.1))
+
+    def l1_case():
+        torch.manual_seed(0)
+        m = L1AutoEncoder(384, L1AutoEncoderConfig.from_dict({"n_dict_components": 200, "recon_alpha": 1e4})).to(device)
+        tr = SAETrainer(m, lr=4e-4, steps=100000, clip_thresh=1.0, optimizer="radam", scheduler="cosine",
+                        precision="bf16", materialize_outputs=False)
+        xs = [synth_batch(100, 1500, 384, 70 + i, device=device) for i in range(3)]
+        ms = _timed(lambda i: tr.step(xs[i % 3]), 10)
+        # SURVEY.md 8(d): 7.7 kB/token of minimum traffic with the latent kept
+        return {"ms_per_step": ms, "tokens_per_s": 150000 / ms * 1e3, "hbm_floor_ms": 150000 * 7.7e3 / (peaks["hbm"] * 1e9) * 1e3,
+                "workload": "C1: L1 SAE d=384 n=200 B=100x1500 (configs/train/tiny_l1.json), RAdam + cosine"}
+
+    guarded("c1_l1_bf16", l1_case)
+
+    def search_case():
+        n_files, T, F = 10000, 1500, 384
+        g = torch.Generator(device=device).manual_seed(0)
+        n_frames = torch.randint(50, 1501, (n_files,), generator=g, device=device, dtype=torch.int32)
+        dense = torch.empty((n_files, T, F), dtype=torch.float32, device=device)
+        for s0 in range(0, n_files, 500):
+            dense[s0:s0 + 500].normal_(generator=g)
+        feats = [int(v) for v in torch.randint(0, F, (16,), generator=g, device=device)]
+        tab_ms = _timed(lambda i: ops.search_table_dense(dense, n_frames), 3, warm=1)
+        tv, ta, tb = ops.search_table_dense(dense, n_frames)
+        scanned = float(n_frames.sum()) * F * 4
+
+        def q(i):
+            f = feats[i % 16]
+            ops.search_topn(tv[:, f].contiguous(), tb[:, f].contiguous(), bool(i & 1), None, None, 20)
+
+        q_ms = _timed(q, 16)
+        exact = True
+        for f in feats[:4]:  # rankings of the table path == rankings of the per-feature scan of the store
+            vmax, amax, vabs, _ = ops.search_dense(dense, n_frames, f, False)
+            for ab in (False, True):
+                a, ca = ops.search_topn(vmax, vabs, ab, None, None, 20)
+                b, cb = ops.search_topn(tv[:, f].contiguous(), tb[:, f].contiguous(), ab, None, None, 20)
+                exact = exact and torch.equal(a, b) and int(ca) == int(cb) and torch.equal(ta[:, f], amax)
+        return {"files": n_files, "table_build_ms": tab_ms, "table_build_GBps": scanned / tab_ms / 1e6,
+                "frac_of_hbm": scanned / tab_ms / 1e6 / peaks["hbm"], "query_ms": q_ms,
+                "files_per_s_per_query": n_files / q_ms * 1e3, "rankings_exact": bool(exact),
+                "workload": "C5: 10 000 files x 1500 frames x 384 features fp32 (23 GB), trimmed lengths U{50..1500}; one "
+                            "all-feature table pass, then each query is a column gather + ranking kernel"}
+
+    guarded("c5_search_dense", search_case)
+    return out
+
+
+def extra_c4_sharded(device, rank, world):
+    """C4 (d=1280, n=81920, dictionary rows sharded over the ranks) on the ranks of this run: ms/step and a parity
+    check of one sharded step against the unsharded step on rank 0."""
+    import torch.distributed as dist
+
+    w = WORKLOADS["c4"]
+    tr = build_trainer(w, "bf16", None, device)
+    x = synth_batch(w["B"], w["T"], w["d"], 1000, device=device)
+    o = tr.step(x)
+    state = tr.gathered_state()
+    res = {}
+    if rank == 0:
+        single = build_trainer({**w, "sharded": False}, "bf16", None, device)
+        so = single.step(x)
+        torch.cuda.synchronize()
+        res["parity"] = {"loss_rel": abs(float(o["loss"]) - float(so["loss"])) / abs(float(so["loss"])),
+                         "param_rel": max(_rel(state[k], single.params[k].data) for k in _KEYS)}
+        res["parity"]["ok"] = bool(max(res["parity"].values()) < 1e-4)
+        del single, so
+        torch.cuda.empty_cache()
+    dist.barrier()
+    xs = [synth_batch(w["B"], w["T"], w["d"], 1001 + i, device=device) for i in range(2)]
+    ms = _timed(lambda i: tr.step(xs[i % 2]), 10)
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    res.update({"ms_per_step": float(t.item()), "tokens_per_s": w["B"] * w["T"] / float(t.item()) * 1e3,
+                "n_gpus": world, "scaling": "strong", "workload": w["desc"]})
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -459,9 +587,12 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the pre-timing parity check")
+    ap.add_argument("--e2e-dtype", default="fp16", choices=["fp16", "bf16", "fp32"],
+                    help="dtype of the pinned host batches of the end-to-end loop (fp16: CUDA-collected Whisper stores)")
     ap.add_argument("--dp-mode", default="fused", choices=["fused", "nccl"],
                     help="data parallel gradient exchange: fused peer-memory reduce-scatter + sharded Adam, or NCCL")
     ap.add_argument("--no-eager", action="store_true", help="skip the stock-PyTorch-eager-on-this-GPU arm")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads (C1, C2, C4, C5, AuxK live)")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel share table (json) here")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
@@ -568,56 +699,72 @@ def main():
     last_loss = float(out["loss"].item())
 
     # ---------------- end to end: pinned host batch -> H2D -> step -> loss read back, every step
+    # Host batches in float16 by default: the dtype of activation stores collected with Whisper on CUDA
+    # (hooked_model.py:106-108 decodes with fp16=True) -- the step widens them on the device.  The same
+    # loop with float32 host batches (CPU-collected stores; twice the PCIe bytes) is reported as `e2e_fp32_input`.
     copy_stream = torch.cuda.Stream(device)
-    stage = [torch.empty_like(dev_x[0]) for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
     freed = [torch.cuda.Event() for _ in range(2)]
     # feature-sharded ranks all need the SAME batch: each copies B/G files over its own PCIe link and the parts are
     # all-gathered over NVLink (FeatureShardedTopKTrainer.gather_batch) instead of G full copies from the host
     split_feed = sharded and world > 1 and B % world == 0
     per = B // world if split_feed else B
-    part = [torch.empty((per, T, d), dtype=torch.float32, device=device) for _ in range(2)] if split_feed else None
 
-    def prefetch(i):
-        s = i % 2
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(freed[s])
-            if split_feed:
-                part[s].copy_(host[i % n_bufs][rank * per:(rank + 1) * per], non_blocking=True)
-            else:
-                stage[s].copy_(host[i % n_bufs], non_blocking=True)
-            ready[s].record(copy_stream)
+    def run_e2e(dtype):
+        hosts = host if dtype == torch.float32 else [h.to(dtype).pin_memory() for h in host]
+        stage = [torch.empty((B, T, d), dtype=dtype, device=device) for _ in range(2)]
+        part = [torch.empty((per, T, d), dtype=dtype, device=device) for _ in range(2)] if split_feed else None
 
-    def e2e_loop(n):
-        for s in range(2):
-            freed[s].record()
-        prefetch(0)
-        loss_sum, prev = 0.0, None
-        for i in range(n):
-            if i + 1 < n:
-                prefetch(i + 1)  # overlaps the next batch's H2D with this step's compute
-            torch.cuda.current_stream().wait_event(ready[i % 2])
-            if split_feed:
-                tr.gather_batch(part[i % 2], out=stage[i % 2])
-            o = tr.step(stage[i % 2])
-            freed[i % 2].record()
-            # every step's loss is read back (4-byte D2H, train_sae.py:455); reading step i-1's after enqueueing
-            # step i keeps the host one step ahead of the device instead of idling the GPU during the enqueue
-            if prev is not None:
-                loss_sum += float(prev["loss"].item())
-            prev = o
-        loss_sum += float(prev["loss"].item())
-        return loss_sum
+        def prefetch(i):
+            s = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(freed[s])
+                if split_feed:
+                    part[s].copy_(hosts[i % n_bufs][rank * per:(rank + 1) * per], non_blocking=True)
+                else:
+                    stage[s].copy_(hosts[i % n_bufs], non_blocking=True)
+                ready[s].record(copy_stream)
 
-    e2e_loop(2)
-    barrier()
-    t0 = time.perf_counter()
-    ev0.record()
-    e2e_loop(args.steps)
-    ev1.record()
-    barrier()
-    e2e_ms = max_over_ranks(max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3))
+        def e2e_loop(n):
+            for s in range(2):
+                freed[s].record()
+            prefetch(0)
+            loss_sum, prev = 0.0, None
+            for i in range(n):
+                if i + 1 < n:
+                    prefetch(i + 1)  # overlaps the next batch's H2D with this step's compute
+                torch.cuda.current_stream().wait_event(ready[i % 2])
+                if split_feed:
+                    tr.gather_batch(part[i % 2], out=stage[i % 2])
+                o = tr.step(stage[i % 2])
+                freed[i % 2].record()
+                # every step's loss is read back (4-byte D2H, train_sae.py:455); reading step i-1's after enqueueing
+                # step i keeps the host one step ahead of the device instead of idling the GPU during the enqueue
+                if prev is not None:
+                    loss_sum += float(prev["loss"].item())
+                prev = o
+            loss_sum += float(prev["loss"].item())
+            return loss_sum
+
+        e2e_loop(2)
+        barrier()
+        t0 = time.perf_counter()
+        ev0.record()
+        e2e_loop(args.steps)
+        ev1.record()
+        barrier()
+        ms = max_over_ranks(max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3))
+        return ms, (per if split_feed else B) * T * d * hosts[0].element_size() * world
+
+    e2e_dtype = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[args.e2e_dtype]
+    e2e_ms, e2e_h2d = run_e2e(e2e_dtype)
     e2e_value = tokens_per_step * args.steps / (e2e_ms / 1e3)
+    e2e32 = None
+    if e2e_dtype != torch.float32:
+        ms32, h2d32 = run_e2e(torch.float32)
+        e2e32 = {"value": tokens_per_step * args.steps / (ms32 / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": h2d32,
+                 "d2h_bytes_per_step": 4 * world, "ms_per_step": ms32 / args.steps}
+    stage = None
 
     # ---------------- roofline of the dominant kernel (fused encoder GEMM + top-k), from the live events
     peaks = measured_peaks()
@@ -647,6 +794,22 @@ def main():
             json.dump({"workload": args.workload, "precision": args.precision, "n_gpus": world,
                        "ms_per_step": ms_per_step, "kernels": shares}, f, indent=1)
 
+    extras = None
+    want_extras = not args.no_extras and args.workload == "c3" and args.precision == "bf16"
+    dp_exchange = None
+    if dp is not None:
+        dp_exchange = ("fused peer-memory reduce-scatter + sharded Adam + bf16 all-gather" +
+                       (" (multimem)" if getattr(tr.optimizer, "multicast", False) else "")) \
+            if getattr(tr, "fused_dp", False) else "NCCL all-reduce"
+    if want_extras and world > 1:
+        # the feature-sharded configuration on the same ranks, so that the driver's scaling run carries it
+        del tr, dev_x
+        torch.cuda.empty_cache()
+        try:
+            extras = {"c4_feature_sharded": extra_c4_sharded(device, rank, world)}
+        except Exception as ex:  # noqa: BLE001
+            extras = {"c4_feature_sharded": {"error": repr(ex)[:200]}}
+        tr = dev_x = None
     if rank != 0:
         if dist.is_initialized():
             dist.destroy_process_group()
@@ -655,8 +818,10 @@ def main():
     eager = None
     if world == 1 and not sharded:
         # free this arm's trainers first: the eager reference materialises the dense [N,n] buffers
-        del tr, dev_x, stage
+        del tr, dev_x
         torch.cuda.empty_cache()
+        if want_extras:
+            extras = extras_single_gpu(device, peaks)
         if not args.no_eager:
             eager = run_torch_eager_cuda(w, 5, 2, device)
         if not args.no_cpu_baseline:
@@ -673,18 +838,18 @@ def main():
         "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
         "config": {"workload": f"{args.workload}: {w['desc']}", "global_batch_tokens": tokens_per_step,
                    "parallelism": (f"feature-sharded x{world}" if sharded else f"dp{world}"),
-                   "dp_exchange": (None if dp is None else ("fused peer-memory reduce-scatter + sharded Adam + bf16 all-gather"
-                                                            + (" (multimem)" if getattr(tr.optimizer, "multicast", False) else "")
-                                                            if getattr(tr, "fused_dp", False) else "NCCL all-reduce")),
+                   "dp_exchange": dp_exchange,
                    "optimizer": "adam+clip(1.0)+linear-warmup",
                    "l2": f"{n_bufs} rotating input batches of {B * T * d * 4 / 1e6:.0f} MB (> 126 MB L2)"
                    if B * T * d * 4 > 126e6 else f"{n_bufs} rotating input batches ({B * T * d * 4 / 1e6:.0f} MB each, "
                    f"{n_bufs * B * T * d * 4 / 1e6:.0f} MB total > 126 MB L2)"},
-        "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": (per if split_feed else B) * T * d * 4 * world,
-                "d2h_bytes_per_step": 4 * world, "ms_per_step": e2e_ms / args.steps},
+        "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": e2e_h2d,
+                "d2h_bytes_per_step": 4 * world, "ms_per_step": e2e_ms / args.steps,
+                "input_dtype": args.e2e_dtype + " pinned host batches, widened on the device"},
+        "e2e_fp32_input": e2e32,
 
         "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-        "loss": last_loss, "parity_check": parity, "torch_eager_b200": eager,
+        "loss": last_loss, "parity_check": parity, "torch_eager_b200": eager, "extra": extras,
         "kernel_shares": {k_: round(v["share"], 4) for k_, v in shares.items()},
     }
     print(json.dumps(line), flush=True)

@@ -225,10 +225,16 @@ def l1_decode_fused(c16: torch.Tensor, w16: torch.Tensor, n: int, target: torch.
     return r16, sums, x_hat
 
 
+def _lib_sm_count() -> int:
+    return torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count if torch.cuda.is_available() else 148
+
+
 def _splits_for(M: int, K: int, splits=None):
     total_kb = (K + 63) // 64
     if splits is None:
-        splits = max(1, min(total_kb, -(-148 // max(1, (M + 127) // 128))))  # about one CTA per SM
+        # one wave: row blocks x splits <= SM count (rounding UP put 160 CTAs on 148 SMs: a second, nearly empty wave
+        # doubled the time of the [2458, 768] AuxK weight-gradient products)
+        splits = max(1, min(total_kb, _lib_sm_count() // max(1, (M + 127) // 128)))
     per = (total_kb + splits - 1) // splits
     return (total_kb + per - 1) // per  # the split count the kernel will actually run (no empty partials)
 
@@ -418,7 +424,7 @@ def l1_weight_grad_tc(x, dxhat, dc, latent, scales4):
     call("freud_l1_grad_operands", _ptr(x), _ptr(dxhat), _ptr(dc), _ptr(latent), _ptr(scales4), _ptr(At), _ptr(Bt),
          _ptr(db), N, Np, d, n, _stream())
     row_blocks = (d + 127) // 128
-    splits = max(1, min((2 * Np) // 64, -(-148 // row_blocks)))  # one CTA per SM
+    splits = max(1, min((2 * Np) // 64, 148 // row_blocks))  # one wave of CTAs
     return gemm_nt_splitk(At, Bt, splits), db
 
 
