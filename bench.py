@@ -772,7 +772,7 @@ def main():
     step_kernel_ms = sum(v[1] for v in prof.values())
     roofline = None
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_encoder_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_encoder_traffic.json")
     if os.path.exists(tpath) and world == 1:
         with open(tpath) as f:
             traffic = json.load(f).get(f"{args.workload}.{args.precision}")  # bytes/launch from the ncu capture
@@ -780,7 +780,7 @@ def main():
         # 2*d*n per token (algorithmic, one bf16 pass); a shard multiplies n/world features
         flops = 2.0 * B * T * d * (w["n"] // world if sharded else w["n"])
         achieved = flops / (enc_ms / enc_calls * 1e-3) / 1e12
-        roofline = {"kernel": "sm100_gemm_kernel<EPI_TOPK> (freud_topk_encode)", "bound": "tensor",
+        roofline = {"kernel": "sm100_topk_kernel (freud_topk_encode)", "bound": "tensor",
                     "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                     "frac": achieved / peaks["tf_sustained"], "traffic": traffic,
                     "algorithmic_bytes": (B * T * d + (w["n"] // world if sharded else w["n"]) * d) * 2 + B * T * 256,

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfreud_b200.so")
 STAMP = os.path.join(HERE, ".libfreud_b200.stamp")
-SOURCES = ["common.cu", "encoder.cu", "sparse.cu", "select.cu", "optim.cu", "l1.cu", "search.cu", "stats.cu", "collective.cu"]
+SOURCES = ["common.cu", "encoder.cu", "sparse.cu", "decode_dacts.cu", "select.cu", "optim.cu", "l1.cu", "search.cu", "stats.cu", "collective.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 NVCC_FLAGS.remove("--use_fast_math=false")  # IEEE division / sqrt: parity with the reference matters

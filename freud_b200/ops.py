@@ -284,6 +284,26 @@ def topk_decode(top_vals, top_idx, W_dec, b_dec, target=None, *, resid_dtype=Non
     return sae_out, resid, sse, colsum
 
 
+def decode_dacts_supported(d: int, k: int) -> bool:
+    return bool(_lib.lib().freud_topk_decode_dacts_supported(d, k))
+
+
+def topk_decode_dacts(top_vals, top_idx, W_dec, b_dec, target):
+    """Fused bf16 fast path: (sae_out fp32, residual bf16, sse, colsum, dacts) with the decoder rows gathered once."""
+    N, k = top_vals.shape
+    d = W_dec.shape[1]
+    dev = top_vals.device
+    assert W_dec.dtype == torch.bfloat16
+    sae_out = torch.empty((N, d), dtype=torch.float32, device=dev)
+    resid = torch.empty((N, d), dtype=torch.bfloat16, device=dev)
+    sse = torch.zeros(1, dtype=torch.float64, device=dev)
+    colsum = torch.zeros(d, dtype=torch.float32, device=dev)
+    dacts = torch.empty((N, k), dtype=torch.float32, device=dev)
+    call("freud_topk_decode_dacts", _ptr(top_vals), _ptr(top_idx), _ptr(W_dec), _ptr(b_dec), _ptr(target),
+         _ptr(sae_out), _ptr(resid), _ptr(sse), _ptr(colsum), _ptr(dacts), N, d, k, _stream())
+    return sae_out, resid, sse, colsum, dacts
+
+
 def topk_dacts(g, top_idx, W_dec):
     N, k = top_idx.shape
     d = W_dec.shape[1]

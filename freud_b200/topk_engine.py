@@ -9,6 +9,7 @@ Two routes through the same C ABI:
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Optional
 
@@ -43,6 +44,7 @@ class TopKState:
     scal_ready: Optional[torch.cuda.Event] = None  # set when `scal` is still being produced on a side stream
     csc_ready: Optional[torch.cuda.Event] = None   # recorded once `offsets` is complete on the main stream
     csc: Optional[tuple] = None  # (offsets, entries, event) of the main selection, built on the side stream
+    dacts: Optional[torch.Tensor] = None  # <e, W_dec[idx]> when the forward already formed it (fused decode + dacts)
     extra: dict = field(default_factory=dict)
 
 
@@ -66,7 +68,8 @@ def aux_stream(device):
     key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
     s = _aux_streams.get(key)
     if s is None:
-        s = _aux_streams[key] = torch.cuda.Stream(torch.device("cuda", key))
+        prio = -1 if os.environ.get("FREUD_CSC_MODE", "side") == "side_hi" else 0
+        s = _aux_streams[key] = torch.cuda.Stream(torch.device("cuda", key), priority=prio)
     return s
 
 
@@ -132,7 +135,7 @@ def topk_forward(x, W_enc, b_enc, W_dec, b_dec, k, *, precision, dead_mask=None,
         vals, idx = ops.row_topk(pre, k)
 
     csc = None
-    if fused_main and need_grad and not generic:
+    if fused_main and need_grad and not generic and os.environ.get("FREUD_CSC_MODE", "side") != "serial":
         # the feature-major (CSC) index of the backward depends on the indices alone: built on a side stream while
         # the main stream decodes and forms the activation gradients
         cur, side = torch.cuda.current_stream(), aux_stream(x.device)
@@ -150,8 +153,13 @@ def topk_forward(x, W_enc, b_enc, W_dec, b_dec, k, *, precision, dead_mask=None,
         resid_dtype = torch.float32
     elif need_grad:
         resid_dtype = torch.bfloat16 if precision == BF16 else torch.float32
-    sae_out, e, sse, colsum_e = ops.topk_decode(vals, idx, wd, b_dec, x2, resid_dtype=resid_dtype, want_sse=True,
-                                                want_colsum=need_grad)
+    dacts = None
+    if (fused_main and need_grad and not generic and precision == BF16 and ops.decode_dacts_supported(d, k)):
+        # the decoder rows of a token are gathered once for the reconstruction AND the activation gradients
+        sae_out, e, sse, colsum_e, dacts = ops.topk_decode_dacts(vals, idx, wd, b_dec, x2)
+    else:
+        sae_out, e, sse, colsum_e = ops.topk_decode(vals, idx, wd, b_dec, x2, resid_dtype=resid_dtype, want_sse=True,
+                                                    want_colsum=need_grad)
     numel = N * d
     scal_ready = None
     side = dp.side_stream() if dp is not None else None
@@ -182,6 +190,7 @@ def topk_forward(x, W_enc, b_enc, W_dec, b_dec, k, *, precision, dead_mask=None,
                    idx, e, colsum_e, auxk_alpha=auxk_alpha)
     st.scal_ready = scal_ready
     st.csc = csc
+    st.dacts = dacts
 
     auxk = zero
     if num_dead > 0:
@@ -273,7 +282,7 @@ def topk_backward(st: TopKState, g_fvu, g_aux=None, g_multi=None, *, out=None, o
             scales = st.scal[2:4]  # (2/tv, 2/tv) straight from the loss-scalar kernel, no extra launch
         else:
             scales = st.scal[2:4] * float(g_fvu)
-        dacts = ops.topk_dacts(st.e, st.idx, st.wd)
+        dacts = st.dacts if st.dacts is not None else ops.topk_dacts(st.e, st.idx, st.wd)
         if st.csc is not None:
             offsets, entries, csc_done = st.csc
             torch.cuda.current_stream().wait_event(csc_done)

@@ -153,6 +153,16 @@ int freud_topk_decode(const float* top_vals, const int32_t* top_idx, const void*
 int freud_topk_dacts(const void* g, int g_is_bf16, const int32_t* top_idx, const void* W_dec, int w_is_bf16,
                      float* dacts, int64_t N, int64_t d, int64_t k, void* stream);
 
+/* Fused twin of the two calls above for the bf16 fast path (k == 32, d in {384, 512, 768, 1024, 1280}): a token's 32
+ * decoder rows are fetched once (one TMA bulk copy per row into shared memory) and serve both the reconstruction
+ * (topkautoencoder.py:15-18,87-91,101) and dacts[t,j] = <bf16(sae_out[t] - target[t]), W_dec[top_idx[t,j]]> (autograd
+ * of :17-18).  All outputs required; sse / colsum are accumulated into (caller zeroes).  Entries with index -1
+ * (another dictionary shard's) contribute nothing and get dacts 0. */
+int freud_topk_decode_dacts_supported(int64_t d, int64_t k);
+int freud_topk_decode_dacts(const float* top_vals, const int32_t* top_idx, const void* W_dec_bf16, const float* b_dec,
+                            const float* target, float* sae_out, void* resid_bf16, double* sse, float* colsum,
+                            float* dacts, int64_t N, int64_t d, int64_t k, void* stream);
+
 /* fp32 mode: top_vals[t,j] <- relu((x[t] - b_dec) . W_enc[top_idx[t,j]] + b_enc[top_idx[t,j]]) with an fp32 FMA
  * chain (topkautoencoder.py:72-77 restricted to the selected latents): the tensor-core product selects, this pass
  * restores the selected values to fp32-GEMM accuracy.  Entries with index -1 are left untouched. */

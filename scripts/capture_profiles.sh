@@ -1,24 +1,38 @@
 #!/bin/bash
-# Round artefacts, captured on the GPU box (gpurun -- 'bash scripts/capture_profiles.sh r01').
+# Round artefacts, captured on the GPU box (gpurun -- 'bash scripts/capture_profiles.sh r02').
 # Bench lines are taken WITHOUT a profiler; ncu runs are separate processes.  Everything lands in gpurun_out/cap_<tag>/;
 # scripts/summarize_profiles.py turns that directory into the tracked files under profiles/.
 set -u
-TAG=${1:-r01}
+TAG=${1:-r02}
 OUT=gpurun_out/cap_$TAG
 mkdir -p $OUT
 python bench.py --profile-out $OUT/prof_c3.json > $OUT/bench_c3.json 2> $OUT/bench_c3.err
-python bench.py --workload c2 --no-cpu-baseline --profile-out $OUT/prof_c2.json > $OUT/bench_c2.json 2> $OUT/bench_c2.err
-python bench.py --workload c2 --precision fp32 --no-cpu-baseline > $OUT/bench_c2_fp32.json 2> /dev/null
-python bench.py --workload c4 --no-cpu-baseline --profile-out $OUT/prof_c4.json > $OUT/bench_c4_1gpu.json 2> $OUT/bench_c4.err
+python bench.py --workload c2 --no-cpu-baseline --no-eager --profile-out $OUT/prof_c2.json > $OUT/bench_c2.json 2> $OUT/bench_c2.err
+python bench.py --workload c2 --precision fp32 --no-cpu-baseline --no-eager --no-parity > $OUT/bench_c2_fp32.json 2> /dev/null
+python bench.py --workload c4 --no-cpu-baseline --no-eager --no-parity --profile-out $OUT/prof_c4.json > $OUT/bench_c4_1gpu.json 2> $OUT/bench_c4.err
 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_reference_arm.json 2> $OUT/bench_ref.err
 python scripts/bench_extra.py > $OUT/bench_extra.json 2> $OUT/bench_extra.err
+python scripts/l2_microbench.py > $OUT/l2_microbench.json 2> $OUT/l2_microbench.err
 # launch list of the bench step (cold-cache, serialised: shares only)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_c3.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_launch.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-eager --no-parity --no-extras > $OUT/ncu_launch.log 2>&1
 # one --set full capture each of the dominant kernels (launch of the 4th step)
-for spec in "enc:sm100_gemm_kernel" "sgw:sparse_grads_warp_kernel" "dec:decode_fixed_kernel" "dac:dacts_fixed_kernel" "adam:adam_kernel"; do
+for spec in "enc:sm100_topk_kernel" "sgw:sparse_grads_warp_kernel" "dec:decode_fixed_kernel" "dac:dacts_fixed_kernel" "adam:adam_kernel"; do
   name=${spec%%:*}; rx=${spec##*:}
   ncu --set full --clock-control none --import-source on -k regex:$rx -s 3 -c 1 -o $OUT/full_${name}_c3 \
-      python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_full_$name.log 2>&1
+      python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-eager --no-parity --no-extras > $OUT/ncu_full_$name.log 2>&1
 done
+ncu --set full --clock-control none --import-source on -k regex:sm100_topk_kernel -s 3 -c 1 -o $OUT/full_enc_c2 \
+      python bench.py --workload c2 --steps 1 --warmup 3 --no-cpu-baseline --no-eager --no-parity > $OUT/ncu_full_enc_c2.log 2>&1
+ncu --set full --clock-control none -k regex:search_table_kernel -c 1 -o $OUT/full_search_table \
+      python scripts/bench_extra.py > /dev/null 2>&1
+# gpurun copies back at most 64 MiB: keep the raw metric page of every capture as CSV, drop the reports
+for rep in $OUT/*.ncu-rep; do
+  ncu -i $rep --page raw --csv > ${rep%.ncu-rep}.raw.csv 2> /dev/null && rm -f $rep
+done
+# SASS evidence of the Blackwell-native path (tcgen05 / TMEM / TMA / multimem mnemonics in the shipped library)
+cuobjdump -sass freud_b200/libfreud_b200.so | grep -oE "UTCHMMA[A-Z0-9_.]*|UTCQMMA[A-Z0-9_.]*|LDTM[A-Z0-9_.]*|STTM[A-Z0-9_.]*|UTMALDG[A-Z0-9_.]*|UTMASTG[A-Z0-9_.]*|UBLKCP[A-Z0-9_.]*|UTCBAR[A-Z0-9_.]*|SYNCS[A-Z0-9_.]*|MULTIMEM[A-Z0-9_.]*|HMMA[A-Z0-9_.]*" | sort | uniq -c | sort -rn > $OUT/sass_mnemonics.txt
+# compute-sanitizer over the kernels with hand-rolled synchronisation
+bash scripts/sanitize.sh memcheck racecheck > $OUT/sanitize.log 2>&1
+cp gpurun_out/sanitize_*.log $OUT/ 2>/dev/null
 ls -la $OUT

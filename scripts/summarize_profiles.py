@@ -75,11 +75,15 @@ def launch_list():
 def full_captures():
     traffic = {}
     for fn in sorted(os.listdir(cap)):
-        if not fn.endswith(".ncu-rep"):
+        if fn.endswith(".raw.csv"):  # exported on the GPU box (capture_profiles.sh), the report itself is not kept
+            name = fn[:-len(".raw.csv")]
+            raw = open(os.path.join(cap, fn)).read()
+        elif fn.endswith(".ncu-rep"):
+            name = fn[:-len(".ncu-rep")]
+            raw = subprocess.run(["ncu", "-i", os.path.join(cap, fn), "--page", "raw", "--csv"], capture_output=True,
+                                 text=True, check=True).stdout
+        else:
             continue
-        name = fn[:-len(".ncu-rep")]
-        raw = subprocess.run(["ncu", "-i", os.path.join(cap, fn), "--page", "raw", "--csv"], capture_output=True,
-                             text=True, check=True).stdout
         rows = list(csv.reader(io.StringIO(raw)))
         h, units, r = rows[0], rows[1], rows[2]
         with open(os.path.join(out, f"{tag}_ncu_{name}.csv"), "w") as f:
@@ -100,7 +104,7 @@ def full_captures():
             def val(m):
                 v, u = float(r[h.index(m)]), units[h.index(m)]
                 return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
-            traffic["c3.bf16"] = val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
+            traffic["c2.bf16" if name.endswith("c2") else "c3.bf16"] = val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
     if traffic:
         traffic["note"] = (f"dram__bytes_read.sum + dram__bytes_write.sum of the fused encoder kernel per launch, "
                            f"ncu --set full, profiles/{tag}_ncu_full_enc_c3.csv")

@@ -256,9 +256,74 @@ def search_case():
     print("wrote search")
 
 
+def clip_case():
+    """top_activations_for_audio / manipulate_latent (utils/activations.py:135-300) with a stand-in Whisper: the
+    cache's forward() just exposes a seeded [1, 1500, d] activation tensor, the substituted model records what it is
+    handed.  Everything after the Whisper forward -- SAE forward, per-frame loops, trims, decode -- is the reference's."""
+    import src.utils.activations as ua
+
+    ua.get_mels_from_np_array = lambda device, audio, n_mels: ("mel", len(audio), n_mels)
+
+    class Result:
+        def __init__(self, text):
+            self.text = text
+
+    class Cache:
+        model_name, device = "tiny", "cpu"
+
+        def __init__(self, acts):
+            self._acts = acts
+
+        def forward(self, mel):
+            self.activations = self._acts.clone()
+            return Result("baseline")
+
+    class Subbed:
+        def __init__(self):
+            self.seen = []
+
+        def forward(self, mel, sub):
+            self.seen.append(sub.detach().clone())
+            return Result(f"subbed{len(self.seen)}")
+
+    torch.manual_seed(11)
+    d, T, top_n = 32, 1500, 6
+    audio = np.zeros(139_777, dtype=np.float32)  # 8.736 s -> 436 frames kept of the padded 1500
+    acts = torch.randn(1, T, d) * 0.7
+    acts[0, 100:110] = acts[0, 90:100]  # repeated frames: exact value ties across frames
+    topk = TopKAutoEncoder(d, TopKAutoEncoderConfig.from_dict({"n_dict_components": 256, "k": 8}))
+    l1 = L1AutoEncoder(d, L1AutoEncoderConfig.from_dict({"n_dict_components": 40}))
+    with torch.no_grad():
+        l1.encoder_bias.add_(0.05)
+    rec = {"acts": acts, "audio_len": np.int64(len(audio)), "top_n": np.int64(top_n)}
+    for k_, v in topk.state_dict().items():
+        rec[f"topk.{k_}"] = v.clone()
+    for k_, v in l1.state_dict().items():
+        rec[f"l1.{k_}"] = v.clone()
+    for tag, sae in (("topk", topk), ("l1", l1), ("none", None)):
+        feats, traces = ua.top_activations_for_audio(audio, Cache(acts), sae, top_n)
+        rec[f"{tag}.top.features"] = np.asarray(feats, dtype=np.int64)
+        rec[f"{tag}.top.traces"] = torch.stack([torch.as_tensor(t).float() for t in traces])
+        feat = int(feats[1])
+        sub = Subbed()
+        base, man_text, std_text, pre, man = ua.manipulate_latent(audio, Cache(acts), sae, sub, feat, 3.5)
+        rec[f"{tag}.man.feature"] = np.int64(feat)
+        rec[f"{tag}.man.texts"] = np.asarray([str(base), man_text, std_text])
+        rec[f"{tag}.man.pre"] = pre.float()
+        rec[f"{tag}.man.value"] = man.float()
+        rec[f"{tag}.man.sub_manipulated"] = sub.seen[0].float()
+        rec[f"{tag}.man.sub_standard"] = sub.seen[1].float()
+    out = {k_: (v.detach().numpy() if isinstance(v, torch.Tensor) else v) for k_, v in rec.items()}
+    np.savez_compressed(os.path.join(HERE, "clip.npz"), **out)
+    print("wrote clip")
+
+
 if __name__ == "__main__":
     if not ref_shims.reference_available():
         sys.exit("reference tree not found")
+    if sys.argv[1:] == ["clip"]:
+        clip_case()
+        sys.exit(0)
     topk_case("topk_fp32", 4, 6, 32, 256, 8, auxk_alpha=1 / 32, multi_topk=False, n_dead=0, autocast=False, steps=3)
     topk_case("topk_fp32_auxk", 4, 6, 32, 256, 8, auxk_alpha=1 / 32, multi_topk=False, n_dead=40, autocast=False, steps=2)
     topk_case("topk_fp32_auxk_few", 4, 6, 32, 256, 8, auxk_alpha=1 / 32, multi_topk=False, n_dead=5, autocast=False, steps=1)
@@ -272,3 +337,4 @@ if __name__ == "__main__":
     misc_case()
     feature_stats_case()
     search_case()
+    clip_case()

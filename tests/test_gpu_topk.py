@@ -345,3 +345,47 @@ def test_gradients_through_sae_out_and_top_acts(precision, tol):
     named = dict(model.named_parameters())
     for key in TOPK_KEYS:
         assert rel_err(named[key].grad.cpu(), cpu[key].grad) < tol, key
+
+
+@pytest.mark.parametrize("d,N", [(384, 1000), (512, 77), (768, 1500), (1024, 130), (1280, 301)])
+@pytest.mark.parametrize("sharded", [False, True])
+def test_fused_decode_dacts_matches_separate_kernels(d, N, sharded):
+    """freud_topk_decode_dacts (rows gathered once through shared memory) == freud_topk_decode followed by
+    freud_topk_dacts: reconstruction / residual / column sums bit-for-bit (same FMA order), dacts to fp32 rounding of
+    a differently-ordered dot, and both against an fp64 evaluation of eager_decode (topkautoencoder.py:15-18) and its
+    autograd; `sharded` marks a third of the entries as another shard's (index -1)."""
+    from freud_b200 import ops
+
+    g = torch.Generator().manual_seed(d + N)
+    n, k = 4096, 32
+    W = (torch.randn(n, d, generator=g) / d ** 0.5).to(torch.bfloat16).cuda()
+    b_dec = (0.1 * torch.randn(d, generator=g)).cuda()
+    x = torch.randn(N, d, generator=g).cuda()
+    idx = torch.stack([torch.randperm(n, generator=g)[:k] for _ in range(N)]).to(torch.int32)
+    vals = torch.rand(N, k, generator=g)
+    if sharded:
+        drop = torch.rand(N, k, generator=g) < 0.33
+        drop[0] = True  # a token none of whose winners this shard owns
+        idx[drop] = -1
+        vals[drop] = 0.0
+    idx, vals = idx.cuda(), vals.cuda()
+    out_f, e_f, sse_f, cs_f, da_f = ops.topk_decode_dacts(vals, idx, W, b_dec, x)
+    out_s, e_s, sse_s, cs_s = ops.topk_decode(vals, idx, W, b_dec, x, resid_dtype=torch.bfloat16, want_sse=True,
+                                              want_colsum=True)
+    da_s = ops.topk_dacts(e_s, idx, W)
+    torch.cuda.synchronize()
+    assert torch.equal(out_f, out_s)
+    assert torch.equal(e_f.view(torch.int16), e_s.view(torch.int16))
+    assert rel_err(sse_f.cpu(), sse_s.cpu()) < 1e-12
+    assert rel_err(cs_f.cpu(), cs_s.cpu()) < 1e-5
+    assert rel_err(da_f.cpu(), da_s.cpu()) < 2e-6
+    # fp64 evaluation
+    Wd = W.double().cpu()
+    safe = idx.cpu().long().clamp_min(0)
+    live = (idx.cpu() >= 0).double()
+    rows = Wd[safe]                                                    # [N,k,d]
+    out64 = ((vals.cpu().double() * live).unsqueeze(-1) * rows).sum(1) + b_dec.double().cpu()
+    assert rel_err(out_f.cpu(), out64) < 1e-6
+    da64 = (rows * e_f.double().cpu().unsqueeze(1)).sum(-1) * live
+    assert rel_err(da_f.cpu(), da64) < 2e-6
+    assert bool((da_f.cpu()[idx.cpu() < 0] == 0).all())
