@@ -792,15 +792,38 @@ __global__ void __launch_bounds__(256) sparse_grads_warp_kernel(
         rg[u] = ldg_keep(gcol + static_cast<int64_t>(t[u]) * d, keep);
         rx[u] = ldg_keep(xcol + static_cast<int64_t>(t[u]) * d, keep);
       }
+      if constexpr (sizeof(GT) == 2 && sizeof(XT) == 2) {
+        // both rows bf16: one packed fp32 FMA (FFMA2) per bf16 PAIR -- each half an IEEE fma, bit-identical to the
+        // scalar chain; the kernel is bound by instruction issue, and the FMAs were 40 % of its instructions
 #pragma unroll
-      for (int u = 0; u < R; ++u) {
-        float gv[V], xv[V];
-        RowVec<GT>::unpack(rg[u], gv);
-        RowVec<XT>::unpack(rx[u], xv);
+        for (int u = 0; u < R; ++u) {
+          const uint32_t wg[4] = {rg[u].x, rg[u].y, rg[u].z, rg[u].w};
+          const uint32_t wx[4] = {rx[u].x, rx[u].y, rx[u].z, rx[u].w};
 #pragma unroll
-        for (int e = 0; e < V; ++e) {
-          accd[e] = fmaf(a[u], gv[e], accd[e]);
-          acce[e] = fmaf(dp[u], kRecenter ? xv[e] - bd[e] : xv[e], acce[e]);
+          for (int q = 0; q < 4; ++q) {
+            const float2 rd = __ffma2_rn(make_float2(a[u], a[u]),
+                                         make_float2(__uint_as_float(wg[q] << 16), __uint_as_float(wg[q] & 0xffff0000u)),
+                                         make_float2(accd[2 * q], accd[2 * q + 1]));
+            accd[2 * q] = rd.x;
+            accd[2 * q + 1] = rd.y;
+            const float2 re = __ffma2_rn(make_float2(dp[u], dp[u]),
+                                         make_float2(__uint_as_float(wx[q] << 16), __uint_as_float(wx[q] & 0xffff0000u)),
+                                         make_float2(acce[2 * q], acce[2 * q + 1]));
+            acce[2 * q] = re.x;
+            acce[2 * q + 1] = re.y;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < R; ++u) {
+          float gv[V], xv[V];
+          RowVec<GT>::unpack(rg[u], gv);
+          RowVec<XT>::unpack(rx[u], xv);
+#pragma unroll
+          for (int e = 0; e < V; ++e) {
+            accd[e] = fmaf(a[u], gv[e], accd[e]);
+            acce[e] = fmaf(dp[u], kRecenter ? xv[e] - bd[e] : xv[e], acce[e]);
+          }
         }
       }
     }
