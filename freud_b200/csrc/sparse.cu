@@ -4,6 +4,9 @@
 // L2 / HBM bandwidth; none is reshaped into a GEMM.
 #include <type_traits>
 
+#include <algorithm>
+#include <cstdlib>
+#include <string>
 #include "device_utils.cuh"
 #include "host_common.h"
 #include "../../include/freud_b200.h"
@@ -560,24 +563,52 @@ __device__ __forceinline__ int32_t block_excl_scan_1024(int32_t v, int32_t* warp
   return (w > 0 ? warp_tot[w - 1] : 0) + incl - v;
 }
 
-// Single-block exclusive scan of counts[0..n) -> offsets[0..n]; cursor[f] = offsets[f].  Every thread owns a run
-// of ceil(n/1024) consecutive counts (serial in registers), so the block synchronises once, not once per 1024.
+// Single-block exclusive scan of counts[0..n) -> offsets[0..n]; cursor[f] = offsets[f]; cursor[n] = 0 (the long-list
+// work counter of the sort kernels).  Tiles of 4096 counts: thread i owns the 16-byte run {4i .. 4i+3} of a tile, so the
+// loads and stores are coalesced (the first version gave every thread one long private run: 24 strided loads per
+// thread, 32 us at n = 24 576); the next tile's loads are issued before the block scan of the current one.
 __global__ void __launch_bounds__(1024) csc_scan_kernel(int32_t* __restrict__ offsets, int32_t* __restrict__ cursor,
                                                         int n) {
   __shared__ int32_t warp_tot[32];
-  const int per = (n + 1023) / 1024;
-  const int lo = min(n, static_cast<int>(threadIdx.x) * per), hi = min(n, lo + per);
-  int32_t sum = 0;
-  for (int i = lo; i < hi; ++i) sum += offsets[i];  // offsets holds the raw counts on entry
-  int32_t total;
-  int32_t run = block_excl_scan_1024(sum, warp_tot, &total);
-  for (int i = lo; i < hi; ++i) {
-    const int32_t v = offsets[i];
-    offsets[i] = run;
-    cursor[i] = run;
-    run += v;
+  const int tiles = (n + 4095) / 4096;
+  int32_t carry = 0;
+  auto load_tile = [&](int tile) {
+    const int i0 = tile * 4096 + static_cast<int>(threadIdx.x) * 4;
+    int4 v = make_int4(0, 0, 0, 0);
+    if (i0 + 3 < n && (n & 3) == 0) {
+      v = *reinterpret_cast<const int4*>(offsets + i0);
+    } else {
+      if (i0 < n) v.x = offsets[i0];
+      if (i0 + 1 < n) v.y = offsets[i0 + 1];
+      if (i0 + 2 < n) v.z = offsets[i0 + 2];
+      if (i0 + 3 < n) v.w = offsets[i0 + 3];
+    }
+    return v;
+  };
+  int4 nxt = load_tile(0);
+  for (int tile = 0; tile < tiles; ++tile) {
+    const int4 v = nxt;
+    if (tile + 1 < tiles) nxt = load_tile(tile + 1);
+    int32_t total;
+    const int32_t run = carry + block_excl_scan_1024(v.x + v.y + v.z + v.w, warp_tot, &total);
+    const int4 o = make_int4(run, run + v.x, run + v.x + v.y, run + v.x + v.y + v.z);
+    const int i0 = tile * 4096 + static_cast<int>(threadIdx.x) * 4;
+    if (i0 + 3 < n && (n & 3) == 0) {
+      *reinterpret_cast<int4*>(offsets + i0) = o;
+      *reinterpret_cast<int4*>(cursor + i0) = o;
+    } else {
+      if (i0 < n) offsets[i0] = cursor[i0] = o.x;
+      if (i0 + 1 < n) offsets[i0 + 1] = cursor[i0 + 1] = o.y;
+      if (i0 + 2 < n) offsets[i0 + 2] = cursor[i0 + 2] = o.z;
+      if (i0 + 3 < n) offsets[i0 + 3] = cursor[i0 + 3] = o.w;
+    }
+    carry += total;
+    __syncthreads();  // warp_tot is reused by the next tile
   }
-  if (threadIdx.x == 0) offsets[n] = total;
+  if (threadIdx.x == 0) {
+    offsets[n] = carry;
+    cursor[n] = 0;
+  }
 }
 
 __global__ void __launch_bounds__(256) csc_fill_kernel(const int32_t* __restrict__ top_idx, int64_t total,
@@ -601,12 +632,17 @@ constexpr int kRankSortMax = 256;  // O(len^2 / 256) per thread: beyond this the
 // Lists of up to 128 entries (the common case: N*k/n on average): one warp per feature, 4 entries per lane, rank
 // sort by shuffle broadcast (entries are distinct positions, so rank = number of smaller entries).
 __global__ void __launch_bounds__(256) csc_sort_warp_kernel(const int32_t* __restrict__ offsets,
-                                                            int32_t* __restrict__ entries, int n) {
+                                                            int32_t* __restrict__ entries, int32_t* __restrict__ worklist,
+                                                            int n) {
   const int lane = threadIdx.x & 31;
   const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (f >= n) return;
   const int beg = offsets[f], len = offsets[f + 1] - beg;
-  if (len <= 1 || len > kWarpSortMax) return;
+  if (len > kWarpSortMax) {  // left to csc_sort_kernel: queue the feature (cursor is free once the fill is done)
+    if (lane == 0 && len <= kSortMax) worklist[atomicAdd(worklist + n, 1)] = f;
+    return;
+  }
+  if (len <= 1) return;
   int32_t v[4];
   int rank[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -627,12 +663,17 @@ __global__ void __launch_bounds__(256) csc_sort_warp_kernel(const int32_t* __res
   for (int q = 0; q < 4; ++q)
     if (lane + 32 * q < len) entries[beg + rank[q]] = v[q];
 }
+// Lists of kWarpSortMax + 1 .. kSortMax entries, queued by csc_sort_warp_kernel: a fixed grid walks the queue (one CTA
+// per feature used to be launched -- n CTAs that almost all returned at once cost 16 us at n = 24 576).
 __global__ void __launch_bounds__(256) csc_sort_kernel(const int32_t* __restrict__ offsets,
-                                                       int32_t* __restrict__ entries) {
+                                                       int32_t* __restrict__ entries,
+                                                       const int32_t* __restrict__ worklist, int n) {
   __shared__ int32_t buf[kSortMax];
-  const int f = blockIdx.x;
+  const int count = worklist[n];
+  for (int item = blockIdx.x; item < count; item += gridDim.x) {
+  __syncthreads();  // buf is reused
+  const int f = worklist[item];
   const int beg = offsets[f], len = offsets[f + 1] - beg;
-  if (len <= kWarpSortMax || len > kSortMax) return;  // short lists: csc_sort_warp_kernel
   if (len <= kRankSortMax) {
     // medium lists: rank sort -- every thread counts the entries smaller than its own (shared-memory broadcast
     // reads, one barrier) instead of ~50 barrier-separated bitonic stages
@@ -645,7 +686,7 @@ __global__ void __launch_bounds__(256) csc_sort_kernel(const int32_t* __restrict
       for (int j = 0; j < len; ++j) rank += buf[j] < v;
       entries[beg + rank] = v;
     }
-    return;
+    continue;
   }
   int m = 2;
   while (m < len) m <<= 1;
@@ -668,6 +709,7 @@ __global__ void __launch_bounds__(256) csc_sort_kernel(const int32_t* __restrict
     }
   }
   for (int i = threadIdx.x; i < len; i += blockDim.x) entries[beg + i] = buf[i];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ weight grads
@@ -1387,8 +1429,8 @@ extern "C" int freud_csc_build(const int32_t* top_idx, int64_t N, int64_t k, int
   csc_hist_kernel<<<grid, 256, 0, STREAM>>>(top_idx, total, offsets);
   csc_scan_kernel<<<1, 1024, 0, STREAM>>>(offsets, cursor, (int)n);
   csc_fill_kernel<<<grid, 256, 0, STREAM>>>(top_idx, total, cursor, entries);
-  csc_sort_warp_kernel<<<(int)((n + 7) / 8), 256, 0, STREAM>>>(offsets, entries, (int)n);
-  csc_sort_kernel<<<(int)n, 256, 0, STREAM>>>(offsets, entries);
+  csc_sort_warp_kernel<<<(int)((n + 7) / 8), 256, 0, STREAM>>>(offsets, entries, cursor, (int)n);
+  csc_sort_kernel<<<(int)std::min<int64_t>(n, sm_count() * 4), 256, 0, STREAM>>>(offsets, entries, cursor, (int)n);
   FREUD_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -353,7 +353,7 @@ def csc_build(top_idx: torch.Tensor, n: int):
     dev = top_idx.device
     offsets = torch.empty(n + 1, dtype=torch.int32, device=dev)
     entries = torch.empty(N * k, dtype=torch.int32, device=dev)
-    cursor = torch.empty(n, dtype=torch.int32, device=dev)
+    cursor = torch.empty(n + 1, dtype=torch.int32, device=dev)  # fill cursors, then the long-list sort queue + its counter
     call("freud_csc_build", _ptr(top_idx), N, k, n, _ptr(offsets), _ptr(entries), _ptr(cursor), _stream())
     return offsets, entries
 

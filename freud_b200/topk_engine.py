@@ -68,8 +68,7 @@ def aux_stream(device):
     key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
     s = _aux_streams.get(key)
     if s is None:
-        prio = -1 if os.environ.get("FREUD_CSC_MODE", "side") == "side_hi" else 0
-        s = _aux_streams[key] = torch.cuda.Stream(torch.device("cuda", key), priority=prio)
+        s = _aux_streams[key] = torch.cuda.Stream(torch.device("cuda", key))
     return s
 
 

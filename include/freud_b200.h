@@ -193,8 +193,9 @@ int freud_residual(const float* sae_out, const float* target, void* resid, int r
 /* ------------------------------------------------------------------ TopK SAE backward */
 
 /* Feature-major (CSC) index of the selected entries: offsets[f]..offsets[f+1] lists the flat positions
- * p = t*k + j with top_idx[p] == f.  offsets is int32 [n+1]; entries int32 [N*k]; cursor int32 [n]
- * workspace.  Also the did_fire bookkeeping of train_sae.py:442 (offsets[f+1] > offsets[f]). */
+ * p = t*k + j with top_idx[p] == f.  offsets is int32 [n+1]; entries int32 [N*k]; cursor int32 [n+1]
+ * workspace (fill cursors, then the queue of long lists for the sort pass and its counter).  Every list of up to 4096
+ * entries is token-ordered, so the gradient sums are run-to-run deterministic.  Also the did_fire bookkeeping of train_sae.py:442 (offsets[f+1] > offsets[f]). */
 int freud_csc_build(const int32_t* top_idx, int64_t N, int64_t k, int64_t n, int32_t* offsets,
                     int32_t* entries, int32_t* cursor, void* stream);
 
