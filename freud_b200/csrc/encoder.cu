@@ -104,6 +104,17 @@ static int launch_gemm(const void* a_hi, const void* a_lo, const void* b_hi, con
     mB1 = mB0;
   }
   p.passes = passes;
+  // output through TMA boxes when the output matrix qualifies (16-byte aligned rows; no split-K partial planes)
+  CUtensorMap mO = mA0;
+  p.tma_out = 0;
+  if (L::kHasOut && p.kb_per_split == 0 && !getenv("FREUD_NO_TMA_OUT")) {
+    if (EPI == EPI_STORE) {
+      if (p.out && (p.ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0)
+        p.tma_out = make_tensor_map_2d(&mO, p.out, p.M, p.N, p.ldo, 4, 32) == 0;
+    } else if (p.out16 && (p.ld16 & 7) == 0 && (reinterpret_cast<uintptr_t>(p.out16) & 15) == 0) {
+      p.tma_out = make_tensor_map_2d(&mO, p.out16, p.M, p.ld16, p.ld16, 2, 32) == 0;
+    }
+  }
   auto kern = sm100_gemm_kernel<BN, STAGES, EPI, TF32, SETS, CL, NBUF, CEV, AMN, BMN>;
   if (const char* e = getenv("FREUD_ENC_FLAGS")) p.flags = atoi(e);
   static bool attr_set = false;
@@ -157,7 +168,7 @@ static int launch_gemm(const void* a_hi, const void* a_lo, const void* b_hi, con
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  FREUD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, mA0, mA1, mB0, mB1, p));
+  FREUD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, mA0, mA1, mB0, mB1, mO, p));
   if (p.tail_split > 1) {
     const int row0 = p.full_count * kBM;
     topk_merge_pieces_kernel<<<(p.M - row0 + 7) / 8, 256, 0, stream>>>(p.part_vals, p.part_idx, p.part_stride, p.top_vals,
@@ -301,11 +312,11 @@ extern "C" int freud_gemm_nt(const void* a_hi, const void* a_lo, const void* b_h
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (precision == FREUD_BF16) {
     FREUD_REQUIRE(K % 8 == 0, "K must be a multiple of 8 for bf16 operands");
-    return launch_gemm<256, 4, EPI_STORE, false, 2, 1>(a_hi, nullptr, b_hi, nullptr, p, 1, s);
+    return launch_gemm<256, 3, EPI_STORE, false, 2, 1>(a_hi, nullptr, b_hi, nullptr, p, 1, s);
   }
   if (precision == FREUD_FP32) {
     FREUD_REQUIRE(K % 4 == 0, "K must be a multiple of 4 for fp32 operands");
-    return launch_gemm<256, 4, EPI_STORE, true, 2, 1>(a_hi, a_lo, b_hi, b_lo, p, 3, s);
+    return launch_gemm<256, 3, EPI_STORE, true, 2, 1>(a_hi, a_lo, b_hi, b_lo, p, 3, s);
   }
   FREUD_REQUIRE(false, "unknown precision");
 }
@@ -328,7 +339,7 @@ extern "C" int freud_gemm_nt_splitk(const void* a_hi, const void* b_hi, float* w
   FREUD_REQUIRE((total_kb + p.kb_per_split - 1) / p.kb_per_split == splits,
                 "splits must equal ceil(k_blocks / ceil(k_blocks / splits)) so that no partial is left unwritten");
   p.split_stride = M * N;
-  return launch_gemm<256, 4, EPI_STORE, false, 2, 1>(a_hi, nullptr, b_hi, nullptr, p, 1, static_cast<cudaStream_t>(stream));
+  return launch_gemm<256, 3, EPI_STORE, false, 2, 1>(a_hi, nullptr, b_hi, nullptr, p, 1, static_cast<cudaStream_t>(stream));
 }
 
 // Products whose operands are stored "the other way round" (MN-major operands, see sm100_gemm_kernel):
@@ -354,7 +365,7 @@ extern "C" int freud_gemm_tn_splitk(const void* a, const void* b, float* workspa
   FREUD_REQUIRE((total_kb + p.kb_per_split - 1) / p.kb_per_split == splits,
                 "splits must equal ceil(k_blocks / ceil(k_blocks / splits)) so that no partial is left unwritten");
   p.split_stride = M * N;
-  return launch_gemm<256, 4, EPI_STORE, false, 2, 1, 2, 0, true, true>(a, nullptr, b, nullptr, p, 1,
+  return launch_gemm<256, 3, EPI_STORE, false, 2, 1, 2, 0, true, true>(a, nullptr, b, nullptr, p, 1,
                                                                        static_cast<cudaStream_t>(stream));
 }
 
@@ -373,7 +384,7 @@ extern "C" int freud_gemm_nn(const void* a, const void* b, const float* bias, fl
   p.relu = relu;
   p.out = out;
   p.ldo = ldo;
-  return launch_gemm<256, 4, EPI_STORE, false, 2, 1, 2, 0, false, true>(a, nullptr, b, nullptr, p, 1,
+  return launch_gemm<256, 3, EPI_STORE, false, 2, 1, 2, 0, false, true>(a, nullptr, b, nullptr, p, 1,
                                                                         static_cast<cudaStream_t>(stream));
 }
 
@@ -394,7 +405,7 @@ extern "C" int freud_gemm_nt_mask(const void* a, const void* b, const void* act_
   p.ld16 = ld16;
   p.affine = affine;
   p.lda = lda;
-  return launch_gemm<256, 4, EPI_MASK, false, 2, 1>(a, nullptr, b, nullptr, p, 1, static_cast<cudaStream_t>(stream));
+  return launch_gemm<256, 3, EPI_MASK, false, 2, 1>(a, nullptr, b, nullptr, p, 1, static_cast<cudaStream_t>(stream));
 }
 
 // L1 SAE forward on bf16 operands (l1autoencoder.py:69-95):
@@ -419,7 +430,7 @@ extern "C" int freud_l1_encode_fused(const void* x_bf16, const void* wt_bf16, co
   p.out = latent;
   p.ldo = N;
   p.sums = sums;
-  return launch_gemm<256, 4, EPI_RELU16, false, 2, 1>(x_bf16, nullptr, wt_bf16, nullptr, p, 1,
+  return launch_gemm<256, 3, EPI_RELU16, false, 2, 1>(x_bf16, nullptr, wt_bf16, nullptr, p, 1,
                                                       static_cast<cudaStream_t>(stream));
 }
 
@@ -443,6 +454,6 @@ extern "C" int freud_l1_decode_fused(const void* c_bf16, const void* w_bf16, con
   p.out = x_hat;
   p.ldo = N;
   p.sums = sums;
-  return launch_gemm<256, 4, EPI_RESID, false, 2, 1>(c_bf16, nullptr, w_bf16, nullptr, p, 1,
+  return launch_gemm<256, 3, EPI_RESID, false, 2, 1>(c_bf16, nullptr, w_bf16, nullptr, p, 1,
                                                      static_cast<cudaStream_t>(stream));
 }

@@ -101,6 +101,11 @@ struct GemmParams {
   const float* target;            // EPI_RESID: fp32 [M, ldt]
   int64_t ldt;
   double* sums;                   // EPI_RELU16: [sum c]; EPI_RESID: [masked sse, count, sse]
+  // Output through TMA (set by the launcher when the output pitch allows it and there is no split-K): the epilogue
+  // warps stage 32-row x 128-byte boxes in swizzled shared memory and one lane issues a bulk tensor store per box --
+  // whole 128-byte lines instead of 32 half-written sectors per store instruction (fp32 out for EPI_STORE, the bf16
+  // out16 matrix for EPI_MASK / EPI_RELU16 / EPI_RESID)
+  int tma_out;
   int64_t lda, ldb;  // host side only: row pitch (elements) of the A / B matrix as stored; 0 = dense
   int flags;  // experiments (FREUD_ENC_FLAGS): bit 0 = do not share 16th-largest values between the epilogue sets;
               // bits 1-4 = bare spin (no sleep between polls) in the producer / MMA-empty / MMA-full / epilogue waits
@@ -120,13 +125,16 @@ struct GemmSmem {
   static constexpr int kBBytes = BN * kBKBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kRing = STAGES * kStageBytes;
+  static constexpr bool kHasOut = EPI == EPI_STORE || EPI == EPI_MASK || EPI == EPI_RELU16 || EPI == EPI_RESID;
+  static constexpr int kOutBox = 32 * 128;                              // 32 rows x 128 bytes
+  static constexpr int kStageOut = kHasOut ? kEpiWarps * 2 * kOutBox : 0;  // two boxes per epilogue warp, 1024-aligned
   static constexpr int kBufPerWarp = kNewSlots * kSlotStride;
   static constexpr int kBuf = EPI == EPI_TOPK ? kEpiWarps * kBufPerWarp : 0;
   static constexpr int kThr = 2 * kBM * 4 + 16;  // per-set published 16th-largest values
   static constexpr int kCols = BN / SETS;                   // columns of a tile one epilogue warp scans
   static constexpr int kBiasS = kEpiWarps * 2 * kCols * 4;  // staged bias rows: [epilogue warp][use parity][kCols]
   static constexpr int kBars = (2 * STAGES + 2 * NBUF) * 8 + 16;
-  static constexpr int kTotal = kRing + kBuf + kThr + kBiasS + kBars;
+  static constexpr int kTotal = kRing + kStageOut + kBuf + kThr + kBiasS + kBars;
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -244,7 +252,7 @@ template <int BN, int STAGES, int EPI, bool TF32, int SETS, int CL, int NBUF = 2
 __global__ void __launch_bounds__(128 + SETS * 128, 1)
 sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                   const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
-                  const GemmParams p) {
+                  const __grid_constant__ CUtensorMap mapO, const GemmParams p) {
   using L = GemmSmem<BN, STAGES, EPI, SETS, NBUF>;
   constexpr int kEpiWarps = L::kEpiWarps;
   constexpr uint16_t kMcMask = static_cast<uint16_t>((1u << CL) - 1u);
@@ -259,15 +267,17 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* ring = smem;
-  uint8_t* cand = smem + L::kRing;
-  float* thr_s = reinterpret_cast<float*>(smem + L::kRing + L::kBuf);
-  float* bias_s = reinterpret_cast<float*>(smem + L::kRing + L::kBuf + L::kThr);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kRing + L::kBuf + L::kThr + L::kBiasS);
+  uint8_t* stage_out = smem + L::kRing;
+  uint8_t* cand = smem + L::kRing + L::kStageOut;
+  float* thr_s = reinterpret_cast<float*>(smem + L::kRing + L::kStageOut + L::kBuf);
+  float* bias_s = reinterpret_cast<float*>(smem + L::kRing + L::kStageOut + L::kBuf + L::kThr);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kRing + L::kStageOut + L::kBuf + L::kThr + L::kBiasS);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tfull_bar = bars + 2 * STAGES;
   uint64_t* tempty_bar = bars + 2 * STAGES + NBUF;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * NBUF);
+  int* tile_ctr = reinterpret_cast<int*>(tmem_slot + 1);  // tiles the MMA issuer has started (read by the prefetch warp)
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -321,6 +331,7 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     tmem_relinquish();
   }
   if (threadIdx.x < 2 * kBM) thr_s[threadIdx.x] = 0.f;  // published per-set 16th-largest values start at the ReLU floor
+  if (threadIdx.x == 0) *tile_ctr = -1;
   tc_fence_before();
   __syncthreads();
   if constexpr (CL > 1) cluster_sync_all();  // peers' barriers are initialised before anyone signals them
@@ -385,6 +396,7 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         if (p.flags & 4) mbar_wait(&tempty_bar[buf], ((lt / NBUF) & 1) ^ 1);
         else mbar_wait_relaxed(&tempty_bar[buf], ((lt / NBUF) & 1) ^ 1, 32);
         tc_fence_after();
+        if constexpr (EPI == EPI_RESID || EPI == EPI_MASK) *reinterpret_cast<volatile int*>(tile_ctr) = lt;
         const uint32_t d_tmem = tmem_base + buf * BN;
         for (int vk = 0; vk < num_vk; ++vk) {
           if (p.flags & 8) mbar_wait(&full_bar[stage], phase);
@@ -415,6 +427,43 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         tc_commit(&tfull_bar[buf]);
       }
     }
+  } else if (warp_idx == 3) {
+    // ===================== epilogue-input prefetcher (EPI_RESID / EPI_MASK) =====================
+    // The epilogue threads read their OWN rows of the target / mask matrix (16-byte pieces, 32 rows per request):
+    // latency-bound at DRAM distance (ncu: long_scoreboard, 18 % warps active).  This otherwise idle warp pulls the
+    // NEXT tile's rows into L2 with bulk prefetches while the current tile is computed and drained.
+    if constexpr (EPI == EPI_RESID || EPI == EPI_MASK) {
+      const uint8_t* base = EPI == EPI_RESID ? reinterpret_cast<const uint8_t*>(p.target)
+                                             : reinterpret_cast<const uint8_t*>(p.mask_src);
+      const int64_t pitch = EPI == EPI_RESID ? p.ldt * 4 : p.ld16 * 2;  // bytes
+      const int esz = EPI == EPI_RESID ? 4 : 2;
+      const int64_t row_cols = EPI == EPI_RESID ? p.N : p.ld16;          // readable columns of a row
+      const bool ok = (pitch & 15) == 0 && ((row_cols * esz) & 15) == 0;
+      for (int lt = 0; ok && lt < num_lt; ++lt) {
+        // tile lt's rows are requested once the MMA issuer has reached tile lt - 1.  Paced by a monotone counter, not
+        // by the accumulator barriers: a waiter that falls two phases behind a parity barrier would wait for a
+        // completion that never comes at the end of the run.
+        if (lt > 0) {
+          uint32_t spins = 0;
+          while (*reinterpret_cast<volatile int*>(tile_ctr) < lt - 1) {
+            asm volatile("nanosleep.u32 %0;" ::"r"(200u));
+            if (++spins > (1u << 22)) __trap();
+          }
+        }
+        const int mb = static_cast<int>((g_begin + lt) / num_nt);
+        const int nt = static_cast<int>(g_begin + lt - static_cast<int64_t>(mb) * num_nt);
+        const int64_t c0 = static_cast<int64_t>(nt) * BN;
+        const int64_t cols = min(static_cast<int64_t>(BN), row_cols - c0);
+        if (cols <= 0) continue;
+        const uint32_t bytes = static_cast<uint32_t>(cols * esz) & ~15u;
+        for (int r = lane; r < kBM; r += 32) {
+          const int64_t row = static_cast<int64_t>(mb) * kBM + r;
+          if (row < p.M && bytes > 0)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + row * pitch + c0 * esz), "r"(bytes)
+                         : "memory");
+        }
+      }
+    }
   } else if (warp_idx >= 4) {
     // ===================== epilogue =====================
     const int q = warp_idx & 3;  // TMEM lane quarter
@@ -431,6 +480,7 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     constexpr int kCols = L::kCols;            // this warp scans columns [cb, cb + kCols) of every tile
     constexpr int kPerLane = kCols / 32;       // bias columns a lane stages
     static_assert(kCols % 32 == 0 && kPerLane <= 8 && kPerLane % 4 == 0, "bias staging layout");
+    static_assert(!L::kHasOut || kCols % 64 == 0, "output boxes are 32 fp32 / 64 bf16 columns wide");
     const int cb = set * kCols;
     float* bias_w = bias_s + ew * (2 * kCols);
     float nb[kPerLane];
@@ -448,6 +498,27 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       for (int j = 0; j < kPerLane; j += 4) dst[j / 4] = make_float4(nb[j], nb[j + 1], nb[j + 2], nb[j + 3]);
     };
 
+    // TMA output staging of this warp: two 32 x 128-byte boxes, SWIZZLE_128B (16-byte piece pc of row r sits at
+    // r * 128 + ((pc ^ (r & 7)) * 16): conflict-free for the row-per-lane writes, undone by the tensor map)
+    const bool tma_out = L::kHasOut && p.tma_out != 0;
+    uint8_t* my_stage = stage_out + ew * (2 * L::kOutBox);
+    int sbuf = 0;
+    auto stage_piece = [&](int pc, uint4 v4) {
+      *reinterpret_cast<uint4*>(my_stage + sbuf * L::kOutBox + lane * 128 + ((pc ^ (lane & 7)) << 4)) = v4;
+    };
+    auto stage_begin = [&]() {  // the box about to be written must have been read by the store issued two boxes ago
+      if (lane == 0) bulk_wait_group_read<1>();
+      __syncwarp();
+    };
+    auto stage_flush = [&](int col, int row0) {
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&mapO, my_stage + sbuf * L::kOutBox, col, row0);
+        bulk_commit_group();
+      }
+      sbuf ^= 1;
+    };
     double acc_sum[3] = {0.0, 0.0, 0.0};  // EPI_RELU16 / EPI_RESID running sums of this thread's rows
     float aff_scale = 1.f, aff_shift = 0.f;
     if constexpr (EPI == EPI_MASK) {
@@ -514,6 +585,39 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       tc_fence_after();
       const uint32_t t_addr = lane_taddr + buf * BN + cb;
       uint32_t r[2][kChunk];
+      // epilogue inputs of a chunk (EPI_RESID: 16 fp32 targets; EPI_MASK: 16 bf16 gate activations) are requested one
+      // chunk ahead, like the TMEM loads, so their latency overlaps the previous chunk's arithmetic and stores
+      float xin[2][EPI == EPI_RESID ? kChunk : 1];
+      uint4 gin[2][EPI == EPI_MASK ? 2 : 1];
+      const int64_t tile_col0 = static_cast<int64_t>(nt) * BN + cb;
+      auto load_inputs = [&](int cc, int slot) {
+        if constexpr (EPI == EPI_RESID) {
+          const int64_t col0 = tile_col0 + cc;
+          if (row < p.M) {
+            const float* trow = p.target + static_cast<int64_t>(row) * p.ldt + col0;
+            if (col0 + kChunk <= p.N && (p.ldt & 3) == 0) {
+#pragma unroll
+              for (int j = 0; j < kChunk; j += 4) {
+                const float4 t4 = __ldg(reinterpret_cast<const float4*>(trow + j));
+                xin[slot][j] = t4.x; xin[slot][j + 1] = t4.y; xin[slot][j + 2] = t4.z; xin[slot][j + 3] = t4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < kChunk; ++j) xin[slot][j] = col0 + j < p.N ? __ldg(trow + j) : 0.f;
+            }
+          }
+        } else if constexpr (EPI == EPI_MASK) {
+          const int64_t col0 = tile_col0 + cc;
+          if (row < p.M) {
+#pragma unroll
+            for (int h8 = 0; h8 < 2; ++h8)
+              if (col0 + h8 * 8 < p.ld16)
+                gin[slot][h8] = __ldg(reinterpret_cast<const uint4*>(p.mask_src + static_cast<int64_t>(row) * p.ld16 +
+                                                                     col0 + h8 * 8));
+          }
+        }
+      };
+      load_inputs(0, 0);
       tmem_ld_32x32b_x16(t_addr, r[0]);
 #pragma unroll 1
       for (int c0 = 0; c0 < kCols; c0 += 2 * kChunk) {
@@ -523,6 +627,7 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           tmem_ld_wait();
           if (cc + kChunk < kCols) {
             tmem_ld_32x32b_x16(t_addr + cc + kChunk, r[h ^ 1]);  // prefetch the next chunk
+            load_inputs(cc + kChunk, h ^ 1);
           } else {
             // this warp's columns now sit in registers: hand the buffer back to the MMA issuer before scanning the rest
             tc_fence_before();
@@ -573,52 +678,24 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             }
           } else if constexpr (EPI == EPI_NONE) {
             if (v[0] == 1.2345e38f) p.out[0] = 1.f;  // keep the loads alive
-          } else if constexpr (EPI == EPI_RELU16) {
-            if (row < p.M) {
-              const int64_t col0 = static_cast<int64_t>(nt) * BN + cb + cc;
+          } else if constexpr (EPI == EPI_RELU16 || EPI == EPI_RESID || EPI == EPI_MASK) {
+            // three epilogues with a bf16 output row [M, ld16]: o[j] = the chunk's 16 output values
+            const bool rv = row < p.M;
+            const int64_t col0 = static_cast<int64_t>(nt) * BN + cb + cc;
+            float o[kChunk];
+            if constexpr (EPI == EPI_RELU16) {
 #pragma unroll
               for (int j = 0; j < kChunk; ++j) {
                 v[j] = fmaxf(v[j], 0.f);  // columns past N carry a -inf bias: they come out as 0
-                acc_sum[0] += v[j];
+                o[j] = v[j];
+                if (rv) acc_sum[0] += v[j];
               }
-#pragma unroll
-              for (int h8 = 0; h8 < kChunk; h8 += 8) {
-                if (col0 + h8 < p.ld16) {
-                  uint4 q;
-                  uint32_t* qw = reinterpret_cast<uint32_t*>(&q);
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const __nv_bfloat162 h = __floats2bfloat162_rn(v[h8 + 2 * j], v[h8 + 2 * j + 1]);
-                    qw[j] = *reinterpret_cast<const uint32_t*>(&h);
-                  }
-                  *reinterpret_cast<uint4*>(p.out16 + static_cast<int64_t>(row) * p.ld16 + col0 + h8) = q;
-                }
-              }
-              if (p.out != nullptr) {
-#pragma unroll
-                for (int j = 0; j < kChunk; ++j)
-                  if (col0 + j < p.N) p.out[static_cast<int64_t>(row) * p.ldo + col0 + j] = v[j];
-              }
-            }
-          } else if constexpr (EPI == EPI_RESID) {
-            if (row < p.M) {
-              const int64_t col0 = static_cast<int64_t>(nt) * BN + cb + cc;
-              float e[kChunk], xt[kChunk];
-              const float* trow = p.target + static_cast<int64_t>(row) * p.ldt + col0;
-              if (col0 + kChunk <= p.N && (p.ldt & 3) == 0) {  // 16-byte loads: 4 per chunk instead of 16 scalar ones
-#pragma unroll
-                for (int j = 0; j < kChunk; j += 4) {
-                  const float4 t4 = __ldg(reinterpret_cast<const float4*>(trow + j));
-                  xt[j] = t4.x; xt[j + 1] = t4.y; xt[j + 2] = t4.z; xt[j + 3] = t4.w;
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < kChunk; ++j) xt[j] = col0 + j < p.N ? __ldg(trow + j) : 0.f;
-              }
+            } else if constexpr (EPI == EPI_RESID) {
+              const float (&xt)[kChunk] = xin[h];
 #pragma unroll
               for (int j = 0; j < kChunk; ++j) {
                 float ev = 0.f;
-                if (col0 + j < p.N) {
+                if (rv && col0 + j < p.N) {
                   const float xv = xt[j];
                   const float d0 = v[j] - xv;
                   const float d2 = d0 * d0;
@@ -629,55 +706,71 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                     ev = d0;
                   }
                 }
-                e[j] = ev;
+                o[j] = ev;
               }
+            } else {
 #pragma unroll
               for (int h8 = 0; h8 < kChunk; h8 += 8) {
-                if (col0 + h8 < p.ld16) {
-                  uint4 q;
-                  uint32_t* qw = reinterpret_cast<uint32_t*>(&q);
+                const uint4 a8 = (rv && col0 + h8 < p.ld16) ? gin[h][h8 / 8] : make_uint4(0, 0, 0, 0);
+                const uint32_t aw[4] = {a8.x, a8.y, a8.z, a8.w};
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const __nv_bfloat162 h = __floats2bfloat162_rn(e[h8 + 2 * j], e[h8 + 2 * j + 1]);
-                    qw[j] = *reinterpret_cast<const uint32_t*>(&h);
-                  }
-                  *reinterpret_cast<uint4*>(p.out16 + static_cast<int64_t>(row) * p.ld16 + col0 + h8) = q;
+                for (int j = 0; j < 4; ++j) {
+                  // bf16 > 0  <=>  sign clear and not zero
+                  const bool p0 = (aw[j] & 0x8000u) == 0 && (aw[j] & 0x7fffu) != 0;
+                  const bool p1 = (aw[j] & 0x80000000u) == 0 && (aw[j] & 0x7fff0000u) != 0;
+                  o[h8 + 2 * j] = p0 ? fmaf(aff_scale, v[h8 + 2 * j], aff_shift) : 0.f;
+                  o[h8 + 2 * j + 1] = p1 ? fmaf(aff_scale, v[h8 + 2 * j + 1], aff_shift) : 0.f;
                 }
               }
-              if (p.out != nullptr) {
+            }
+            const int grp = (cc / kChunk) & 3;  // chunk within the 64-column (128-byte) output box
+#pragma unroll
+            for (int h8 = 0; h8 < kChunk; h8 += 8) {
+              uint4 q;
+              uint32_t* qw = reinterpret_cast<uint32_t*>(&q);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const __nv_bfloat162 hh = __floats2bfloat162_rn(o[h8 + 2 * j], o[h8 + 2 * j + 1]);
+                qw[j] = *reinterpret_cast<const uint32_t*>(&hh);
+              }
+              if (tma_out) {
+                if (grp == 0 && h8 == 0) stage_begin();
+                stage_piece(grp * 2 + h8 / 8, q);
+              } else if (rv && col0 + h8 < p.ld16) {  // ld16 % 8 == 0: a group of 8 is inside the pitch or outside
+                *reinterpret_cast<uint4*>(p.out16 + static_cast<int64_t>(row) * p.ld16 + col0 + h8) = q;
+              }
+            }
+            if (tma_out && grp == 3)
+              stage_flush(static_cast<int>(col0) - 3 * kChunk, mb * kBM + q * 32);
+            if constexpr (EPI != EPI_MASK) {
+              if (rv && p.out != nullptr) {  // optional fp32 copy (module API); the trainer does not ask for it
 #pragma unroll
                 for (int j = 0; j < kChunk; ++j)
                   if (col0 + j < p.N) p.out[static_cast<int64_t>(row) * p.ldo + col0 + j] = v[j];
               }
             }
-          } else if constexpr (EPI == EPI_MASK) {
-            if (row < p.M) {
-              const int64_t col0 = static_cast<int64_t>(nt) * BN + cb + cc;
-#pragma unroll
-              for (int h8 = 0; h8 < kChunk; h8 += 8) {
-                if (col0 + h8 < p.ld16) {  // ld16 % 8 == 0: a group of 8 is either inside the pitch or outside
-                  const int64_t o = static_cast<int64_t>(row) * p.ld16 + col0 + h8;
-                  const uint4 a8 = __ldg(reinterpret_cast<const uint4*>(p.mask_src + o));
-                  const uint32_t aw[4] = {a8.x, a8.y, a8.z, a8.w};
-                  uint4 q;
-                  uint32_t* qw = reinterpret_cast<uint32_t*>(&q);
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    // bf16 > 0  <=>  sign clear and not zero
-                    const bool p0 = (aw[j] & 0x8000u) == 0 && (aw[j] & 0x7fffu) != 0;
-                    const bool p1 = (aw[j] & 0x80000000u) == 0 && (aw[j] & 0x7fff0000u) != 0;
-                    const __nv_bfloat162 h = __floats2bfloat162_rn(p0 ? fmaf(aff_scale, v[h8 + 2 * j], aff_shift) : 0.f,
-                                                                   p1 ? fmaf(aff_scale, v[h8 + 2 * j + 1], aff_shift) : 0.f);
-                    qw[j] = *reinterpret_cast<const uint32_t*>(&h);
-                  }
-                  *reinterpret_cast<uint4*>(p.out16 + o) = q;
-                }
-              }
-            }
           } else {
-            if (row < p.M) {
-              float* orow = p.out + split * p.split_stride + static_cast<int64_t>(row) * p.ldo + nt * BN + cb + cc;
-              const bool full_chunk = (nt * BN + cb + cc + kChunk <= p.N) && ((p.ldo & 3) == 0);
+            const bool rv = row < p.M;
+            const int64_t col0 = static_cast<int64_t>(nt) * BN + cb + cc;
+            if (tma_out) {
+              const int grp = (cc / kChunk) & 1;  // chunk within the 32-column (128-byte) output box
+              if (grp == 0) stage_begin();
+#pragma unroll
+              for (int j = 0; j < kChunk; j += 4) {
+                float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                if (p.relu) {
+                  o.x = fmaxf(o.x, 0.f);
+                  o.y = fmaxf(o.y, 0.f);
+                  o.z = fmaxf(o.z, 0.f);
+                  o.w = fmaxf(o.w, 0.f);
+                }
+                stage_piece(grp * 4 + j / 4, make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z),
+                                                        __float_as_uint(o.w)));
+              }
+              if (grp == 1) stage_flush(static_cast<int>(col0) - kChunk, mb * kBM + q * 32);
+            } else if (rv) {
+              float* orow = p.out + split * p.split_stride + static_cast<int64_t>(row) * p.ldo + col0;
+              const bool full_chunk = (col0 + kChunk <= p.N) && ((p.ldo & 3) == 0);
               if (full_chunk) {
 #pragma unroll
                 for (int j = 0; j < kChunk; j += 4) {
@@ -693,7 +786,7 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
               } else {
 #pragma unroll
                 for (int j = 0; j < kChunk; ++j) {
-                  if (nt * BN + cb + cc + j < p.N) {
+                  if (col0 + j < p.N) {
                     float o = v[j];
                     if (p.relu) o = fmaxf(o, 0.f);
                     orow[j] = o;
@@ -786,6 +879,7 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     }
       lt0 = seg_end;
     }
+    if (tma_out && lane == 0) bulk_wait_group_read<0>();  // the boxes must outlive the stores that read them
     if constexpr (EPI == EPI_RELU16 || EPI == EPI_RESID) {
       constexpr int kSums = EPI == EPI_RELU16 ? 1 : 3;
 #pragma unroll

@@ -627,7 +627,7 @@ __global__ void __launch_bounds__(256) csc_fill_kernel(const int32_t* __restrict
 // shared memory; lists longer than kSortMax entries are left in fill order (still correct, not bit-stable).
 constexpr int kSortMax = 4096;
 constexpr int kWarpSortMax = 128;
-constexpr int kRankSortMax = 256;  // O(len^2 / 256) per thread: beyond this the bitonic network wins
+constexpr int kRankSortMax = 1024;  // O(len^2 / 256) per thread (4096 compares at 1024): beyond this the bitonic network wins
 
 // Lists of up to 128 entries (the common case: N*k/n on average): one warp per feature, 4 entries per lane, rank
 // sort by shuffle broadcast (entries are distinct positions, so rank = number of smaller entries).
