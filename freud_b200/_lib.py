@@ -29,7 +29,7 @@ _p, _i64, _i, _f, _d = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_double
 
 # name -> argtypes, exactly the prototypes of include/freud_b200.h
 SIGNATURES = {
-    "freud_topk_prep_x": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i, _p],
+    "freud_topk_prep_x": [_p, _i, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i, _p],
     "freud_split_operand": [_p, _p, _p, _i64, _i, _p],
     "freud_topk_encode_workspace": [_i64, _i64, _p],
     "freud_topk_encode": [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i, _p, _i64, _p],
@@ -52,7 +52,7 @@ SIGNATURES = {
     "freud_topk_decode": [_p, _p, _p, _i, _p, _p, _p, _p, _i, _p, _p, _i64, _i64, _i64, _p],
     "freud_topk_dacts": [_p, _i, _p, _p, _i, _p, _i64, _i64, _i64, _p],
     "freud_topk_decode_dacts_supported": [_i64, _i64],
-    "freud_topk_decode_dacts": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _p],
+    "freud_topk_decode_dacts": [_p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _i64, _i64, _i64, _p],
     "freud_topk_refine": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _p],
     "freud_axpby": [_p, _p, _p, _p, _i, _i64, _p],
     "freud_shard_merge": [_p, _p, _p, _p, _i64, _i64, _i64, _p],

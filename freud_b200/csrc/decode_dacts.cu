@@ -52,11 +52,11 @@ struct DecodeDactsCfg {
   static constexpr size_t kSmem = kRows + TOK * 8 + D * 4 + 32 * 8;
 };
 
-template <int D, int PARTS, int TOK>
+template <int D, int PARTS, int TOK, typename XT>
 __global__ void __launch_bounds__(32 * TOK, 1)
 decode_dacts_kernel(const float* __restrict__ top_vals, const int32_t* __restrict__ top_idx,
                     const __nv_bfloat16* __restrict__ W, const float* __restrict__ b_dec,
-                    const float* __restrict__ target, float* __restrict__ sae_out,
+                    const XT* __restrict__ target, float* __restrict__ sae_out,
                     __nv_bfloat16* __restrict__ resid, double* __restrict__ sse, float* __restrict__ colsum,
                     float* __restrict__ dacts, int64_t N) {
   using Cfg = DecodeDactsCfg<D, PARTS, TOK>;
@@ -207,12 +207,12 @@ decode_dacts_kernel(const float* __restrict__ top_vals, const int32_t* __restric
   if (threadIdx.x == 0) atomicAdd(sse, tot);
 }
 
-template <int D, int PARTS, int TOK>
-static int launch_decode_dacts(const float* tv, const int32_t* ti, const void* W, const float* b_dec,
-                               const float* target, float* sae_out, void* resid, double* sse, float* colsum,
-                               float* dacts, int64_t N, cudaStream_t s) {
+template <int D, int PARTS, int TOK, typename XT>
+static int launch_decode_dacts_t(const float* tv, const int32_t* ti, const void* W, const float* b_dec,
+                                 const void* target, float* sae_out, void* resid, double* sse, float* colsum,
+                                 float* dacts, int64_t N, cudaStream_t s) {
   using Cfg = DecodeDactsCfg<D, PARTS, TOK>;
-  auto kern = decode_dacts_kernel<D, PARTS, TOK>;
+  auto kern = decode_dacts_kernel<D, PARTS, TOK, XT>;
   static bool configured = false;
   if (!configured) {
     FREUD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
@@ -220,11 +220,22 @@ static int launch_decode_dacts(const float* tv, const int32_t* ti, const void* W
   }
   int64_t grid = (N + TOK - 1) / TOK;
   if (grid > sm_count()) grid = sm_count();
-  kern<<<(int)grid, Cfg::kThreads, Cfg::kSmem, s>>>(tv, ti, static_cast<const __nv_bfloat16*>(W), b_dec, target,
-                                                      sae_out, static_cast<__nv_bfloat16*>(resid), sse, colsum, dacts,
-                                                      N);
+  kern<<<(int)grid, Cfg::kThreads, Cfg::kSmem, s>>>(tv, ti, static_cast<const __nv_bfloat16*>(W), b_dec,
+                                                      static_cast<const XT*>(target), sae_out,
+                                                      static_cast<__nv_bfloat16*>(resid), sse, colsum, dacts, N);
   FREUD_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+template <int D, int PARTS, int TOK>
+static int launch_decode_dacts(const float* tv, const int32_t* ti, const void* W, const float* b_dec,
+                               const void* target, int target_dtype, float* sae_out, void* resid, double* sse,
+                               float* colsum, float* dacts, int64_t N, cudaStream_t s) {
+  if (target_dtype == 1)
+    return launch_decode_dacts_t<D, PARTS, TOK, __half>(tv, ti, W, b_dec, target, sae_out, resid, sse, colsum, dacts, N, s);
+  if (target_dtype == 2)
+    return launch_decode_dacts_t<D, PARTS, TOK, __nv_bfloat16>(tv, ti, W, b_dec, target, sae_out, resid, sse, colsum, dacts, N, s);
+  return launch_decode_dacts_t<D, PARTS, TOK, float>(tv, ti, W, b_dec, target, sae_out, resid, sse, colsum, dacts, N, s);
 }
 
 }  // namespace freud
@@ -236,18 +247,19 @@ extern "C" int freud_topk_decode_dacts_supported(int64_t d, int64_t k) {
 }
 
 extern "C" int freud_topk_decode_dacts(const float* top_vals, const int32_t* top_idx, const void* W_dec_bf16,
-                                       const float* b_dec, const float* target, float* sae_out, void* resid_bf16,
-                                       double* sse, float* colsum, float* dacts, int64_t N, int64_t d, int64_t k,
-                                       void* stream) {
+                                       const float* b_dec, const void* target, int target_dtype, float* sae_out,
+                                       void* resid_bf16, double* sse, float* colsum, float* dacts, int64_t N, int64_t d,
+                                       int64_t k, void* stream) {
   FREUD_REQUIRE(N > 0 && freud_topk_decode_dacts_supported(d, k),
                 "fused decode + dacts needs k == 32 and d in {384, 512, 768, 1024, 1280}");
   FREUD_REQUIRE(target && sae_out && resid_bf16 && sse && colsum && dacts, "all outputs are required");
+  FREUD_REQUIRE(target_dtype >= 0 && target_dtype <= 2, "target_dtype: 0 fp32, 1 fp16, 2 bf16");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (d) {
-    case 384: return launch_decode_dacts<384, 1, 8>(top_vals, top_idx, W_dec_bf16, b_dec, target, sae_out, resid_bf16, sse, colsum, dacts, N, s);
-    case 512: return launch_decode_dacts<512, 1, 6>(top_vals, top_idx, W_dec_bf16, b_dec, target, sae_out, resid_bf16, sse, colsum, dacts, N, s);
-    case 768: return launch_decode_dacts<768, 2, 8>(top_vals, top_idx, W_dec_bf16, b_dec, target, sae_out, resid_bf16, sse, colsum, dacts, N, s);
-    case 1024: return launch_decode_dacts<1024, 2, 6>(top_vals, top_idx, W_dec_bf16, b_dec, target, sae_out, resid_bf16, sse, colsum, dacts, N, s);
-    default: return launch_decode_dacts<1280, 2, 5>(top_vals, top_idx, W_dec_bf16, b_dec, target, sae_out, resid_bf16, sse, colsum, dacts, N, s);
+    case 384: return launch_decode_dacts<384, 1, 8>(top_vals, top_idx, W_dec_bf16, b_dec, target, target_dtype, sae_out, resid_bf16, sse, colsum, dacts, N, s);
+    case 512: return launch_decode_dacts<512, 1, 6>(top_vals, top_idx, W_dec_bf16, b_dec, target, target_dtype, sae_out, resid_bf16, sse, colsum, dacts, N, s);
+    case 768: return launch_decode_dacts<768, 2, 8>(top_vals, top_idx, W_dec_bf16, b_dec, target, target_dtype, sae_out, resid_bf16, sse, colsum, dacts, N, s);
+    case 1024: return launch_decode_dacts<1024, 2, 6>(top_vals, top_idx, W_dec_bf16, b_dec, target, target_dtype, sae_out, resid_bf16, sse, colsum, dacts, N, s);
+    default: return launch_decode_dacts<1280, 2, 5>(top_vals, top_idx, W_dec_bf16, b_dec, target, target_dtype, sae_out, resid_bf16, sse, colsum, dacts, N, s);
   }
 }

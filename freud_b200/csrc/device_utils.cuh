@@ -1,6 +1,7 @@
 // Small device helpers shared by the bandwidth-bound kernels.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 
@@ -57,6 +58,12 @@ __device__ __forceinline__ float4 load4(const __nv_bfloat16* p) {
   const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
   return make_float4(fa.x, fa.y, fb.x, fb.y);
 }
+__device__ __forceinline__ float4 load4(const __half* p) {
+  const uint2 raw = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 fa = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+  const float2 fb = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
 __device__ __forceinline__ void store4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ void store4(__nv_bfloat16* p, float4 v) {
   const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
@@ -92,6 +99,17 @@ __device__ __forceinline__ void store4_stream(__nv_bfloat16* p, float4 v) {
   __stcs(reinterpret_cast<uint2*>(p), raw);
 }
 __device__ __forceinline__ float4 load4_stream(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 load4_stream(const __half* p) {
+  const uint2 raw = __ldcs(reinterpret_cast<const uint2*>(p));
+  const float2 fa = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+  const float2 fb = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+__device__ __forceinline__ float4 load4_stream(const __nv_bfloat16* p) {
+  const uint2 raw = __ldcs(reinterpret_cast<const uint2*>(p));
+  return make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u), __uint_as_float(raw.y << 16),
+                     __uint_as_float(raw.y & 0xffff0000u));
+}
 
 __device__ __forceinline__ float to_tf32(float x) {
   uint32_t r;

@@ -115,6 +115,17 @@ static int launch_gemm(const void* a_hi, const void* a_lo, const void* b_hi, con
       p.tma_out = make_tensor_map_2d(&mO, p.out16, p.M, p.ld16, p.ld16, 2, 32) == 0;
     }
   }
+  // EPI_RESID / EPI_MASK: the matrix the epilogue reads row-per-thread arrives as TMA boxes too
+  CUtensorMap mI = mA0;
+  p.tma_in = 0;
+  if (L::kHasIn && p.tma_out && !getenv("FREUD_NO_TMA_IN")) {
+    if (EPI == EPI_RESID) {
+      if (p.target && (p.ldt & 3) == 0 && (reinterpret_cast<uintptr_t>(p.target) & 15) == 0)
+        p.tma_in = make_tensor_map_2d(&mI, p.target, p.M, p.N, p.ldt, 4, 32) == 0;
+    } else if (p.mask_src && (reinterpret_cast<uintptr_t>(p.mask_src) & 15) == 0) {
+      p.tma_in = make_tensor_map_2d(&mI, p.mask_src, p.M, p.ld16, p.ld16, 2, 32) == 0;
+    }
+  }
   auto kern = sm100_gemm_kernel<BN, STAGES, EPI, TF32, SETS, CL, NBUF, CEV, AMN, BMN>;
   if (const char* e = getenv("FREUD_ENC_FLAGS")) p.flags = atoi(e);
   static bool attr_set = false;
@@ -168,7 +179,7 @@ static int launch_gemm(const void* a_hi, const void* a_lo, const void* b_hi, con
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  FREUD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, mA0, mA1, mB0, mB1, mO, p));
+  FREUD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, mA0, mA1, mB0, mB1, mO, mI, p));
   if (p.tail_split > 1) {
     const int row0 = p.full_count * kBM;
     topk_merge_pieces_kernel<<<(p.M - row0 + 7) / 8, 256, 0, stream>>>(p.part_vals, p.part_idx, p.part_stride, p.top_vals,
@@ -405,7 +416,7 @@ extern "C" int freud_gemm_nt_mask(const void* a, const void* b, const void* act_
   p.ld16 = ld16;
   p.affine = affine;
   p.lda = lda;
-  return launch_gemm<256, 3, EPI_MASK, false, 2, 1>(a, nullptr, b, nullptr, p, 1, static_cast<cudaStream_t>(stream));
+  return launch_gemm<256, 2, EPI_MASK, false, 2, 1>(a, nullptr, b, nullptr, p, 1, static_cast<cudaStream_t>(stream));
 }
 
 // L1 SAE forward on bf16 operands (l1autoencoder.py:69-95):
@@ -454,6 +465,6 @@ extern "C" int freud_l1_decode_fused(const void* c_bf16, const void* w_bf16, con
   p.out = x_hat;
   p.ldo = N;
   p.sums = sums;
-  return launch_gemm<256, 3, EPI_RESID, false, 2, 1>(c_bf16, nullptr, w_bf16, nullptr, p, 1,
+  return launch_gemm<256, 2, EPI_RESID, false, 2, 1>(c_bf16, nullptr, w_bf16, nullptr, p, 1,
                                                      static_cast<cudaStream_t>(stream));
 }

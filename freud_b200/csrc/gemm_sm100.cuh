@@ -106,6 +106,7 @@ struct GemmParams {
   // whole 128-byte lines instead of 32 half-written sectors per store instruction (fp32 out for EPI_STORE, the bf16
   // out16 matrix for EPI_MASK / EPI_RELU16 / EPI_RESID)
   int tma_out;
+  int tma_in;   // EPI_RESID target / EPI_MASK mask_src arrive as TMA boxes (needs tma_out: the smem budget assumes both)
   int64_t lda, ldb;  // host side only: row pitch (elements) of the A / B matrix as stored; 0 = dense
   int flags;  // experiments (FREUD_ENC_FLAGS): bit 0 = do not share 16th-largest values between the epilogue sets;
               // bits 1-4 = bare spin (no sleep between polls) in the producer / MMA-empty / MMA-full / epilogue waits
@@ -127,14 +128,19 @@ struct GemmSmem {
   static constexpr int kRing = STAGES * kStageBytes;
   static constexpr bool kHasOut = EPI == EPI_STORE || EPI == EPI_MASK || EPI == EPI_RELU16 || EPI == EPI_RESID;
   static constexpr int kOutBox = 32 * 128;                              // 32 rows x 128 bytes
-  static constexpr int kStageOut = kHasOut ? kEpiWarps * 2 * kOutBox : 0;  // two boxes per epilogue warp, 1024-aligned
+  // EPI_RESID / EPI_MASK also READ a matrix row-per-thread (target / gate activations): those boxes come in by TMA as
+  // well (two per epilogue warp, fetched one box ahead), and the output then gets by with one box per warp
+  static constexpr bool kHasIn = EPI == EPI_RESID || EPI == EPI_MASK;
+  static constexpr int kOutBufs = kHasIn ? 1 : 2;
+  static constexpr int kStageOut = kHasOut ? kEpiWarps * kOutBufs * kOutBox : 0;  // boxes are 1024-byte aligned
+  static constexpr int kStageIn = kHasIn ? kEpiWarps * 2 * kOutBox : 0;
   static constexpr int kBufPerWarp = kNewSlots * kSlotStride;
   static constexpr int kBuf = EPI == EPI_TOPK ? kEpiWarps * kBufPerWarp : 0;
   static constexpr int kThr = 2 * kBM * 4 + 16;  // per-set published 16th-largest values
   static constexpr int kCols = BN / SETS;                   // columns of a tile one epilogue warp scans
   static constexpr int kBiasS = kEpiWarps * 2 * kCols * 4;  // staged bias rows: [epilogue warp][use parity][kCols]
-  static constexpr int kBars = (2 * STAGES + 2 * NBUF) * 8 + 16;
-  static constexpr int kTotal = kRing + kStageOut + kBuf + kThr + kBiasS + kBars;
+  static constexpr int kBars = (2 * STAGES + 2 * NBUF) * 8 + 16 + (kHasIn ? kEpiWarps * 2 * 8 : 0);
+  static constexpr int kTotal = kRing + kStageOut + kStageIn + kBuf + kThr + kBiasS + kBars;
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -252,7 +258,8 @@ template <int BN, int STAGES, int EPI, bool TF32, int SETS, int CL, int NBUF = 2
 __global__ void __launch_bounds__(128 + SETS * 128, 1)
 sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                   const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
-                  const __grid_constant__ CUtensorMap mapO, const GemmParams p) {
+                  const __grid_constant__ CUtensorMap mapO, const __grid_constant__ CUtensorMap mapI,
+                  const GemmParams p) {
   using L = GemmSmem<BN, STAGES, EPI, SETS, NBUF>;
   constexpr int kEpiWarps = L::kEpiWarps;
   constexpr uint16_t kMcMask = static_cast<uint16_t>((1u << CL) - 1u);
@@ -268,16 +275,19 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* ring = smem;
   uint8_t* stage_out = smem + L::kRing;
-  uint8_t* cand = smem + L::kRing + L::kStageOut;
-  float* thr_s = reinterpret_cast<float*>(smem + L::kRing + L::kStageOut + L::kBuf);
-  float* bias_s = reinterpret_cast<float*>(smem + L::kRing + L::kStageOut + L::kBuf + L::kThr);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kRing + L::kStageOut + L::kBuf + L::kThr + L::kBiasS);
+  uint8_t* stage_in = smem + L::kRing + L::kStageOut;
+  constexpr int kIo = L::kStageOut + L::kStageIn;
+  uint8_t* cand = smem + L::kRing + kIo;
+  float* thr_s = reinterpret_cast<float*>(smem + L::kRing + kIo + L::kBuf);
+  float* bias_s = reinterpret_cast<float*>(smem + L::kRing + kIo + L::kBuf + L::kThr);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kRing + kIo + L::kBuf + L::kThr + L::kBiasS);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tfull_bar = bars + 2 * STAGES;
   uint64_t* tempty_bar = bars + 2 * STAGES + NBUF;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * NBUF);
   int* tile_ctr = reinterpret_cast<int*>(tmem_slot + 1);  // tiles the MMA issuer has started (read by the prefetch warp)
+  uint64_t* in_bar = bars + 2 * STAGES + 2 * NBUF + 2;    // [epilogue warp][2]: input boxes landed
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -323,6 +333,9 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     for (int b = 0; b < NBUF; ++b) {
       mbar_init(&tfull_bar[b], 1);
       mbar_init(&tempty_bar[b], 4 * SETS);  // every epilogue warp drains its column range of buffer b
+    }
+    if constexpr (L::kHasIn) {
+      for (int i = 0; i < kEpiWarps * 2; ++i) mbar_init(&in_bar[i], 1);
     }
     fence_barrier_init();
   }
@@ -438,7 +451,7 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       const int64_t pitch = EPI == EPI_RESID ? p.ldt * 4 : p.ld16 * 2;  // bytes
       const int esz = EPI == EPI_RESID ? 4 : 2;
       const int64_t row_cols = EPI == EPI_RESID ? p.N : p.ld16;          // readable columns of a row
-      const bool ok = (pitch & 15) == 0 && ((row_cols * esz) & 15) == 0;
+      const bool ok = (pitch & 15) == 0 && ((row_cols * esz) & 15) == 0 && p.tma_in == 0;
       for (int lt = 0; ok && lt < num_lt; ++lt) {
         // tile lt's rows are requested once the MMA issuer has reached tile lt - 1.  Paced by a monotone counter, not
         // by the accumulator barriers: a waiter that falls two phases behind a parity barrier would wait for a
@@ -480,7 +493,6 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     constexpr int kCols = L::kCols;            // this warp scans columns [cb, cb + kCols) of every tile
     constexpr int kPerLane = kCols / 32;       // bias columns a lane stages
     static_assert(kCols % 32 == 0 && kPerLane <= 8 && kPerLane % 4 == 0, "bias staging layout");
-    static_assert(!L::kHasOut || kCols % 64 == 0, "output boxes are 32 fp32 / 64 bf16 columns wide");
     const int cb = set * kCols;
     float* bias_w = bias_s + ew * (2 * kCols);
     float nb[kPerLane];
@@ -501,15 +513,41 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     // TMA output staging of this warp: two 32 x 128-byte boxes, SWIZZLE_128B (16-byte piece pc of row r sits at
     // r * 128 + ((pc ^ (r & 7)) * 16): conflict-free for the row-per-lane writes, undone by the tensor map)
     const bool tma_out = L::kHasOut && p.tma_out != 0;
-    uint8_t* my_stage = stage_out + ew * (2 * L::kOutBox);
+    uint8_t* my_stage = stage_out + ew * (L::kOutBufs * L::kOutBox);
     int sbuf = 0;
     auto stage_piece = [&](int pc, uint4 v4) {
       *reinterpret_cast<uint4*>(my_stage + sbuf * L::kOutBox + lane * 128 + ((pc ^ (lane & 7)) << 4)) = v4;
     };
-    auto stage_begin = [&]() {  // the box about to be written must have been read by the store issued two boxes ago
-      if (lane == 0) bulk_wait_group_read<1>();
+    auto stage_begin = [&]() {  // the box about to be written must have been read by the store that last used it
+      if (lane == 0) bulk_wait_group_read<L::kOutBufs - 1>();
       __syncwarp();
     };
+    // input boxes (EPI_RESID: 32 fp32 target columns; EPI_MASK: 64 bf16 gate columns; 32 rows x 128 bytes either way):
+    // box g of this warp's sequence lives in buffer g & 1 and is requested while box g - 1 is consumed
+    const bool tma_in = L::kHasIn && p.tma_in != 0;
+    uint8_t* my_in = stage_in + ew * (2 * L::kOutBox);
+    uint64_t* my_in_bar = in_bar + ew * 2;
+    constexpr int kInCols = EPI == EPI_RESID ? 32 : 64;         // columns per input box
+    constexpr int kInPerTile = L::kHasIn ? kCols / kInCols : 1;  // boxes per tile and warp
+    uint32_t in_phase[2] = {0u, 0u};
+    auto in_issue = [&](int64_t g) {  // g: box ordinal over this CTA's tiles
+      const int lt_g = static_cast<int>(g / kInPerTile);
+      if (lt_g >= num_lt) return;
+      const int bx = static_cast<int>(g - static_cast<int64_t>(lt_g) * kInPerTile);
+      const int mb_g = static_cast<int>((g_begin + lt_g) / num_nt);
+      const int nt_g = static_cast<int>(g_begin + lt_g - static_cast<int64_t>(mb_g) * num_nt);
+      if (lane == 0) {
+        uint64_t* b = my_in_bar + (g & 1);
+        mbar_arrive_expect_tx(b, L::kOutBox);
+        tma_load_2d(my_in + (g & 1) * L::kOutBox, &mapI, b, nt_g * BN + cb + bx * kInCols, mb_g * kBM + q * 32,
+                    kEvictNormal);
+      }
+    };
+    auto in_piece = [&](int64_t g, int pc) {
+      return *reinterpret_cast<const uint4*>(my_in + (g & 1) * L::kOutBox + lane * 128 + ((pc ^ (lane & 7)) << 4));
+    };
+    int64_t in_g = 0;  // ordinal of the box being consumed
+    if (tma_in) in_issue(0);
     auto stage_flush = [&](int col, int row0) {
       fence_proxy_async();
       __syncwarp();
@@ -517,8 +555,9 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
         tma_store_2d(&mapO, my_stage + sbuf * L::kOutBox, col, row0);
         bulk_commit_group();
       }
-      sbuf ^= 1;
+      sbuf = (sbuf + 1) % L::kOutBufs;
     };
+    static_assert(!L::kHasOut || kCols % 64 == 0, "output boxes are 32 fp32 / 64 bf16 columns wide");
     double acc_sum[3] = {0.0, 0.0, 0.0};  // EPI_RELU16 / EPI_RESID running sums of this thread's rows
     float aff_scale = 1.f, aff_shift = 0.f;
     if constexpr (EPI == EPI_MASK) {
@@ -591,6 +630,7 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       uint4 gin[2][EPI == EPI_MASK ? 2 : 1];
       const int64_t tile_col0 = static_cast<int64_t>(nt) * BN + cb;
       auto load_inputs = [&](int cc, int slot) {
+        if (tma_in) return;  // the chunk's inputs are read from this warp's TMA box instead
         if constexpr (EPI == EPI_RESID) {
           const int64_t col0 = tile_col0 + cc;
           if (row < p.M) {
@@ -683,6 +723,29 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             const bool rv = row < p.M;
             const int64_t col0 = static_cast<int64_t>(nt) * BN + cb + cc;
             float o[kChunk];
+            constexpr int kChunksPerIn = kInCols / kChunk;
+            const int cib = (cc / kChunk) % kChunksPerIn;  // chunk within the current input box
+            if constexpr (L::kHasIn) {
+              if (tma_in && cib == 0) {
+                __syncwarp();          // every lane is done with the other buffer (the previous box)
+                in_issue(in_g + 1);    // request the next box, then wait for this one
+                mbar_wait(my_in_bar + (in_g & 1), in_phase[in_g & 1]);
+                in_phase[in_g & 1] ^= 1u;
+              }
+              if (tma_in) {
+                if constexpr (EPI == EPI_RESID) {
+#pragma unroll
+                  for (int j = 0; j < kChunk; j += 4) {
+                    const uint4 t4 = in_piece(in_g, cib * 4 + j / 4);
+                    xin[h][j] = __uint_as_float(t4.x); xin[h][j + 1] = __uint_as_float(t4.y);
+                    xin[h][j + 2] = __uint_as_float(t4.z); xin[h][j + 3] = __uint_as_float(t4.w);
+                  }
+                } else {
+                  gin[h][0] = in_piece(in_g, cib * 2);
+                  gin[h][1] = in_piece(in_g, cib * 2 + 1);
+                }
+              }
+            }
             if constexpr (EPI == EPI_RELU16) {
 #pragma unroll
               for (int j = 0; j < kChunk; ++j) {
@@ -742,6 +805,9 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             }
             if (tma_out && grp == 3)
               stage_flush(static_cast<int>(col0) - 3 * kChunk, mb * kBM + q * 32);
+            if constexpr (L::kHasIn) {
+              if (tma_in && cib == kChunksPerIn - 1) ++in_g;
+            }
             if constexpr (EPI != EPI_MASK) {
               if (rv && p.out != nullptr) {  // optional fp32 copy (module API); the trainer does not ask for it
 #pragma unroll

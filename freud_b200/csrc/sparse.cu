@@ -16,8 +16,10 @@ namespace freud {
 // ------------------------------------------------------------------------------------------------ prep_x
 // One thread per (t, 4 channels); loops over the batch axis so the per-(t,c) mean of topkautoencoder.py:104 is a
 // private register reduction.  Shifted sums (shift = x[0,t,c]) keep sum((x-mean)^2) = s2 - s1^2/B well conditioned.
-template <int MODE>  // 0: bf16 out, 1: tf32 hi/lo out
-__global__ void __launch_bounds__(256) prep_x_kernel(const float* __restrict__ x, const float* __restrict__ b_dec,
+// XT: storage type of x (fp32, or fp16 / bf16 as collected activation stores hold it: widened here, exactly, instead of
+// in a separate pass over the batch).
+template <int MODE, typename XT>  // MODE 0: bf16 out, 1: tf32 hi/lo out
+__global__ void __launch_bounds__(256) prep_x_kernel(const XT* __restrict__ x, const float* __restrict__ b_dec,
                                                      void* __restrict__ out_hi, void* __restrict__ out_lo,
                                                      double* __restrict__ tv, float* __restrict__ colmean, int B,
                                                      int64_t T, int d) {
@@ -30,7 +32,7 @@ __global__ void __launch_bounds__(256) prep_x_kernel(const float* __restrict__ x
     const int c = static_cast<int>(idx - t * d4) * 4;
     const float4 bd = load4(b_dec + c);
     const int64_t stride = T * d;
-    const float* px = x + t * d + c;
+    const XT* px = x + t * d + c;
     const float4 sh = load4(px);
     float4 s1 = make_float4(0, 0, 0, 0), s2 = make_float4(0, 0, 0, 0);
 #pragma unroll 8
@@ -1222,16 +1224,30 @@ static inline int grid_for(int64_t work, int block, int max_blocks) {
 using namespace freud;
 #define STREAM static_cast<cudaStream_t>(stream)
 
-extern "C" int freud_topk_prep_x(const float* x, const float* b_dec, void* xc_hi, void* xc_lo, double* tv,
+extern "C" int freud_topk_prep_x(const void* x, int x_dtype, const float* b_dec, void* xc_hi, void* xc_lo, double* tv,
                                  float* colmean, int64_t B, int64_t T, int64_t d, int precision, void* stream) {
   FREUD_REQUIRE(B > 0 && T > 0 && d > 0 && d % 4 == 0, "prep_x needs d % 4 == 0");
+  FREUD_REQUIRE(x_dtype >= 0 && x_dtype <= 2, "x_dtype: 0 fp32, 1 fp16, 2 bf16");
   FREUD_CHECK_CUDA(cudaMemsetAsync(tv, 0, sizeof(double), STREAM));
   const int64_t work = T * (d / 4);
   const int grid = static_cast<int>((work + 255) / 256);
+#define FREUD_PREP(MODE)                                                                                              \
+  do {                                                                                                                \
+    if (x_dtype == 0)                                                                                                 \
+      prep_x_kernel<MODE, float><<<grid, 256, 0, STREAM>>>(static_cast<const float*>(x), b_dec, xc_hi, xc_lo, tv,     \
+                                                           colmean, (int)B, T, (int)d);                               \
+    else if (x_dtype == 1)                                                                                            \
+      prep_x_kernel<MODE, __half><<<grid, 256, 0, STREAM>>>(static_cast<const __half*>(x), b_dec, xc_hi, xc_lo, tv,   \
+                                                            colmean, (int)B, T, (int)d);                              \
+    else                                                                                                              \
+      prep_x_kernel<MODE, __nv_bfloat16><<<grid, 256, 0, STREAM>>>(static_cast<const __nv_bfloat16*>(x), b_dec, xc_hi, \
+                                                                   xc_lo, tv, colmean, (int)B, T, (int)d);            \
+  } while (0)
   if (precision == FREUD_BF16)
-    prep_x_kernel<0><<<grid, 256, 0, STREAM>>>(x, b_dec, xc_hi, xc_lo, tv, colmean, (int)B, T, (int)d);
+    FREUD_PREP(0);
   else
-    prep_x_kernel<1><<<grid, 256, 0, STREAM>>>(x, b_dec, xc_hi, xc_lo, tv, colmean, (int)B, T, (int)d);
+    FREUD_PREP(1);
+#undef FREUD_PREP
   FREUD_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

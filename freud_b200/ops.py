@@ -45,9 +45,18 @@ def split_operand(w: torch.Tensor, precision: int):
     return hi, lo
 
 
+_X_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+
+
+def _x_dtype(x: torch.Tensor) -> int:
+    """Storage type code of an activation batch (fp32, or fp16 / bf16 as collected stores hold it)."""
+    if x.dtype not in _X_DTYPES or not x.is_cuda or not x.is_contiguous():
+        raise TypeError("activations must be a contiguous CUDA tensor of dtype float32, float16 or bfloat16")
+    return _X_DTYPES[x.dtype]
+
+
 def topk_prep_x(x: torch.Tensor, b_dec: torch.Tensor, precision: int, want_colmean: bool = False):
     """x [B,T,d] -> (xc_hi, xc_lo operand(s) of x - b_dec as [N,d], tv double[1][, x.mean(0) [T,d]])."""
-    _f32(x, "x")
     B, T, d = x.shape
     tv = torch.empty(1, dtype=torch.float64, device=x.device)
     colmean = torch.empty((T, d), dtype=torch.float32, device=x.device) if want_colmean else None
@@ -57,8 +66,8 @@ def topk_prep_x(x: torch.Tensor, b_dec: torch.Tensor, precision: int, want_colme
     else:
         hi = torch.empty((B * T, d), dtype=torch.float32, device=x.device)
         lo = torch.empty_like(hi)
-    call("freud_topk_prep_x", _ptr(x), _ptr(b_dec), _ptr(hi), _ptr(lo), _ptr(tv), _ptr(colmean), B, T, d, precision,
-         _stream())
+    call("freud_topk_prep_x", _ptr(x), _x_dtype(x), _ptr(b_dec), _ptr(hi), _ptr(lo), _ptr(tv), _ptr(colmean), B, T, d,
+         precision, _stream())
     if want_colmean:
         return hi, lo, tv, colmean
     return hi, lo, tv
@@ -300,7 +309,7 @@ def topk_decode_dacts(top_vals, top_idx, W_dec, b_dec, target):
     colsum = torch.zeros(d, dtype=torch.float32, device=dev)
     dacts = torch.empty((N, k), dtype=torch.float32, device=dev)
     call("freud_topk_decode_dacts", _ptr(top_vals), _ptr(top_idx), _ptr(W_dec), _ptr(b_dec), _ptr(target),
-         _ptr(sae_out), _ptr(resid), _ptr(sse), _ptr(colsum), _ptr(dacts), N, d, k, _stream())
+         _x_dtype(target), _ptr(sae_out), _ptr(resid), _ptr(sse), _ptr(colsum), _ptr(dacts), N, d, k, _stream())
     return sae_out, resid, sse, colsum, dacts
 
 

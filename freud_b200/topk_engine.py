@@ -110,6 +110,16 @@ def topk_forward(x, W_enc, b_enc, W_dec, b_dec, k, *, precision, dead_mask=None,
     x = x.contiguous()
     B, T, d = x.shape
     N, n = B * T, W_enc.shape[0]
+    # reference: `int(dead_mask.sum())` (topkautoencoder.py:109) -- one 8-byte device->host read, as upstream
+    if num_dead is None:
+        num_dead = int(dead_mask.sum()) if dead_mask is not None else 0
+    fused_main = (k == ops.K_FUSED) and not multi_topk
+    generic = not fused_main or num_dead > 0  # backward needs materialised gradient seeds (AuxK couples e_hat and e)
+    fused_decode = (fused_main and need_grad and not generic and precision == BF16 and ops.decode_dacts_supported(d, k))
+    # fp16 / bf16 activations (what collected stores hold) feed the fused bf16 path as they are -- the two kernels that
+    # read x widen it exactly -- every other route works on an fp32 copy
+    if x.dtype != torch.float32 and not fused_decode:
+        x = x.float()
     x2 = x.view(N, d)
     shadows = shadows if (shadows and precision == BF16) else {}
     xc_hi, xc_lo, we_hi, we_lo, tv = encode_operands(x, W_enc, b_dec, precision, dp, shadows.get("encoder.weight"))
@@ -117,11 +127,6 @@ def topk_forward(x, W_enc, b_enc, W_dec, b_dec, k, *, precision, dead_mask=None,
         wd = shadows["W_dec"] if "W_dec" in shadows else ops.split_operand(W_dec, BF16)[0]
     else:
         wd = W_dec
-    # reference: `int(dead_mask.sum())` (topkautoencoder.py:109) -- one 8-byte device->host read, as upstream
-    if num_dead is None:
-        num_dead = int(dead_mask.sum()) if dead_mask is not None else 0
-    fused_main = (k == ops.K_FUSED) and not multi_topk
-    generic = not fused_main or num_dead > 0  # backward needs materialised gradient seeds (AuxK couples e_hat and e)
     zero = torch.zeros((), dtype=torch.float32, device=x.device)
 
     pre = None
@@ -153,7 +158,7 @@ def topk_forward(x, W_enc, b_enc, W_dec, b_dec, k, *, precision, dead_mask=None,
     elif need_grad:
         resid_dtype = torch.bfloat16 if precision == BF16 else torch.float32
     dacts = None
-    if (fused_main and need_grad and not generic and precision == BF16 and ops.decode_dacts_supported(d, k)):
+    if fused_decode:
         # the decoder rows of a token are gathered once for the reconstruction AND the activation gradients
         sae_out, e, sse, colsum_e, dacts = ops.topk_decode_dacts(vals, idx, wd, b_dec, x2)
     else:

@@ -264,10 +264,14 @@ class SAETrainer:
                 "sae_out": out.sae_out, "latent": out.encoded.latent}  # None when materialize_outputs is False
 
     def step(self, activations: torch.Tensor):
-        """One optimisation step on a [B, T, d] fp32 CUDA batch.  Returns device tensors (no host sync)."""
+        """One optimisation step on a [B, T, d] CUDA batch (fp32, or fp16 / bf16 as stored).  Returns device tensors (no
+        host sync)."""
         if not activations.is_cuda:
             raise RuntimeError("activations must already be on the CUDA device")
-        x = activations.float().contiguous()
+        if self.is_topk and self.precision == BF16 and activations.dtype in (torch.float16, torch.bfloat16):
+            x = activations.contiguous()  # collected stores hold fp16: the fused bf16 path widens it in its own kernels
+        else:
+            x = activations.float().contiguous()
         out = self._topk_step(x) if self.is_topk else self._l1_step(x)
         self.step_count += 1
         return out

@@ -33,11 +33,13 @@ int freud_version(void);
 
 /* x - b_dec (topkautoencoder.py:74) written as the encoder GEMM's A operand, fused with the batch-axis
  * total variance sum((x - x.mean(0))^2) of topkautoencoder.py:104 (accumulated into *tv, which the call
- * zeroes first).  x is [B,T,d] fp32.  FREUD_BF16: xc_hi = bf16 [N,d], xc_lo unused.
+ * zeroes first).  x is [B,T,d] in fp32 (x_dtype 0), fp16 (1) or bf16 (2) -- activation stores collected on CUDA hold
+ * fp16; the widening is exact and happens in this pass.  FREUD_BF16: xc_hi = bf16 [N,d], xc_lo unused.
  * FREUD_FP32: xc_hi / xc_lo = fp32 [N,d] holding the tf32 high / low parts.
  * colmean (optional, [T,d] fp32) receives x.mean(0); data-parallel ranks exchange it to form the variance of
  * the concatenated batch. */
-int freud_topk_prep_x(const float* x, const float* b_dec, void* xc_hi, void* xc_lo, double* tv, float* colmean,
+int freud_topk_prep_x(const void* x, int x_dtype, const float* b_dec, void* xc_hi, void* xc_lo, double* tv,
+                      float* colmean,
                       int64_t B, int64_t T, int64_t d, int precision, void* stream);
 
 /* Weight operand preparation (the implicit autocast cast of nn.Linear / matmul operands):
@@ -160,8 +162,9 @@ int freud_topk_dacts(const void* g, int g_is_bf16, const int32_t* top_idx, const
  * (another dictionary shard's) contribute nothing and get dacts 0. */
 int freud_topk_decode_dacts_supported(int64_t d, int64_t k);
 int freud_topk_decode_dacts(const float* top_vals, const int32_t* top_idx, const void* W_dec_bf16, const float* b_dec,
-                            const float* target, float* sae_out, void* resid_bf16, double* sse, float* colsum,
-                            float* dacts, int64_t N, int64_t d, int64_t k, void* stream);
+                            const void* target, int target_dtype /* 0 fp32, 1 fp16, 2 bf16 */, float* sae_out,
+                            void* resid_bf16, double* sse, float* colsum, float* dacts, int64_t N, int64_t d, int64_t k,
+                            void* stream);
 
 /* fp32 mode: top_vals[t,j] <- relu((x[t] - b_dec) . W_enc[top_idx[t,j]] + b_enc[top_idx[t,j]]) with an fp32 FMA
  * chain (topkautoencoder.py:72-77 restricted to the selected latents): the tensor-core product selects, this pass

@@ -389,3 +389,32 @@ def test_fused_decode_dacts_matches_separate_kernels(d, N, sharded):
     da64 = (rows * e_f.double().cpu().unsqueeze(1)).sum(-1) * live
     assert rel_err(da_f.cpu(), da64) < 2e-6
     assert bool((da_f.cpu()[idx.cpu() < 0] == 0).all())
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_half_precision_activations_feed_the_fused_path_exactly(dtype):
+    """Activation stores collected on CUDA hold fp16 (hooked_model.py:106-108 decodes with fp16=True): SAETrainer.step
+    takes them as stored -- freud_topk_prep_x / freud_topk_decode_dacts widen exactly -- and must produce bit-for-bit
+    what it produces for the same values widened to fp32 first."""
+    from freud_b200.models.config import TopKAutoEncoderConfig
+    from freud_b200.models.topkautoencoder import TopKAutoEncoder
+    from freud_b200.trainer import SAETrainer
+
+    d, n = 384, 2048
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(3, 200, d, generator=g) * 0.7).to(dtype).cuda()
+    outs = []
+    for feed in (x, x.float()):
+        torch.manual_seed(1)
+        model = TopKAutoEncoder(d, TopKAutoEncoderConfig.from_dict({"n_dict_components": n, "k": 32})).cuda()
+        tr = SAETrainer(model, lr=1e-3, steps=10, clip_thresh=1.0, optimizer="adam", scheduler="linear",
+                        scheduler_params={"num_warmup_steps": 2}, dead_feature_threshold=10 ** 9, precision="bf16")
+        o = None
+        for _ in range(2):
+            o = tr.step(feed)
+        torch.cuda.synchronize()
+        outs.append((float(o["loss"]), o["sae_out"].clone(), o["top_idx"].clone(), model.W_dec.data.clone(),
+                     model.encoder.weight.data.clone()))
+    assert outs[0][0] == outs[1][0]
+    for a, b in zip(outs[0][1:], outs[1][1:]):
+        assert torch.equal(a, b)
