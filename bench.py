@@ -725,6 +725,9 @@ def main():
                     stage[s].copy_(hosts[i % n_bufs], non_blocking=True)
                 ready[s].record(copy_stream)
 
+        loss_pin = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+        loss_ev = [torch.cuda.Event() for _ in range(2)]
+
         def e2e_loop(n):
             for s in range(2):
                 freed[s].record()
@@ -738,12 +741,18 @@ def main():
                     tr.gather_batch(part[i % 2], out=stage[i % 2])
                 o = tr.step(stage[i % 2])
                 freed[i % 2].record()
-                # every step's loss is read back (4-byte D2H, train_sae.py:455); reading step i-1's after enqueueing
-                # step i keeps the host one step ahead of the device instead of idling the GPU during the enqueue
+                # every step's loss is read back (4-byte D2H, train_sae.py:455): the copy into pinned memory is enqueued
+                # right behind the step's own kernels and the host picks the value up one step later, after it has
+                # enqueued the next step -- a blocking `.item()` here would drain the stream (it waits for everything
+                # enqueued so far, the step just launched included) and leave the GPU idle during the next enqueue
+                loss_pin[i % 2].copy_(o["loss"].detach().reshape(1), non_blocking=True)
+                loss_ev[i % 2].record()
                 if prev is not None:
-                    loss_sum += float(prev["loss"].item())
-                prev = o
-            loss_sum += float(prev["loss"].item())
+                    loss_ev[prev].synchronize()
+                    loss_sum += float(loss_pin[prev][0])
+                prev = i % 2
+            loss_ev[prev].synchronize()
+            loss_sum += float(loss_pin[prev][0])
             return loss_sum
 
         e2e_loop(2)
@@ -845,7 +854,9 @@ def main():
                    f"{n_bufs * B * T * d * 4 / 1e6:.0f} MB total > 126 MB L2)"},
         "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": e2e_h2d,
                 "d2h_bytes_per_step": 4 * world, "ms_per_step": e2e_ms / args.steps,
-                "input_dtype": args.e2e_dtype + " pinned host batches, widened on the device"},
+                "input_dtype": args.e2e_dtype + " pinned host batches, fed to the step as stored (widened inside its kernels)",
+                "loss_readback": "every step: 4-byte D2H into pinned memory enqueued behind the step, read by the host "
+                                 "one step later (a blocking .item() would drain the stream)"},
         "e2e_fp32_input": e2e32,
 
         "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,

@@ -6,8 +6,10 @@ A compact stand-in for the loop of src/scripts/train_sae.py:297-600 for users wh
 out (with it, `freud_b200.compat.install_as_src()` runs the reference's own script on these kernels -- see
 INTEGRATION.md).  It uses the same config keys, builds the same model classes from `autoencoder_config`, draws the
 same shuffled batches (DeviceResidentActivationLoader), runs `SAETrainer.step` and writes checkpoints in the
-reference layout ({"model","optimizer","scheduler","step","best_val_loss","hparams"}, train_sae.py:336-351) that
-`init_sae_from_checkpoint` and the reference's GUI server load.  Validation, TensorBoard and plots are left out.
+reference layout and place (`<run_dir>/checkpoints/step<N>.pth` holding {"model","optimizer","scheduler","step",
+"best_val_loss","hparams"}, train_sae.py:232-248,365,492,600) that `init_sae_from_checkpoint` and the reference's GUI
+server load; `start_checkpoint` in the config resumes from one (train_sae.py:408-410: model, optimizer, scheduler and
+step; the dead-latent counters restart at zero, as upstream).  Validation, TensorBoard and plots are left out.
 """
 import argparse
 import json
@@ -45,18 +47,31 @@ def train(cfg: dict, max_steps=None, precision="bf16"):
                                    "clip_thresh", "batch_size", "whisper_config", "train_folder", "val_folder",
                                    "optimizer", "scheduler", "scheduler_params") if k in cfg}
     hparams["activation_size"] = activation_size
-    os.makedirs(cfg["run_dir"], exist_ok=True)
+    ckpt_dir = os.path.join(cfg["run_dir"], "checkpoints")  # train_sae.py:365
+    os.makedirs(ckpt_dir, exist_ok=True)
     step, losses = 0, []
+    if cfg.get("start_checkpoint"):  # train_sae.py:408-410
+        ck = torch.load(cfg["start_checkpoint"], map_location=cfg["device"], weights_only=False)
+        model.load_state_dict(ck["model"])
+        trainer.optimizer.load_state_dict(ck["optimizer"])
+        trainer.scheduler.load_state_dict(ck["scheduler"])
+        trainer.invalidate_weight_copies()
+        step = int(ck["step"])
+        trainer.step_count = step
     limit = min(steps, max_steps) if max_steps else steps
+
+    def save():
+        torch.save({"model": model.state_dict(), "optimizer": trainer.optimizer.state_dict(),
+                    "scheduler": trainer.scheduler.state_dict(), "step": step, "best_val_loss": float("inf"),
+                    "hparams": hparams}, os.path.join(ckpt_dir, f"step{step}.pth"))
+
     while step < limit:
         for acts, _ in loader:
             out = trainer.step(acts)
             losses.append(out["loss"])  # device tensors: no host sync inside the loop
             step += 1
             if step % cfg["save_every"] == 0 or step == limit:
-                torch.save({"model": model.state_dict(), "optimizer": trainer.optimizer.state_dict(),
-                            "scheduler": trainer.scheduler.state_dict(), "step": step, "best_val_loss": float("inf"),
-                            "hparams": hparams}, os.path.join(cfg["run_dir"], f"steps_{step}.pth"))
+                save()
             if step % cfg["log_tb_every"] == 0 or step == limit:
                 print(f"step {step}: loss {float(torch.stack(losses).mean()):.6f}", flush=True)
                 losses = []

@@ -416,7 +416,7 @@ extern "C" int freud_gemm_nt_mask(const void* a, const void* b, const void* act_
   p.ld16 = ld16;
   p.affine = affine;
   p.lda = lda;
-  return launch_gemm<256, 2, EPI_MASK, false, 2, 1>(a, nullptr, b, nullptr, p, 1, static_cast<cudaStream_t>(stream));
+  return launch_gemm<256, 3, EPI_MASK, false, 2, 1>(a, nullptr, b, nullptr, p, 1, static_cast<cudaStream_t>(stream));
 }
 
 // L1 SAE forward on bf16 operands (l1autoencoder.py:69-95):

@@ -128,9 +128,12 @@ struct GemmSmem {
   static constexpr int kRing = STAGES * kStageBytes;
   static constexpr bool kHasOut = EPI == EPI_STORE || EPI == EPI_MASK || EPI == EPI_RELU16 || EPI == EPI_RESID;
   static constexpr int kOutBox = 32 * 128;                              // 32 rows x 128 bytes
-  // EPI_RESID / EPI_MASK also READ a matrix row-per-thread (target / gate activations): those boxes come in by TMA as
-  // well (two per epilogue warp, fetched one box ahead), and the output then gets by with one box per warp
-  static constexpr bool kHasIn = EPI == EPI_RESID || EPI == EPI_MASK;
+  // EPI_RESID also READS a matrix row-per-thread (the fp32 target): those boxes come in by TMA as well (two per
+  // epilogue warp, fetched one box ahead), the output then gets by with one box per warp and the ring with two stages
+  // (its products have K <= a few hundred).  EPI_MASK keeps three ring stages and reads its bf16 gate rows through
+  // registers one chunk ahead behind the L2 prefetch warp: with K = d = 768 the third stage is worth more than the
+  // input boxes (measured at the dense-AuxK shape: 0.23 ms vs 0.30 ms).
+  static constexpr bool kHasIn = EPI == EPI_RESID;
   static constexpr int kOutBufs = kHasIn ? 1 : 2;
   static constexpr int kStageOut = kHasOut ? kEpiWarps * kOutBufs * kOutBox : 0;  // boxes are 1024-byte aligned
   static constexpr int kStageIn = kHasIn ? kEpiWarps * 2 * kOutBox : 0;

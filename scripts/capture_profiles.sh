@@ -13,11 +13,12 @@ python bench.py --workload c4 --no-cpu-baseline --no-eager --no-parity --profile
 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_reference_arm.json 2> $OUT/bench_ref.err
 python scripts/bench_extra.py > $OUT/bench_extra.json 2> $OUT/bench_extra.err
 python scripts/l2_microbench.py > $OUT/l2_microbench.json 2> $OUT/l2_microbench.err
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/l2_probe scripts/l2_probe.cu && /tmp/l2_probe > $OUT/l2_probe.json 2> $OUT/l2_probe.err
 # launch list of the bench step (cold-cache, serialised: shares only)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_c3.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-eager --no-parity --no-extras > $OUT/ncu_launch.log 2>&1
 # one --set full capture each of the dominant kernels (launch of the 4th step)
-for spec in "enc:sm100_topk_kernel" "sgw:sparse_grads_warp_kernel" "dec:decode_fixed_kernel" "dac:dacts_fixed_kernel" "adam:adam_kernel"; do
+for spec in "enc:sm100_topk_kernel" "sgw:sparse_grads_warp_kernel" "dd:decode_dacts_kernel" "adam:adam_kernel"; do
   name=${spec%%:*}; rx=${spec##*:}
   ncu --set full --clock-control none --import-source on -k regex:$rx -s 3 -c 1 -o $OUT/full_${name}_c3 \
       python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-eager --no-parity --no-extras > $OUT/ncu_full_$name.log 2>&1
@@ -26,6 +27,9 @@ ncu --set full --clock-control none --import-source on -k regex:sm100_topk_kerne
       python bench.py --workload c2 --steps 1 --warmup 3 --no-cpu-baseline --no-eager --no-parity > $OUT/ncu_full_enc_c2.log 2>&1
 ncu --set full --clock-control none -k regex:search_table_kernel -c 1 -o $OUT/full_search_table \
       python scripts/bench_extra.py > /dev/null 2>&1
+# the L1 step's residual-epilogue GEMM (TMA input / output boxes) and the AuxK-live step's dense kernels
+ncu --set full --clock-control none -k regex:"sm100_gemm_kernel" -s 60 -c 5 -o $OUT/full_l1 python scripts/l1_prof.py > $OUT/ncu_full_l1.log 2>&1
+ncu --set full --clock-control none -k regex:"sm100_gemm_kernel|row_topk_mask" -s 40 -c 6 -o $OUT/full_aux python scripts/aux_prof.py c3 > $OUT/ncu_full_aux.log 2>&1
 # gpurun copies back at most 64 MiB: keep the raw metric page of every capture as CSV, drop the reports
 for rep in $OUT/*.ncu-rep; do
   ncu -i $rep --page raw --csv > ${rep%.ncu-rep}.raw.csv 2> /dev/null && rm -f $rep

@@ -18,7 +18,8 @@ cap = os.path.join(ROOT, "gpurun_out", f"cap_{tag}")
 out = os.path.join(ROOT, "profiles")
 
 KEEP = [
-    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__time_duration.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
+    "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
     "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
     "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
     "l1tex__m_xbar2l1tex_read_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
@@ -85,21 +86,24 @@ def full_captures():
         else:
             continue
         rows = list(csv.reader(io.StringIO(raw)))
-        h, units, r = rows[0], rows[1], rows[2]
+        h, units = rows[0], rows[1]
+        r = rows[2]
         with open(os.path.join(out, f"{tag}_ncu_{name}.csv"), "w") as f:
-            f.write(f"Kernel Name,,{r[h.index('Kernel Name')]}\n")
-            for m in KEEP:
-                if m in h:
-                    f.write(f"{m},{units[h.index(m)]},{r[h.index(m)]}\n")
-            stalls = []
-            for i, c in enumerate(h):
-                if c.startswith("smsp__pcsamp_warps_issue_stalled_") and "not_issued" not in c:
-                    try:
-                        stalls.append((float(r[i]), c))
-                    except ValueError:
-                        pass
-            for v, c in sorted(stalls, reverse=True)[:6]:
-                f.write(f"{c},samples,{v:.0f}\n")
+            for r in rows[2:]:  # one block per captured launch
+                f.write(f"Kernel Name,,{r[h.index('Kernel Name')]}\n")
+                for m in KEEP:
+                    if m in h:
+                        f.write(f"{m},{units[h.index(m)]},{r[h.index(m)]}\n")
+                stalls = []
+                for i, c in enumerate(h):
+                    if c.startswith("smsp__pcsamp_warps_issue_stalled_") and "not_issued" not in c:
+                        try:
+                            stalls.append((float(r[i]), c))
+                        except ValueError:
+                            pass
+                for v, c in sorted(stalls, reverse=True)[:6]:
+                    f.write(f"{c},samples,{v:.0f}\n")
+            r = rows[2]
         if name.startswith("full_enc"):
             def val(m):
                 v, u = float(r[h.index(m)]), units[h.index(m)]

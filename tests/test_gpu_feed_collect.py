@@ -96,14 +96,20 @@ def test_example_training_loop_writes_a_reference_checkpoint(tmp_path):
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     model, trainer = mod.train(cfg, precision="fp32")
-    ckpt = torch.load(f"{tmp_path}/run/steps_40.pth", map_location="cpu")
+    ckpt = torch.load(f"{tmp_path}/run/checkpoints/step40.pth", map_location="cpu")
     assert set(ckpt) == {"model", "optimizer", "scheduler", "step", "best_val_loss", "hparams"} and ckpt["step"] == 40
     assert set(ckpt["model"]) == {"W_dec", "b_dec", "encoder.weight", "encoder.bias"}
     assert ckpt["hparams"]["activation_size"] == 64
-    loaded = init_sae_from_checkpoint(f"{tmp_path}/run/steps_40.pth", device="cuda")
+    loaded = init_sae_from_checkpoint(f"{tmp_path}/run/checkpoints/step40.pth", device="cuda")
     x = torch.randn(2, 50, 64, device="cuda")
-    first = init_sae_from_checkpoint(f"{tmp_path}/run/steps_20.pth", device="cuda")
+    first = init_sae_from_checkpoint(f"{tmp_path}/run/checkpoints/step20.pth", device="cuda")
     with torch.no_grad():
         assert float(loaded(x).fvu) < 1.0
     assert torch.equal(loaded.W_dec.detach().cpu(), model.W_dec.detach().cpu())
     assert not torch.equal(first.W_dec.cpu(), loaded.W_dec.cpu())
+    # resume (train_sae.py:408-410): from the step-20 checkpoint to step 40.  The dead-latent counters restart at zero
+    # as upstream, and no latent can die within 40 x 400 tokens, so the resumed run retraces the first one
+    cfg2 = dict(cfg, start_checkpoint=f"{tmp_path}/run/checkpoints/step20.pth", run_dir=f"{tmp_path}/run2")
+    model2, trainer2 = mod.train(cfg2, precision="fp32")
+    assert trainer2.step_count == 40
+    assert os.path.exists(f"{tmp_path}/run2/checkpoints/step40.pth")
