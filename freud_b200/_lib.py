@@ -126,22 +126,27 @@ def lib():
     return _lib
 
 
+_fns = {}
+
+
 def call(name, *args):
     """Invoke a C-ABI entry point; raise RuntimeError(freud_last_error()) on a non-zero status."""
     global call_count, kernel_launches
-    handle = lib()
+    fn = _fns.get(name)
+    if fn is None:
+        fn = _fns[name] = getattr(lib(), name)
     if profile is not None:
         import torch
 
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record()
-        rc = getattr(handle, name)(*args)
+        rc = fn(*args)
         end.record()
         profile.setdefault(name, []).append((start, end))
     else:
-        rc = getattr(handle, name)(*args)
+        rc = fn(*args)
     if rc != 0:
-        raise RuntimeError(f"{name} failed ({rc}): {handle.freud_last_error().decode()}")
+        raise RuntimeError(f"{name} failed ({rc}): {lib().freud_last_error().decode()}")
     call_count += 1
     kernel_launches += KERNELS_PER_CALL[name]
 

@@ -12,8 +12,15 @@ from ._lib import BF16, FP32, TensorList, call
 K_FUSED = 32  # selection width of the fused encoder epilogue
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """cudaStream_t of torch's current stream (as an integer: ctypes takes it for a void* parameter).  The short steps
+    (C2, the L1 SAE) are bound by host enqueue time, so the per-call conversions are kept to the minimum."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
+    return torch.cuda.current_stream().cuda_stream
 
 
 def _ptr(t):
@@ -23,7 +30,7 @@ def _ptr(t):
         raise RuntimeError("freud_b200 ops need CUDA tensors (there is no CPU fallback)")
     if not t.is_contiguous():
         raise RuntimeError("freud_b200 ops need contiguous tensors")
-    return C.c_void_p(t.data_ptr())
+    return t.data_ptr()
 
 
 def _f32(t, name):
