@@ -67,6 +67,7 @@ SIGNATURES = {
     "freud_rownorm_project": [_p, _i64, _i64, _f, _p],
     "freud_remove_parallel_grad": [_p, _p, _i64, _i64, _p],
     "freud_l1_colnorm": [_p, _p, _i64, _i64, _p],
+    "freud_l1_loss_scalars": [_p, _d, _d, _d, _p, _p],
     "freud_l1_loss_reduce": [_p, _p, _p, _p, _p, _i64, _i64, _i64, _p],
     "freud_l1_dz": [_p, _p, _p, _p, _i64, _i64, _p],
     "freud_l1_weight_grad": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _p],
@@ -93,7 +94,7 @@ KERNELS_PER_CALL = {
     "freud_topk_decode": 1, "freud_topk_dacts": 1, "freud_topk_decode_dacts": 1, "freud_topk_decode_dacts_supported": 0, "freud_topk_refine": 1, "freud_axpby": 1, "freud_shard_merge": 1, "freud_shard_localize": 1, "freud_residual": 1, "freud_csc_build": 5,
     "freud_csc_meta": 1, "freud_topk_sparse_grads": 3, "freud_topk_bdec_grad": 1, "freud_topk_loss_scalars": 1,
     "freud_dead_latent_update": 1, "freud_rownorm_project": 1, "freud_remove_parallel_grad": 1,
-    "freud_l1_colnorm": 1, "freud_l1_loss_reduce": 1, "freud_l1_dz": 1, "freud_l1_weight_grad": 1, "freud_l1_grad_operands": 1,
+    "freud_l1_colnorm": 1, "freud_l1_loss_scalars": 1, "freud_l1_loss_reduce": 1, "freud_l1_dz": 1, "freud_l1_weight_grad": 1, "freud_l1_grad_operands": 1,
     "freud_grad_sumsq": 1, "freud_clip_grads": 1, "freud_adam_step": 1, "freud_radam_step": 1,
     "freud_dp_reduce_scatter": 1, "freud_dp_adam_allgather": 1,
     "freud_feature_absmax": 1, "freud_col_absmax": 1,

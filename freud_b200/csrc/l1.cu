@@ -307,3 +307,24 @@ extern "C" int freud_l1_grad_operands(const float* x, const float* dxhat, const 
   FREUD_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+
+// Loss values and gradient scales of the L1 SAE from the four accumulated sums (l1autoencoder.py:85-86,29-36):
+//   acc = [sum|c|, sum over x != -1 of (x_hat - x)^2, count of x != -1, sum (x_hat - x)^2]
+//   out = [l1_loss, reconstruction_loss, mse, d recon / d x_hat scale 2 alpha / count, d l1 / d c scale 1 / N]
+// One launch instead of a dozen scalar torch ops: the L1 step is bound by host enqueue time.
+__global__ void l1_loss_scalars_kernel(const double* __restrict__ acc, double n_glob, double d, double recon_alpha,
+                                       float* __restrict__ out) {
+  out[0] = static_cast<float>(acc[0] / n_glob);
+  out[1] = static_cast<float>(recon_alpha * acc[1] / acc[2]);
+  out[2] = static_cast<float>(acc[3] / (n_glob * d));
+  out[3] = static_cast<float>(2.0 * recon_alpha / acc[2]);
+  out[4] = static_cast<float>(1.0 / n_glob);
+}
+
+extern "C" int freud_l1_loss_scalars(const double* acc, double n_glob, double d, double recon_alpha, float* out,
+                                     void* stream) {
+  FREUD_REQUIRE(acc != nullptr && out != nullptr && n_glob > 0 && d > 0, "l1_loss_scalars: bad arguments");
+  l1_loss_scalars_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(acc, n_glob, d, recon_alpha, out);
+  FREUD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -79,9 +79,9 @@ class _L1ForwardFn(torch.autograd.Function):
             x16 = ops.split_operand(x2, BF16)[0]
             wt16 = ops.split_operand(Wt, BF16)[0]                                   # [n, d]
             w16 = _pad_cols_bf16(W.data)                                            # [d, ceil8(n)]
-            c16, l1sum, latent = ops.l1_encode_fused(x16, wt16, b, want_outputs)    # relu(x @ W + b)
-            dxh16, sums, x_hat = ops.l1_decode_fused(c16, w16, n, x2, want_outputs)  # c @ W.T vs x
-            acc = torch.cat((l1sum, sums))
+            acc = torch.zeros(4, dtype=torch.float64, device=x2.device)  # [sum|c|, masked sse, count, sse]
+            c16, _, latent = ops.l1_encode_fused(x16, wt16, b, want_outputs, sums=acc[0:1])     # relu(x @ W + b)
+            dxh16, _, x_hat = ops.l1_decode_fused(c16, w16, n, x2, want_outputs, sums=acc[1:4])  # c @ W.T vs x
             saved = (x16, c16, dxh16, wt16)
         else:
             x_ops = _gemm_operands(x2, precision)
@@ -96,26 +96,27 @@ class _L1ForwardFn(torch.autograd.Function):
         if dp is not None:  # losses (and with them the gradient scales) of the batch concatenated over ranks
             acc = dp.all_reduce_sum(acc)
             n_glob = N * dp.world_size
-        l1 = (acc[0] / n_glob).float()
-        recon = (recon_alpha * acc[1] / acc[2]).float()
-        mse = (acc[3] / (n_glob * d)).float()
-        ctx.saved = saved + (acc, precision, recon_alpha, n_glob, n, d)
+        # l1 = sum|c| / N, recon = alpha * masked mse, mse, and the two gradient scales: one launch (:85-86, :29-36)
+        scal = ops.l1_loss_scalars(acc, n_glob, d, recon_alpha)
+        l1, recon, mse = scal[0], scal[1], scal[2]
+        ctx.saved = saved + (scal, precision, recon_alpha, n_glob, n, d)
         outs = [t for t in (x_hat, latent, mse) if t is not None]
         ctx.mark_non_differentiable(*outs)
         return x_hat, latent, l1, recon, mse
 
     @staticmethod
     def backward(ctx, g_xhat, g_latent, g_l1, g_recon, g_mse):
-        a0, a1, a2, a3, acc, precision, recon_alpha, n_glob, n, d = ctx.saved
+        a0, a1, a2, a3, scal, precision, recon_alpha, n_glob, n, d = ctx.saved
         dev = a0.device
         zero = torch.zeros((), dtype=torch.float32, device=dev)
         g_l1 = zero if g_l1 is None else g_l1.float()
         g_recon = zero if g_recon is None else g_recon.float()
-        s_recon = (g_recon.double() * (2.0 * recon_alpha) / acc[2]).float()   # d recon / d x_hat = 2*alpha*(x_hat-x)/N_unmasked
-        s_l1 = g_l1 / n_glob                                                  # d l1 / d c = 1[c>0]/N
+        # (d recon / d x_hat = 2*alpha*(x_hat-x)/N_unmasked, d l1 / d c = 1[c>0]/N) times the incoming gradients
+        scales = torch.stack((g_recon, g_l1)) * scal[3:5]
+        s_recon, s_l1 = scales[0], scales[1]
         if precision == BF16:
             x16, c16, dxh16, wt16 = a0, a1, a2, a3
-            dz16 = ops.gemm_nt_mask(dxh16, wt16, c16, torch.stack((s_recon, s_l1)))  # (c>0) ? s_recon*(dxhat W) + s_l1 : 0
+            dz16 = ops.gemm_nt_mask(dxh16, wt16, c16, scales)  # (c>0) ? s_recon*(dxhat W) + s_l1 : 0
             db = ops.col_sum_bf16(dz16, n)
             Ga = ops.gemm_tn_splitk(x16, dz16, M=d, N=n)                             # x^T dz
             Gb = ops.gemm_tn_splitk(dxh16, c16, M=d, N=n)                            # dxhat^T c   (dxhat unscaled)
@@ -125,7 +126,7 @@ class _L1ForwardFn(torch.autograd.Function):
             # dc (unscaled) = dxhat_raw @ W  as  A = dxhat [N, K=d], B = W^T [n, K=d]
             dx_ops = _gemm_operands(dxhat, precision)
             dc = ops.gemm_nt(dx_ops[0], dx_ops[1], wt_ops[0], wt_ops[1], None, False, precision)
-            db = ops.l1_dz(dc, latent, torch.stack((s_recon, s_l1)))          # dc becomes dz in place
+            db = ops.l1_dz(dc, latent, scales)          # dc becomes dz in place
             dW = ops.l1_weight_grad(x2, dc, dxhat, latent, torch.stack((torch.ones_like(s_recon), s_recon)))
         ctx.saved = None
         return None, dW, db, None, None, None, None

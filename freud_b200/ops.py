@@ -214,20 +214,29 @@ def gemm_nt_mask(a: torch.Tensor, b: torch.Tensor, act: torch.Tensor, affine: to
     return out
 
 
-def l1_encode_fused(x16: torch.Tensor, wt16: torch.Tensor, bias: torch.Tensor, want_latent: bool):
-    """c = relu(x W + b) as bf16 [M, ceil8(n)] + sum(c) (double[1]) [+ fp32 latent]."""
+def l1_loss_scalars(acc: torch.Tensor, n_glob: int, d: int, recon_alpha: float):
+    """acc double[4] -> float[5] = (l1, recon, mse, 2*alpha/count, 1/n_glob) in one launch."""
+    out = torch.empty(5, dtype=torch.float32, device=acc.device)
+    call("freud_l1_loss_scalars", _ptr(acc), float(n_glob), float(d), float(recon_alpha), _ptr(out), _stream())
+    return out
+
+
+def l1_encode_fused(x16: torch.Tensor, wt16: torch.Tensor, bias: torch.Tensor, want_latent: bool, sums=None):
+    """c = relu(x W + b) as bf16 [M, ceil8(n)] + sum(c) (double[1], accumulated into `sums` when given -- zeroed by the
+    caller) [+ fp32 latent]."""
     M, K = x16.shape
     n = wt16.shape[0]
     ld = (n + 7) // 8 * 8
     c16 = torch.empty((M, ld), dtype=torch.bfloat16, device=x16.device)
     latent = torch.empty((M, n), dtype=torch.float32, device=x16.device) if want_latent else None
-    sums = torch.zeros(1, dtype=torch.float64, device=x16.device)
+    if sums is None:
+        sums = torch.zeros(1, dtype=torch.float64, device=x16.device)
     call("freud_l1_encode_fused", _ptr(x16), _ptr(wt16), _ptr(bias), _ptr(c16), _ptr(latent), _ptr(sums), M, n, K, ld,
          _stream())
     return c16, sums, latent
 
 
-def l1_decode_fused(c16: torch.Tensor, w16: torch.Tensor, n: int, target: torch.Tensor, want_xhat: bool):
+def l1_decode_fused(c16: torch.Tensor, w16: torch.Tensor, n: int, target: torch.Tensor, want_xhat: bool, sums=None):
     """x_hat = c W^T against `target`: (dxhat16 bf16 [M, ceil8(d)] unscaled masked residual, sums double[3] =
     (masked sse, count, sse) [, fp32 x_hat]).  c16 [M, lda] with n valid columns, w16 [d, ldb >= n]."""
     M, lda = c16.shape
@@ -235,7 +244,8 @@ def l1_decode_fused(c16: torch.Tensor, w16: torch.Tensor, n: int, target: torch.
     ld = (d + 7) // 8 * 8
     r16 = torch.empty((M, ld), dtype=torch.bfloat16, device=c16.device)
     x_hat = torch.empty((M, d), dtype=torch.float32, device=c16.device) if want_xhat else None
-    sums = torch.zeros(3, dtype=torch.float64, device=c16.device)
+    if sums is None:
+        sums = torch.zeros(3, dtype=torch.float64, device=c16.device)
     call("freud_l1_decode_fused", _ptr(c16), _ptr(w16), _ptr(_f32(target, "target")), _ptr(r16), _ptr(x_hat),
          _ptr(sums), M, d, n, lda, ldb, ld, _stream())
     return r16, sums, x_hat

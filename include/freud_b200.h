@@ -247,6 +247,11 @@ int freud_remove_parallel_grad(float* G, const float* W, int64_t rows, int64_t c
  * transposed copy Wt [n,d] used as the K-major GEMM operand.  W is decoder.weight [d,n]. */
 int freud_l1_colnorm(float* W, float* Wt, int64_t d, int64_t n, void* stream);
 
+/* L1 SAE loss values and gradient scales from the accumulated sums acc = [sum|c|, masked sse, unmasked count, sse]
+ * (l1autoencoder.py:85-86,29-36): out[0..4] = l1_loss, reconstruction_loss (= recon_alpha * masked mse), mse,
+ * 2 * recon_alpha / count, 1 / n_glob.  n_glob = tokens of the (global) batch, d = activation size. */
+int freud_l1_loss_scalars(const double* acc, double n_glob, double d, double recon_alpha, float* out, void* stream);
+
 /* Loss pieces of L1AutoEncoder.forward (l1autoencoder.py:85-86,94, mse_loss :29-36):
  *   acc[0] += sum |c|,  acc[1] += sum_{x != -1} (x_hat-x)^2,  acc[2] += #{x != -1},  acc[3] += sum (x_hat-x)^2
  * and, if dxhat != NULL, dxhat = (x != -1) * (x_hat - x)  (scaled later).  acc: 4 doubles, caller zeroes. */
