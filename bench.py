@@ -53,27 +53,6 @@ def synth_batch(B, T, d, seed, device="cpu", pin=False):
     return x.to(device) if device != "cpu" else x
 
 
-def bind_to_gpu_numa_node(index):
-    """Pin this rank's threads to the CPUs closest to its GPU (NVML's ideal affinity) BEFORE any pinned host buffer is
-    allocated: with one process per GPU the end-to-end loop is bound by host-memory -> PCIe traffic (8 x 74 MB per
-    3 ms step), and first-touch pages on the wrong socket send every batch over the inter-socket link."""
-    if os.environ.get("FREUD_BENCH_NO_NUMA"):
-        return None
-    try:
-        import pynvml
-
-        pynvml.nvmlInit()
-        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
-        phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
-        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
-        before = len(os.sched_getaffinity(0))
-        pynvml.nvmlDeviceSetCpuAffinity(h)
-        after = len(os.sched_getaffinity(0))
-        return {"cpus_before": before, "cpus_after": after}
-    except Exception as ex:  # noqa: BLE001 -- containers without the privilege keep the inherited mask
-        return {"error": repr(ex)[:120]}
-
-
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -633,7 +612,6 @@ def main():
 
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
-    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     dp = None
     sharded = bool(w.get("sharded"))
     if world > 1 or sharded:
@@ -870,7 +848,7 @@ def main():
         "config": {"workload": f"{args.workload}: {w['desc']}", "global_batch_tokens": tokens_per_step,
                    "parallelism": (f"feature-sharded x{world}" if sharded else f"dp{world}"),
                    "dp_exchange": dp_exchange,
-                   "optimizer": "adam+clip(1.0)+linear-warmup", "numa_binding": numa,
+                   "optimizer": "adam+clip(1.0)+linear-warmup",
                    "l2": f"{n_bufs} rotating input batches of {B * T * d * 4 / 1e6:.0f} MB (> 126 MB L2)"
                    if B * T * d * 4 > 126e6 else f"{n_bufs} rotating input batches ({B * T * d * 4 / 1e6:.0f} MB each, "
                    f"{n_bufs * B * T * d * 4 / 1e6:.0f} MB total > 126 MB L2)"},
