@@ -824,6 +824,13 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
             if (tma_out) {
               const int grp = (cc / kChunk) & 1;  // chunk within the 32-column (128-byte) output box
               if (grp == 0) stage_begin();
+              if (col0 + kChunk > p.N) {
+                // TMA clips a box in 16-byte granules: up to three padding columns of the pitch that share a granule
+                // with the last valid column are written too -- as zeros, not as the -inf of an out-of-range column
+#pragma unroll
+                for (int j = 0; j < kChunk; ++j)
+                  if (col0 + j >= p.N) v[j] = 0.f;
+              }
 #pragma unroll
               for (int j = 0; j < kChunk; j += 4) {
                 float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);

@@ -62,7 +62,8 @@ int freud_topk_encode(const void* xc_hi, const void* xc_lo, const void* w_hi, co
 
 /* out[M,N] = act(A[M,K] @ B[N,K]^T + bias[N]) on the tensor cores; act = relu if relu != 0.
  * (pre_acts materialised for the AuxK / multi-TopK branches, topkautoencoder.py:72-77,121,135; and the
- * L1 SAE's x @ W + b and c @ W.T, l1autoencoder.py:74,84.)  Operands prepared as for freud_topk_encode. */
+ * L1 SAE's x @ W + b and c @ W.T, l1autoencoder.py:74,84.)  Operands prepared as for freud_topk_encode.  * When out has a padded pitch (ldo > N, ldo % 4 == 0) the up to three padding columns that share a 16-byte granule
+ * with column N-1 may be written as zeros (the TMA store clips in 16-byte granules); columns beyond stay untouched. */
 int freud_gemm_nt(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, const float* bias,
                   float* out, int64_t M, int64_t N, int64_t K, int64_t ldo, int relu, int precision,
                   void* stream);

@@ -85,3 +85,39 @@ def test_gemm_nt_mask_epilogue(M, N, K):
     assert float(out[:, N:].float().abs().max()) == 0.0 if ld > N else True
     s = ops.col_sum_bf16(out, N)
     assert _rel(s, out[:, :N].float().sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,K,ldo,relu", [(20000, 200, 384, 200, True),     # persistent CTAs over >1 row block, TMA boxes
+                                            (1000, 2458, 768, 2464, True),    # ragged N inside a padded pitch (dense AuxK)
+                                            (300, 201, 64, 201, False),       # pitch not a multiple of 16 bytes: direct stores
+                                            (129, 64, 128, 64, False), (5, 96, 32, 96, True)])
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_gemm_nt_store_epilogue(M, N, K, ldo, relu, precision):
+    """out = act(A B^T + bias), fp32 output through the TMA-box epilogue (or direct stores when the pitch rules it
+    out): ragged M / N, padded pitch whose padding columns must stay untouched, one CTA walking several row blocks."""
+    from freud_b200 import ops
+    from freud_b200._lib import BF16, FP32
+
+    prec = BF16 if precision == "bf16" else FP32
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    a = torch.randn((M, K), device="cuda", generator=g)
+    b = torch.randn((N, K), device="cuda", generator=g)
+    bias = torch.randn(N, device="cuda", generator=g)
+    a_ops, b_ops = ops.split_operand(a, prec), ops.split_operand(b, prec)
+    out = torch.full((M, ldo), 77.0, device="cuda")
+    ops.gemm_nt(a_ops[0], a_ops[1], b_ops[0], b_ops[1], bias, relu, prec, out=out)
+    if precision == "bf16":
+        ref = a.to(torch.bfloat16).double() @ b.to(torch.bfloat16).double().T + bias.double()
+        tol = 2e-5
+    else:
+        ref = a.double() @ b.double().T + bias.double()
+        tol = 1e-5
+    if relu:
+        ref = torch.relu(ref)
+    assert _rel(out[:, :N], ref) < tol
+    if ldo > N:
+        # padding columns stay untouched, except that the TMA path may zero the (up to 3) padding columns sharing a
+        # 16-byte granule with the last valid column
+        g4 = (N + 3) // 4 * 4
+        assert bool((out[:, g4:] == 77.0).all()), "padding columns of the output pitch were written"
+        assert bool(((out[:, N:g4] == 77.0) | (out[:, N:g4] == 0.0)).all())
