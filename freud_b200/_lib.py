@@ -33,6 +33,7 @@ SIGNATURES = {
     "freud_split_operand": [_p, _p, _p, _i64, _i, _p],
     "freud_topk_encode_workspace": [_i64, _i64, _p],
     "freud_topk_encode": [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i, _p, _i64, _p],
+    "freud_topk_encode_stats": [_p, _i],
     "freud_gemm_nt": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i, _i, _p],
     "freud_row_topk": [_p, _p, _p, _p, _i64, _i64, _i64, _p],
     "freud_gather_rows": [_p, _p, _p, _i64, _i64, _p],
@@ -89,7 +90,7 @@ SIGNATURES = {
 
 # CUDA kernels each entry point enqueues (memsets not counted); bench.py sums these into `gpu_launches`
 KERNELS_PER_CALL = {
-    "freud_topk_prep_x": 1, "freud_split_operand": 1, "freud_topk_encode_workspace": 0, "freud_topk_encode": 2, "freud_gemm_nt": 1,
+    "freud_topk_prep_x": 1, "freud_split_operand": 1, "freud_topk_encode_workspace": 0, "freud_topk_encode": 2, "freud_topk_encode_stats": 0, "freud_gemm_nt": 1,
     "freud_row_topk": 1, "freud_gather_rows": 1, "freud_index_map": 1, "freud_row_topk_mask": 1, "freud_col_sum_bf16": 1, "freud_transpose_bf16": 1, "freud_mask_grad": 1, "freud_scatter_add_rows": 1, "freud_gemm_nt_splitk": 1, "freud_sum_splits": 1, "freud_gemm_nt_mask": 1, "freud_l1_encode_fused": 1, "freud_l1_decode_fused": 1, "freud_gemm_tn_splitk": 1, "freud_gemm_nn": 1,
     "freud_topk_decode": 1, "freud_topk_dacts": 1, "freud_topk_decode_dacts": 1, "freud_topk_decode_dacts_supported": 0, "freud_topk_refine": 1, "freud_axpby": 1, "freud_shard_merge": 1, "freud_shard_localize": 1, "freud_residual": 1, "freud_csc_build": 5,
     "freud_csc_meta": 1, "freud_topk_sparse_grads": 3, "freud_topk_bdec_grad": 1, "freud_topk_loss_scalars": 1,

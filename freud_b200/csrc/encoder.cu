@@ -191,7 +191,16 @@ static int launch_gemm(const void* a_hi, const void* a_lo, const void* b_hi, con
 
 // Fused top-k encoder with specialised scanner / compactor epilogue warps (topk_sm100.cuh): one CTA per row block,
 // the row blocks of a partial last wave cut into column pieces exactly as in launch_gemm.
-template <int BN, int STAGES, bool TF32, int CEV = 0>
+// Cycle counters of the diagnostic build (FREUD_ENC_STATS=1 selects it): [0] scanner warp lifetime, [1] scanner waiting
+// for an accumulator, [2] scanner waiting for a free candidate buffer, [3] hand-overs, [4] compactor warp lifetime,
+// [5] compactor waiting for a hand-over, [6] compactions, [7] compactor warps, [8] tiles scanned (summed over warps).
+static unsigned long long* g_enc_stats = nullptr;
+static bool enc_stats_enabled() {
+  static const bool on = [] { const char* e = getenv("FREUD_ENC_STATS"); return e && atoi(e) != 0; }();
+  return on;
+}
+
+template <int BN, int STAGES, bool TF32, int CEV = 0, bool STATS = false>
 static int launch_topk(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, GemmParams p, int passes,
                        cudaStream_t stream) {
   using L = TopkSmem<BN, STAGES>;
@@ -207,7 +216,15 @@ static int launch_topk(const void* a_hi, const void* a_lo, const void* b_hi, con
     mB1 = mB0;
   }
   p.passes = passes;
-  auto kern = sm100_topk_kernel<BN, STAGES, TF32, CEV>;
+  p.stats = nullptr;
+  if (STATS) {
+    if (g_enc_stats == nullptr) {
+      FREUD_CHECK_CUDA(cudaMalloc(&g_enc_stats, 16 * sizeof(unsigned long long)));
+      FREUD_CHECK_CUDA(cudaMemset(g_enc_stats, 0, 16 * sizeof(unsigned long long)));
+    }
+    p.stats = g_enc_stats;
+  }
+  auto kern = sm100_topk_kernel<BN, STAGES, TF32, CEV, STATS>;
   static bool attr_set = false;
   if (!attr_set) {
     FREUD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -296,7 +313,9 @@ extern "C" int freud_topk_encode(const void* xc_hi, const void* xc_lo, const voi
       case 6: p.out = top_vals; return launch_gemm<256, 3, EPI_NONE, false, 1, 1>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
       case 7: p.out = top_vals; return launch_gemm<256, 4, EPI_NONE, false, 1, 1>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
       case 8: p.out = top_vals; return launch_gemm<256, 3, EPI_NONE, false, 2, 1>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
-      default: return launch_topk<256, 3, false, 2>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
+      default:
+        if (enc_stats_enabled()) return launch_topk<256, 3, false, 2, true>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
+        return launch_topk<256, 3, false, 2>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);
     }
   }
   if (precision == FREUD_FP32) {
@@ -467,4 +486,16 @@ extern "C" int freud_l1_decode_fused(const void* c_bf16, const void* w_bf16, con
   p.sums = sums;
   return launch_gemm<256, 2, EPI_RESID, false, 2, 1>(c_bf16, nullptr, w_bf16, nullptr, p, 1,
                                                      static_cast<cudaStream_t>(stream));
+}
+
+/* Diagnostic: cycle counters of the instrumented top-k encoder build (selected by FREUD_ENC_STATS=1), summed over all
+ * launches since the last reset.  out[0..8], see g_enc_stats.  Synchronises the device. */
+extern "C" int freud_topk_encode_stats(unsigned long long* out, int reset) {
+  FREUD_REQUIRE(out != nullptr, "stats: out is NULL");
+  for (int i = 0; i < 9; ++i) out[i] = 0;
+  if (g_enc_stats == nullptr) return 0;
+  FREUD_CHECK_CUDA(cudaDeviceSynchronize());
+  FREUD_CHECK_CUDA(cudaMemcpy(out, g_enc_stats, 9 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (reset) FREUD_CHECK_CUDA(cudaMemset(g_enc_stats, 0, 16 * sizeof(unsigned long long)));
+  return 0;
 }

@@ -39,7 +39,9 @@ struct TopkSmem {
   static constexpr int kTotal = kRing + kCand + kCnt + kThr + kBiasS + kBars;
 };
 
-template <int BN, int STAGES, bool TF32, int CEV = 0>
+// STATS (diagnostic build, freud_topk_encode_stats): lane 0 of every scanner / compactor warp accumulates clock64
+// cycles spent in its waits and counts its hand-overs / compactions into p.stats.
+template <int BN, int STAGES, bool TF32, int CEV = 0, bool STATS = false>
 __global__ void __launch_bounds__(384, 1)
 sm100_topk_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                   const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
@@ -211,10 +213,13 @@ sm100_topk_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     // hand-over -- must see the compactor's first release (parity 0).  Getting this wrong lets the scanner lap the
     // compactor: two arrivals on a count-1 barrier flip its phase twice and the waiter never sees either.
     uint32_t ephase[2] = {0u, 1u};
+    long long st_t0 = 0, st_tfull = 0, st_cempty = 0, st_ho = 0;
+    if constexpr (STATS) st_t0 = clock64();
     uint32_t base = cand_q;
     uint32_t ptr = base;
     uint32_t ptr_limit = base + (kNewSlots - kCheck) * kSlotStride;
     float thresh = 0.f;
+    uint32_t fill_bound = 0;  // warp-uniform upper bound of the fullest candidate column, in slots
     int bslot = 0;
     // hand the current candidate buffer to the compactor and continue in the other one
     auto hand_over = [&](uint32_t last) {
@@ -223,7 +228,13 @@ sm100_topk_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(&cfull_bar[q * 2 + cur]);
       cur ^= 1;
+      long long c0 = 0;
+      if constexpr (STATS) c0 = clock64();
       mbar_wait(&cempty_bar[q * 2 + cur], ephase[cur]);  // the compactor frees a buffer as soon as it has loaded it
+      if constexpr (STATS) {
+        st_cempty += clock64() - c0;
+        ++st_ho;
+      }
       ephase[cur] ^= 1u;
       base = cand_q + cur * L::kBufBytes;
       ptr = base;
@@ -248,7 +259,10 @@ sm100_topk_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       }
       if (lt + 1 < num_lt) load_bias(lt + 1);  // lands in registers while this tile is scanned
       const uint32_t bs_addr = smem_u32(bias_w + bslot * BN);
+      long long c1 = 0;
+      if constexpr (STATS) c1 = clock64();
       mbar_wait_relaxed(&tfull_bar[buf], (lt / NBUF) & 1, 32);
+      if constexpr (STATS) st_tfull += clock64() - c1;
       tc_fence_after();
       const uint32_t t_addr = lane_taddr + buf * BN;
       uint32_t r[2][kChunk];
@@ -316,8 +330,20 @@ sm100_topk_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                              : "memory");
             }
             ptr = addr[8];
-            // the next kCheck columns could overflow some lane's column
-            if (__any_sync(0xffffffffu, ptr > ptr_limit)) hand_over(0u);
+            // The next kCheck columns could overflow some lane's column.  A warp-uniform upper bound of the fullest
+            // column (it grows by at most kCheck per group) decides whether to look at all; only when the bound
+            // reaches the limit is the exact maximum taken (one REDUX), and the bound re-tightened to it: a vote and
+            // a dependent branch after every group were 18 % of the scanner's stall samples.
+            fill_bound += kCheck;
+            if (fill_bound > kNewSlots - kCheck) {
+              const uint32_t mx = __reduce_max_sync(0xffffffffu, (ptr - base) / kSlotStride);
+              if (mx > kNewSlots - kCheck) {
+                hand_over(0u);
+                fill_bound = 0;
+              } else {
+                fill_bound = mx;
+              }
+            }
           }
         }
       }
@@ -333,6 +359,15 @@ sm100_topk_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(&cfull_bar[q * 2 + cur]);
     }
+    if constexpr (STATS) {
+      if (lane == 0 && p.stats != nullptr) {
+        atomicAdd(p.stats + 0, static_cast<unsigned long long>(clock64() - st_t0));
+        atomicAdd(p.stats + 1, static_cast<unsigned long long>(st_tfull));
+        atomicAdd(p.stats + 2, static_cast<unsigned long long>(st_cempty));
+        atomicAdd(p.stats + 3, static_cast<unsigned long long>(st_ho));
+        atomicAdd(p.stats + 8, static_cast<unsigned long long>(num_lt));
+      }
+    }
   } else if (warp_idx >= 8) {
     // ===================== compactor =====================
     const int q = warp_idx & 3;
@@ -345,8 +380,13 @@ sm100_topk_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     for (int s = 0; s < kTopK; ++s) surv[s] = 0ull;
     int cur = 0;
     uint32_t fphase[2] = {0u, 0u};
+    long long ct_t0 = 0, ct_wait = 0, ct_n = 0;
+    if constexpr (STATS) ct_t0 = clock64();
     for (;;) {
+      long long c2 = 0;
+      if constexpr (STATS) c2 = clock64();
       mbar_wait_suspended(&cfull_bar[q * 2 + cur], fphase[cur]);
+      if constexpr (STATS) ct_wait += clock64() - c2;
       fphase[cur] ^= 1u;
       const uint32_t my_ptr = cnt_q[cur * 64 + lane];
       const uint32_t last = cnt_q[cur * 64 + 32];
@@ -361,6 +401,7 @@ sm100_topk_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
       if (lane == 0) mbar_arrive(&cempty_bar[q * 2 + cur]);  // the scanner may refill it while we sort
       cur ^= 1;
       if (__any_sync(0xffffffffu, my_ptr != my_base)) {
+        if constexpr (STATS) ++ct_n;
         bitonic_sort_desc<kNewSlots, CEV>(fresh);
         // max(descending, reversed descending) = the 32 largest of the union, as a bitonic sequence
 #pragma unroll
@@ -375,6 +416,14 @@ sm100_topk_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           atomicMax(reinterpret_cast<int*>(p.part_thr + row), __float_as_int(t));
       }
       if (last) break;
+    }
+    if constexpr (STATS) {
+      if (lane == 0 && p.stats != nullptr) {
+        atomicAdd(p.stats + 4, static_cast<unsigned long long>(clock64() - ct_t0));
+        atomicAdd(p.stats + 5, static_cast<unsigned long long>(ct_wait));
+        atomicAdd(p.stats + 6, static_cast<unsigned long long>(ct_n));
+        atomicAdd(p.stats + 7, 1ull);
+      }
     }
     // emit this thread's row.  Short rows (fewer than 32 positive pre-activations) are completed with zeros at the
     // lowest indices not already chosen: the oracle's (value desc, index asc) order for the all-zero tail after ReLU.

@@ -60,6 +60,13 @@ int freud_topk_encode(const void* xc_hi, const void* xc_lo, const void* w_hi, co
                       int64_t N, int64_t d, int64_t n, int precision, void* workspace, int64_t workspace_bytes,
                       void* stream);
 
+/* Diagnostic (FREUD_ENC_STATS=1 selects an instrumented build of the encoder kernel): clock64 cycle counters summed over
+ * the scanner / compactor warps of every launch since the last reset -- out[0] scanner lifetime, [1] scanner waiting for
+ * an accumulator tile, [2] scanner waiting for a free candidate buffer, [3] hand-overs, [4] compactor lifetime,
+ * [5] compactor waiting for a hand-over, [6] compactions, [7] compactor warps, [8] tiles scanned.  Host pointer;
+ * synchronises the device.  Zeros when the instrumented build never ran. */
+int freud_topk_encode_stats(unsigned long long* out, int reset);
+
 /* out[M,N] = act(A[M,K] @ B[N,K]^T + bias[N]) on the tensor cores; act = relu if relu != 0.
  * (pre_acts materialised for the AuxK / multi-TopK branches, topkautoencoder.py:72-77,121,135; and the
  * L1 SAE's x @ W + b and c @ W.T, l1autoencoder.py:74,84.)  Operands prepared as for freud_topk_encode.  * When out has a padded pitch (ldo > N, ldo % 4 == 0) the up to three padding columns that share a 16-byte granule
