@@ -625,14 +625,61 @@ __global__ void __launch_bounds__(256) csc_fill_kernel(const int32_t* __restrict
 }
 
 // Sort each feature's list ascending (token order) so the fp32 accumulation order -- and therefore the
-// gradients -- are run-to-run deterministic despite the atomic fill.  One CTA per feature, bitonic sort in
-// shared memory; lists longer than kSortMax entries are left in fill order (still correct, not bit-stable).
+// gradients -- are run-to-run deterministic despite the atomic fill.  Lists of up to kWarpSortMax entries: one WARP per
+// feature, bitonic network over registers and shuffles; longer lists up to kSortMax: one CTA per queued feature, bitonic
+// sort in shared memory; beyond that they are left in fill order (still correct, not bit-stable).
 constexpr int kSortMax = 4096;
-constexpr int kWarpSortMax = 128;
-constexpr int kRankSortMax = 1024;  // O(len^2 / 256) per thread (4096 compares at 1024): beyond this the bitonic network wins
+constexpr int kWarpSortMax = 1024;
 
-// Lists of up to 128 entries (the common case: N*k/n on average): one warp per feature, 4 entries per lane, rank
-// sort by shuffle broadcast (entries are distinct positions, so rank = number of smaller entries).
+// Ascending bitonic sort of 32 * E keys held E per lane; element e of lane l has index l * E + e.  Exchanges at distance
+// j < E stay inside a lane (static register indices), the others cross lanes with one shuffle per element.  No shared
+// memory, no barrier: a 512-key sort is ~1400 instructions of one warp (the CTA-wide shared-memory network with a
+// barrier per stage took 26 us per C2 list, 157 us for the 6144 lists of a C2 step).
+template <int E>
+__device__ __forceinline__ void warp_bitonic_sort_asc(int32_t (&a)[E], int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32 * E; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= E) {  // partner element: same e, lane ^ (j / E)
+        const int lj = j / E;
+        // ascending block iff bit k of the index is clear; k >= 2 j >= 2 E here, so the bit lies in the lane number
+        const bool up = k >= 32 * E ? true : ((lane & (k / E)) == 0);
+        const bool lower = (lane & lj) == 0;
+        const bool take_min = lower == up;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const int32_t o = __shfl_xor_sync(0xffffffffu, a[e], lj);
+          a[e] = take_min ? min(a[e], o) : max(a[e], o);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const int l = e ^ j;
+          if (l > e) {
+            // direction: bit k of the index l * E + e -- inside e when k < E, else in the lane number
+            const bool up = k < E ? ((e & k) == 0) : (k >= 32 * E ? true : ((lane & (k / E)) == 0));
+            const int32_t lo = min(a[e], a[l]), hi = max(a[e], a[l]);
+            a[e] = up ? lo : hi;
+            a[l] = up ? hi : lo;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int E>
+__device__ __forceinline__ void csc_sort_list(int32_t* __restrict__ list, int len, int lane) {
+  int32_t a[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) a[e] = e * 32 + lane < len ? list[e * 32 + lane] : 0x7fffffff;  // coalesced, any order
+  warp_bitonic_sort_asc<E>(a, lane);
+#pragma unroll
+  for (int e = 0; e < E; ++e)
+    if (lane * E + e < len) list[lane * E + e] = a[e];
+}
+
 __global__ void __launch_bounds__(256) csc_sort_warp_kernel(const int32_t* __restrict__ offsets,
                                                             int32_t* __restrict__ entries, int32_t* __restrict__ worklist,
                                                             int n) {
@@ -645,25 +692,13 @@ __global__ void __launch_bounds__(256) csc_sort_warp_kernel(const int32_t* __res
     return;
   }
   if (len <= 1) return;
-  int32_t v[4];
-  int rank[4] = {0, 0, 0, 0};
-#pragma unroll
-  for (int q = 0; q < 4; ++q) v[q] = lane + 32 * q < len ? entries[beg + lane + 32 * q] : 0x7fffffff;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    if (32 * q < len) {  // warp-uniform
-      const int cnt = min(32, len - 32 * q);
-      for (int j = 0; j < cnt; ++j) {
-        const int32_t w = __shfl_sync(0xffffffffu, v[q], j);
-#pragma unroll
-        for (int r = 0; r < 4; ++r) rank[r] += w < v[r];
-      }
-    }
-  }
-  __syncwarp();
-#pragma unroll
-  for (int q = 0; q < 4; ++q)
-    if (lane + 32 * q < len) entries[beg + rank[q]] = v[q];
+  int32_t* list = entries + beg;
+  if (len <= 32) csc_sort_list<1>(list, len, lane);
+  else if (len <= 64) csc_sort_list<2>(list, len, lane);
+  else if (len <= 128) csc_sort_list<4>(list, len, lane);
+  else if (len <= 256) csc_sort_list<8>(list, len, lane);
+  else if (len <= 512) csc_sort_list<16>(list, len, lane);
+  else csc_sort_list<32>(list, len, lane);
 }
 // Lists of kWarpSortMax + 1 .. kSortMax entries, queued by csc_sort_warp_kernel: a fixed grid walks the queue (one CTA
 // per feature used to be launched -- n CTAs that almost all returned at once cost 16 us at n = 24 576).
@@ -676,20 +711,6 @@ __global__ void __launch_bounds__(256) csc_sort_kernel(const int32_t* __restrict
   __syncthreads();  // buf is reused
   const int f = worklist[item];
   const int beg = offsets[f], len = offsets[f + 1] - beg;
-  if (len <= kRankSortMax) {
-    // medium lists: rank sort -- every thread counts the entries smaller than its own (shared-memory broadcast
-    // reads, one barrier) instead of ~50 barrier-separated bitonic stages
-    for (int i = threadIdx.x; i < len; i += blockDim.x) buf[i] = entries[beg + i];
-    __syncthreads();
-    for (int i = threadIdx.x; i < len; i += blockDim.x) {
-      const int32_t v = buf[i];
-      int rank = 0;
-#pragma unroll 8
-      for (int j = 0; j < len; ++j) rank += buf[j] < v;
-      entries[beg + rank] = v;
-    }
-    continue;
-  }
   int m = 2;
   while (m < len) m <<= 1;
   for (int i = threadIdx.x; i < m; i += blockDim.x) buf[i] = i < len ? entries[beg + i] : 0x7fffffff;

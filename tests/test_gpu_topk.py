@@ -418,3 +418,33 @@ def test_half_precision_activations_feed_the_fused_path_exactly(dtype):
     assert outs[0][0] == outs[1][0]
     for a, b in zip(outs[0][1:], outs[1][1:]):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("N,n", [(3000, 64), (3000, 256), (3000, 2048), (700, 32), (5000, 40000), (257, 300)])
+def test_csc_lists_are_complete_and_token_sorted(N, n):
+    """freud_csc_build: offsets = exclusive scan of the per-feature counts, and every feature's list holds exactly its
+    flat positions p = t*k + j in ascending order (the order that makes the gradient sums run-to-run deterministic):
+    warp-level bitonic sorts for lists up to 1024 entries, the CTA-wide network up to 4096; entries of other shards
+    (index -1) are left out."""
+    from freud_b200 import ops
+
+    k = 32
+    g = torch.Generator().manual_seed(N + n)
+    idx = torch.stack([torch.randperm(n, generator=g)[:k] for _ in range(N)]).to(torch.int32) if n >= k else None
+    if idx is None:
+        pytest.skip("needs n >= k")
+    idx[torch.rand(N, k, generator=g) < 0.05] = -1
+    offsets, entries = ops.csc_build(idx.cuda(), n)
+    torch.cuda.synchronize()
+    offsets, entries = offsets.cpu().long(), entries.cpu().long()
+    flat = idx.reshape(-1).long()
+    counts = torch.bincount(flat[flat >= 0], minlength=n)
+    assert torch.equal(offsets[1:] - offsets[:-1], counts)
+    order = torch.sort(flat[flat >= 0], stable=True)
+    want = torch.nonzero(flat >= 0).flatten()[order.indices]  # positions grouped by feature, ascending inside a group
+    total = int(offsets[-1])
+    lens = counts
+    sortable = torch.repeat_interleave(lens <= 4096, lens)
+    assert torch.equal(entries[:total][sortable], want[sortable])
+    # longer lists: complete, order unspecified
+    assert torch.equal(torch.sort(flat[entries[:total]]).values, torch.sort(flat[flat >= 0]).values)
