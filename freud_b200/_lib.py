@@ -32,7 +32,7 @@ SIGNATURES = {
     "freud_topk_prep_x": [_p, _i, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i, _p],
     "freud_split_operand": [_p, _p, _p, _i64, _i, _p],
     "freud_topk_encode_workspace": [_i64, _i64, _p],
-    "freud_topk_encode": [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i, _p, _i64, _p],
+    "freud_topk_encode": [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i, _p, _i64, _p, _p],
     "freud_topk_encode_stats": [_p, _i],
     "freud_gemm_nt": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i, _i, _p],
     "freud_row_topk": [_p, _p, _p, _p, _i64, _i64, _i64, _p],
@@ -59,7 +59,7 @@ SIGNATURES = {
     "freud_shard_merge": [_p, _p, _p, _p, _i64, _i64, _i64, _p],
     "freud_shard_localize": [_p, _p, _p, _p, _i64, _i64, _i64, _p],
     "freud_residual": [_p, _p, _p, _i, _p, _p, _i64, _i64, _p],
-    "freud_csc_build": [_p, _i64, _i64, _i64, _p, _p, _p, _p],
+    "freud_csc_build": [_p, _i64, _i64, _i64, _p, _p, _p, _i, _p],
     "freud_csc_meta": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _p],
     "freud_topk_sparse_grads": [_p, _p, _p, _i, _p, _i, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i, _p],
     "freud_topk_bdec_grad": [_p, _p, _p, _p, _i, _p, _i64, _i64, _i, _p],

@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(256) topk_merge_pieces_kernel(const float* __r
                                                                 const int32_t* __restrict__ part_idx,
                                                                 int64_t part_stride, float* __restrict__ top_vals,
                                                                 int32_t* __restrict__ top_idx, int M, int row0,
-                                                                int pieces) {
+                                                                int pieces, int32_t* __restrict__ hist) {
   const int lane = threadIdx.x & 31;
   const int64_t row = row0 + static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -45,6 +45,17 @@ __global__ void __launch_bounds__(256) topk_merge_pieces_kernel(const float* __r
   }
   top_vals[row * 32 + lane] = __uint_as_float(static_cast<uint32_t>(cur >> 32));
   top_idx[row * 32 + lane] = static_cast<int32_t>(~static_cast<uint32_t>(cur));
+  if (hist != nullptr) atomicAdd(hist + ~static_cast<uint32_t>(cur), 1);
+}
+
+// Per-feature counts of an index matrix: the encoder variants that do not count while they emit.
+__global__ void __launch_bounds__(256) hist_rows_kernel(const int32_t* __restrict__ top_idx, int64_t total,
+                                                        int32_t* __restrict__ hist) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int32_t f = top_idx[i];
+    if (f >= 0) atomicAdd(hist + f, 1);
+  }
 }
 
 // A batch that is not a multiple of sm_count row blocks would leave SMs idle in its last wave, so the row blocks
@@ -183,7 +194,7 @@ static int launch_gemm(const void* a_hi, const void* a_lo, const void* b_hi, con
   if (p.tail_split > 1) {
     const int row0 = p.full_count * kBM;
     topk_merge_pieces_kernel<<<(p.M - row0 + 7) / 8, 256, 0, stream>>>(p.part_vals, p.part_idx, p.part_stride, p.top_vals,
-                                                                       p.top_idx, p.M, row0, p.tail_split);
+                                                                       p.top_idx, p.M, row0, p.tail_split, p.hist);
     FREUD_CHECK_CUDA(cudaGetLastError());
   }
   return 0;
@@ -254,7 +265,7 @@ static int launch_topk(const void* a_hi, const void* a_lo, const void* b_hi, con
   if (p.tail_split > 1) {
     const int row0 = p.full_count * kBM;
     topk_merge_pieces_kernel<<<(p.M - row0 + 7) / 8, 256, 0, stream>>>(p.part_vals, p.part_idx, p.part_stride, p.top_vals,
-                                                                       p.top_idx, p.M, row0, p.tail_split);
+                                                                       p.top_idx, p.M, row0, p.tail_split, p.hist);
     FREUD_CHECK_CUDA(cudaGetLastError());
   }
   return 0;
@@ -288,7 +299,8 @@ extern "C" int freud_topk_encode_workspace(int64_t N, int64_t n, int64_t* bytes)
 
 extern "C" int freud_topk_encode(const void* xc_hi, const void* xc_lo, const void* w_hi, const void* w_lo,
                                  const float* b_enc, float* top_vals, int32_t* top_idx, int64_t N, int64_t d,
-                                 int64_t n, int precision, void* workspace, int64_t workspace_bytes, void* stream) {
+                                 int64_t n, int precision, void* workspace, int64_t workspace_bytes, int32_t* hist,
+                                 void* stream) {
   FREUD_REQUIRE(N > 0 && d > 0 && n >= 64, "freud_topk_encode needs N > 0 and n >= 64");
   FREUD_REQUIRE(d % 8 == 0, "activation size must be a multiple of 8");
   FREUD_REQUIRE(N < (1ll << 31) && n < (1ll << 31), "sizes exceed int32");
@@ -303,6 +315,18 @@ extern "C" int freud_topk_encode(const void* xc_hi, const void* xc_lo, const voi
   p.part_vals = static_cast<float*>(workspace);  // launch_gemm turns these two into the tail-split plan
   p.part_stride = workspace ? workspace_bytes : 0;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // the specialised kernel counts while it emits; the experiment variants get a separate counting pass
+  const int variant = encoder_variant();
+  const bool counts_inline = variant == 0 || variant == 4 || variant == 5 || variant > 8 || precision == FREUD_FP32;
+  p.hist = counts_inline && !(precision == FREUD_FP32 && variant == 1) ? hist : nullptr;
+  if (hist != nullptr && p.hist == nullptr) {
+    const int rc = freud_topk_encode(xc_hi, xc_lo, w_hi, w_lo, b_enc, top_vals, top_idx, N, d, n, precision, workspace,
+                                     workspace_bytes, nullptr, stream);
+    if (rc) return rc;
+    hist_rows_kernel<<<sm_count() * 4, 256, 0, s>>>(top_idx, N * 32, hist);
+    FREUD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (precision == FREUD_BF16) {
     switch (encoder_variant()) {
       case 1: return launch_gemm<256, 3, EPI_TOPK, false, 2, 1>(xc_hi, nullptr, w_hi, nullptr, p, 1, s);

@@ -108,6 +108,9 @@ struct GemmParams {
   int tma_out;
   int tma_in;   // EPI_RESID target / EPI_MASK mask_src arrive as TMA boxes (needs tma_out: the smem budget assumes both)
   int64_t lda, ldb;  // host side only: row pitch (elements) of the A / B matrix as stored; 0 = dense
+  // fused top-k encoder: per-feature counts of the emitted indices (the histogram the CSC index of the backward starts
+  // from), accumulated with one atomic per emitted entry as rows are written; nullptr = not wanted
+  int32_t* hist;
   unsigned long long* stats;  // diagnostic build of the top-k encoder (freud_topk_encode_stats), else nullptr
   int flags;  // experiments (FREUD_ENC_FLAGS): bit 0 = do not share 16th-largest values between the epilogue sets;
               // bits 1-4 = bare spin (no sleep between polls) in the producer / MMA-empty / MMA-full / epilogue waits

@@ -1458,12 +1458,14 @@ extern "C" int freud_sum_splits(const float* parts, float* out, int64_t splits, 
 }
 
 extern "C" int freud_csc_build(const int32_t* top_idx, int64_t N, int64_t k, int64_t n, int32_t* offsets,
-                               int32_t* entries, int32_t* cursor, void* stream) {
+                               int32_t* entries, int32_t* cursor, int counts_ready, void* stream) {
   const int64_t total = N * k;
   FREUD_REQUIRE(total > 0 && total < (1ll << 31) && n > 0 && n < (1ll << 31), "csc sizes out of range");
-  FREUD_CHECK_CUDA(cudaMemsetAsync(offsets, 0, (n + 1) * sizeof(int32_t), STREAM));
   const int grid = grid_for(total, 256, sm_count() * 8);
-  csc_hist_kernel<<<grid, 256, 0, STREAM>>>(top_idx, total, offsets);
+  if (!counts_ready) {  // else offsets[0..n) already holds the per-feature counts (freud_topk_encode's hist output)
+    FREUD_CHECK_CUDA(cudaMemsetAsync(offsets, 0, (n + 1) * sizeof(int32_t), STREAM));
+    csc_hist_kernel<<<grid, 256, 0, STREAM>>>(top_idx, total, offsets);
+  }
   csc_scan_kernel<<<1, 1024, 0, STREAM>>>(offsets, cursor, (int)n);
   csc_fill_kernel<<<grid, 256, 0, STREAM>>>(top_idx, total, cursor, entries);
   csc_sort_warp_kernel<<<(int)((n + 7) / 8), 256, 0, STREAM>>>(offsets, entries, cursor, (int)n);

@@ -440,6 +440,10 @@ sm100_topk_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                                                        static_cast<int>(~static_cast<uint32_t>(surv[s + 2])),
                                                        static_cast<int>(~static_cast<uint32_t>(surv[s + 3])));
         }
+        if (whole && p.hist != nullptr) {
+#pragma unroll
+          for (int s = 0; s < kTopK; ++s) atomicAdd(p.hist + ~static_cast<uint32_t>(surv[s]), 1);
+        }
       } else {
         // survivors are sorted, so the valid ones are surv[0 .. nvalid); the tail takes the free indices
         // (a piece fills from its own first column: across pieces the merge keeps the lowest indices)
@@ -461,6 +465,7 @@ sm100_topk_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
           }
           ov[s] = val;
           oi[s] = static_cast<int32_t>(idx);
+          if (whole && p.hist != nullptr) atomicAdd(p.hist + idx, 1);
         }
       }
     }

@@ -87,8 +87,9 @@ def topk_encode_workspace_bytes(N: int, n: int) -> int:
     return need.value
 
 
-def topk_encode(xc_hi, xc_lo, w_hi, w_lo, b_enc, precision: int):
-    """Fused GEMM + bias + ReLU + top-32.  Returns (top_vals fp32 [N,32], top_idx int32 [N,32])."""
+def topk_encode(xc_hi, xc_lo, w_hi, w_lo, b_enc, precision: int, hist=None):
+    """Fused GEMM + bias + ReLU + top-32.  Returns (top_vals fp32 [N,32], top_idx int32 [N,32]).
+    hist: optional zeroed int32 [>= n] that receives the per-feature counts of the emitted indices (csc_build's start)."""
     N, d = xc_hi.shape
     n = w_hi.shape[0]
     vals = torch.empty((N, K_FUSED), dtype=torch.float32, device=xc_hi.device)
@@ -96,7 +97,7 @@ def topk_encode(xc_hi, xc_lo, w_hi, w_lo, b_enc, precision: int):
     need = topk_encode_workspace_bytes(N, n)
     ws = torch.empty(need, dtype=torch.uint8, device=xc_hi.device) if need else None
     call("freud_topk_encode", _ptr(xc_hi), _ptr(xc_lo), _ptr(w_hi), _ptr(w_lo), _ptr(b_enc), _ptr(vals), _ptr(idx),
-         N, d, n, precision, _ptr(ws), need, _stream())
+         N, d, n, precision, _ptr(ws), need, _ptr(hist), _stream())
     return vals, idx
 
 
@@ -374,13 +375,16 @@ def residual(sae_out, target, resid_dtype, want_colsum=True):
 
 
 # ------------------------------------------------------------------------------------------------ TopK backward
-def csc_build(top_idx: torch.Tensor, n: int):
+def csc_build(top_idx: torch.Tensor, n: int, counts=None):
+    """Feature-major index of the selected entries.  counts: int32 [n+1] already holding the per-feature counts
+    (topk_encode's hist); it becomes the offsets array."""
     N, k = top_idx.shape
     dev = top_idx.device
-    offsets = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    offsets = counts if counts is not None else torch.empty(n + 1, dtype=torch.int32, device=dev)
     entries = torch.empty(N * k, dtype=torch.int32, device=dev)
     cursor = torch.empty(n + 1, dtype=torch.int32, device=dev)  # fill cursors, then the long-list sort queue + its counter
-    call("freud_csc_build", _ptr(top_idx), N, k, n, _ptr(offsets), _ptr(entries), _ptr(cursor), _stream())
+    call("freud_csc_build", _ptr(top_idx), N, k, n, _ptr(offsets), _ptr(entries), _ptr(cursor),
+         int(counts is not None), _stream())
     return offsets, entries
 
 

@@ -130,8 +130,12 @@ def topk_forward(x, W_enc, b_enc, W_dec, b_dec, k, *, precision, dead_mask=None,
     zero = torch.zeros((), dtype=torch.float32, device=x.device)
 
     pre = None
+    side_csc = (fused_main and need_grad and not generic and os.environ.get("FREUD_CSC_MODE", "side") != "serial")
+    counts = None
     if fused_main:
-        vals, idx = ops.topk_encode(xc_hi, xc_lo, we_hi, we_lo, b_enc, precision)
+        if side_csc:  # the encoder counts the entries per feature while it writes its rows: the CSC build starts there
+            counts = torch.zeros(n + 1, dtype=torch.int32, device=x.device)
+        vals, idx = ops.topk_encode(xc_hi, xc_lo, we_hi, we_lo, b_enc, precision, hist=counts)
         if precision == FP32:
             ops.topk_refine(x2, b_dec, W_enc, b_enc, idx, vals)
     else:
@@ -139,13 +143,13 @@ def topk_forward(x, W_enc, b_enc, W_dec, b_dec, k, *, precision, dead_mask=None,
         vals, idx = ops.row_topk(pre, k)
 
     csc = None
-    if fused_main and need_grad and not generic and os.environ.get("FREUD_CSC_MODE", "side") != "serial":
+    if side_csc:
         # the feature-major (CSC) index of the backward depends on the indices alone: built on a side stream while
         # the main stream decodes and forms the activation gradients
         cur, side = torch.cuda.current_stream(), aux_stream(x.device)
         side.wait_stream(cur)
         with torch.cuda.stream(side):
-            offsets, entries = ops.csc_build(idx, n)
+            offsets, entries = ops.csc_build(idx, n, counts=counts)
             csc_done = side.record_event()
         idx.record_stream(side)
         offsets.record_stream(cur)

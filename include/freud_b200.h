@@ -53,11 +53,13 @@ int freud_split_operand(const float* w, void* hi, void* lo, int64_t numel, int p
  * One CTA scans all column tiles of a 128-token row block.  When N is not a multiple of 148 row blocks, the row
  * blocks of the last wave are cut into column ranges scanned by separate CTAs and merged afterwards; this needs
  * `workspace` of freud_topk_encode_workspace(N, n) bytes (may be 0).  With workspace == NULL (or too small) the
- * last wave simply runs with idle SMs; results are identical. */
+ * last wave simply runs with idle SMs; results are identical.  * hist (optional, int32 [n], zeroed by the caller): receives the number of emitted entries per feature -- the
+ * histogram freud_csc_build starts from (pass it there as `offsets` with counts_ready = 1), counted with one atomic
+ * per entry while the rows are written instead of in a pass of its own. */
 int freud_topk_encode_workspace(int64_t N, int64_t n, int64_t* bytes);
 int freud_topk_encode(const void* xc_hi, const void* xc_lo, const void* w_hi, const void* w_lo,
                       const float* b_enc, float* top_vals, int32_t* top_idx,
-                      int64_t N, int64_t d, int64_t n, int precision, void* workspace, int64_t workspace_bytes,
+                      int64_t N, int64_t d, int64_t n, int precision, void* workspace, int64_t workspace_bytes, int32_t* hist,
                       void* stream);
 
 /* Diagnostic (FREUD_ENC_STATS=1 selects an instrumented build of the encoder kernel): clock64 cycle counters summed over
@@ -208,7 +210,7 @@ int freud_residual(const float* sae_out, const float* target, void* resid, int r
  * workspace (fill cursors, then the queue of long lists for the sort pass and its counter).  Every list of up to 4096
  * entries is token-ordered, so the gradient sums are run-to-run deterministic.  Also the did_fire bookkeeping of train_sae.py:442 (offsets[f+1] > offsets[f]). */
 int freud_csc_build(const int32_t* top_idx, int64_t N, int64_t k, int64_t n, int32_t* offsets,
-                    int32_t* entries, int32_t* cursor, void* stream);
+                    int32_t* entries, int32_t* cursor, int counts_ready, void* stream);
 
 /* Row-sparse weight gradients of one decode (autograd of :17-18 and of nn.Linear, :75):
  *   dW_dec[f,:] (+)= s_dec * sum_{p in list(f)} top_vals[p] * g[t(p),:]

@@ -2,7 +2,7 @@
 # epilogue-input prefetch (L2 prefetch warp + one-chunk-ahead registers), col_sum rewrite, interpolated masked top-k,
 # rank-sorted CSC long lists: whole GPU suite, then AuxK-live / L1 per-call breakdowns and C2/C3 bench lines
 set -u
-O=gpurun_out/c22
+O=gpurun_out/c43
 mkdir -p $O
 timeout 1500 python -m pytest tests -m gpu -x -q > $O/pytest.log 2>&1
 tail -4 $O/pytest.log

@@ -36,7 +36,7 @@ def test_c_abi_argument_errors_are_reported_not_thrown(built_lib):
     from freud_b200 import _lib
 
     with pytest.raises(RuntimeError, match="n >= 64"):
-        _lib.call("freud_topk_encode", None, None, None, None, None, None, None, 128, 64, 8, 0, None, 0, None)
+        _lib.call("freud_topk_encode", None, None, None, None, None, None, None, 128, 64, 8, 0, None, 0, None, None)
     assert b"n >= 64" in _lib.lib().freud_last_error()
 
 
