@@ -16,7 +16,7 @@ out = {}
 peaks = bench.measured_peaks()
 
 
-def timed(fn, iters, warm=2):
+def timed(fn, iters, warm=4):
     for i in range(warm):
         fn(i)
     torch.cuda.synchronize()
@@ -49,7 +49,9 @@ for wl, prec, dead_frac in (("c3", "bf16", 0.0), ("c3", "bf16", 0.1), ("c2", "bf
     ms = timed(step, 8)
     out[f"topk_step.{wl}.{prec}.dead{int(dead_frac * 100)}"] = {
         "ms_per_step": ms, "tokens_per_s": w["B"] * w["T"] / ms * 1e3}
-    del tr, xs
+    del tr, xs, step  # (the closure's default arguments hold the trainer and its batches)
+    import gc
+    gc.collect()
     torch.cuda.empty_cache()
 
 # ---- L1 step, C1 (configs/train/tiny_l1.json: d=384, n=200, B=100, RAdam 4e-4, cosine, recon_alpha 1e4)

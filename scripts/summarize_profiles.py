@@ -118,5 +118,6 @@ def full_captures():
 
 bench_lines()
 launch_list()
-full_captures()
+if '--no-ncu' not in sys.argv:
+    full_captures()
 print(sorted(os.listdir(out)))
