@@ -15,7 +15,10 @@ AuxK (topkautoencoder.py:109-127) follows the same pattern once a latent can be 
 k_aux = min(d/2, num_dead) pre-activations among ITS dead latents, the candidate lists are all-gathered, the global
 top-k_aux is taken from them (value descending, dictionary index ascending -- rank-major concatenation keeps that
 order), each rank decodes the winners it owns, and the partial e_hat is all-reduced.  Its backward is rank-local like
-the main one.  multi-TopK is not offered in this mode; the data-parallel mode has it.
+the main one.  multi-TopK (topkautoencoder.py:129-138: a second decode of the top 4k latents, its FVU weighted 1/8) is
+selected the same way over ALL latents of every shard (local top-4k of the materialised shard pre-activations ->
+all-gather -> global top-4k), decoded in parts and all-reduced; as in the reference, the returned reconstruction /
+activations / indices and the did_fire bookkeeping are then those of the 4k selection.
 """
 from __future__ import annotations
 
@@ -33,7 +36,7 @@ _KEYS = ("encoder.weight", "encoder.bias", "W_dec", "b_dec")
 class FeatureShardedTopKTrainer:
     def __init__(self, full_state: dict, k: int, *, lr, steps, clip_thresh=1.0, scheduler="linear",
                  scheduler_params=None, precision="bf16", device=None, group=None, auxk_alpha=0.0,
-                 dead_feature_threshold=None):
+                 dead_feature_threshold=None, multi_topk=False):
         """full_state: the reference state_dict (W_dec, b_dec, encoder.weight, encoder.bias) -- every rank slices
         its own rows, so a checkpoint written by the single-GPU model loads unchanged."""
         if not dist.is_initialized():
@@ -69,6 +72,7 @@ class FeatureShardedTopKTrainer:
         self.num_frames_since_fired = torch.zeros(self.n_local, device=dev, dtype=torch.long)
         self.device = dev
         self.auxk_alpha = float(auxk_alpha)
+        self.multi_topk = bool(multi_topk)
         self.dead_feature_threshold = dead_feature_threshold
         self.tokens_seen = 0
 
@@ -127,7 +131,9 @@ class FeatureShardedTopKTrainer:
         g = {k_: p.grad for k_, p in zip(_KEYS, self.plist)}
         xc = xc_hi if prec == BF16 else x2
         auxk = torch.zeros((), dtype=torch.float32, device=x.device)
-        if num_dead == 0:
+        mfvu = torch.zeros((), dtype=torch.float32, device=x.device)
+        ret_vals, ret_gidx, ret_out = top_vals, top_gidx, sae_out
+        if num_dead == 0 and not self.multi_topk:
             rdt = torch.bfloat16 if prec == BF16 else torch.float32
             e, sse, colsum_e = ops.residual(sae_out, x2, rdt)
             scal = ops.topk_loss_scalars(sse, tv, N * d)
@@ -142,24 +148,35 @@ class FeatureShardedTopKTrainer:
         else:
             e, sse, colsum_e = ops.residual(sae_out, x2, torch.float32)
             scal = ops.topk_loss_scalars(sse, tv, N * d)
-            k_aux = d // 2
-            scale = min(num_dead / k_aux, 1.0)
-            k_aux = min(k_aux, num_dead)
-            a_vals, a_gidx = self._auxk_select(xc_hi, xc_lo, we_hi, we_lo, b_enc, dead_local, k_aux, N, prec)
-            a_own_vals, a_own_idx = ops.shard_localize(a_vals, a_gidx, self.lo, self.n_local)
-            partial, _, _, _ = ops.topk_decode(a_own_vals, a_own_idx, wd, bias)
-            e_hat = self._allreduce(partial)
-            r_aux, sse_aux, _ = ops.residual(e_hat, e, torch.float32, want_colsum=False)  # e_hat - e, e not detached
-            auxk = (scale * sse_aux[0] / scal[4].double()).float() * self.auxk_alpha
-            # ---- backward (rank-local) through the generic engine path: two decodes (main, aux) on this shard's rows;
-            # replicated terms (the direct b_dec gradient) enter on rank 0 only, the sum over ranks completes them
+            # ---- backward (rank-local) through the generic engine path: one decode per selection (main, aux, 4k) on
+            # this shard's rows; replicated terms (the direct b_dec gradient) enter on rank 0 only, the sum over ranks
+            # completes them
             st = topk_engine.TopKState(prec, x2, xc_hi, wd, we_hi if prec == BF16 else W_enc, b_dec, k, self.n_local,
                                        scal, True, own_vals,
                                        own_idx, e, colsum_e if self.rank == 0 else torch.zeros_like(colsum_e),
                                        auxk_alpha=self.auxk_alpha)
-            st.aux = (a_own_vals, a_own_idx, r_aux, scale)
-            topk_engine.topk_backward(st, 1.0, 1.0, None, out=g)
-            offsets = st.offsets
+            if num_dead > 0:
+                k_aux = d // 2
+                scale = min(num_dead / k_aux, 1.0)
+                k_aux = min(k_aux, num_dead)
+                a_vals, a_gidx = self._select_over_shards(xc_hi, xc_lo, we_hi, we_lo, b_enc, dead_local, k_aux, N, prec)
+                a_own_vals, a_own_idx = ops.shard_localize(a_vals, a_gidx, self.lo, self.n_local)
+                partial, _, _, _ = ops.topk_decode(a_own_vals, a_own_idx, wd, bias)
+                e_hat = self._allreduce(partial)
+                r_aux, sse_aux, _ = ops.residual(e_hat, e, torch.float32, want_colsum=False)  # e_hat - e, e not detached
+                auxk = (scale * sse_aux[0] / scal[4].double()).float() * self.auxk_alpha
+                st.aux = (a_own_vals, a_own_idx, r_aux, scale)
+            if self.multi_topk:
+                m_vals, m_gidx = self._select_over_shards(xc_hi, xc_lo, we_hi, we_lo, b_enc, None, 4 * k, N, prec)
+                m_own_vals, m_own_idx = ops.shard_localize(m_vals, m_gidx, self.lo, self.n_local)
+                partial, _, _, _ = ops.topk_decode(m_own_vals, m_own_idx, wd, bias)
+                m_out = self._allreduce(partial)
+                r_m, sse_m, colsum_m = ops.residual(m_out, x2, torch.float32)
+                mfvu = (sse_m[0] / scal[4].double()).float()
+                st.multi = (m_own_vals, m_own_idx, r_m, colsum_m if self.rank == 0 else torch.zeros_like(colsum_m))
+                ret_vals, ret_gidx, ret_out = m_vals, m_gidx, m_out  # the reference rebinds its outputs (:133-138)
+            topk_engine.topk_backward(st, 1.0, 1.0, 1.0 / 8.0, out=g)
+            offsets = st.offsets  # of the returned encoding
         self._allreduce(g["b_dec"])                                                     # [d]
         # ---- global-norm clip + Adam: b_dec's gradient is replicated, count it once
         tl_local = ops.make_tensor_list([p.data for p in self.plist[:3]], [p.grad for p in self.plist[:3]])
@@ -172,16 +189,25 @@ class FeatureShardedTopKTrainer:
         self.scheduler.step()
         ops.dead_latent_update(offsets, self.num_frames_since_fired, N)
         self.tokens_seen += N
-        return {"loss": scal[0] + auxk, "fvu": scal[0], "auxk_loss": auxk, "grad_sumsq": sumsq, "top_idx": top_gidx,
-                "top_acts": top_vals, "sae_out": sae_out}
+        return {"loss": scal[0] + auxk + mfvu / 8, "fvu": scal[0], "auxk_loss": auxk, "multi_topk_fvu": mfvu,
+                "grad_sumsq": sumsq, "top_idx": ret_gidx, "top_acts": ret_vals, "sae_out": ret_out}
 
-    def _auxk_select(self, xc_hi, xc_lo, we_hi, we_lo, b_enc, dead_local, k_aux, N, prec):
-        """Global top-k_aux pre-activations among the dead latents of all shards: (vals [N,k_aux], global idx)."""
+    def _select_over_shards(self, xc_hi, xc_lo, we_hi, we_lo, b_enc, subset, k_aux, N, prec):
+        """Global top-k_aux pre-activations over the latents of all shards -- among this rank's `subset` (bool mask over
+        its rows: the dead latents, AuxK) or among all of them (None: multi-TopK): (vals [N,k_aux], global idx)."""
         dev = xc_hi.device
         lv = torch.full((N, k_aux), -1.0, dtype=torch.float32, device=dev)   # absent candidates lose to relu(.) >= 0
         lg = torch.full((N, k_aux), -1, dtype=torch.int32, device=dev)
-        dead_idx = torch.nonzero(dead_local).squeeze(1).to(torch.int32)
-        S = dead_idx.numel()
+        if subset is None:
+            pre = ops.gemm_nt(xc_hi, xc_lo, we_hi, we_lo, b_enc, True, prec)            # [N, n_local] fp32
+            kk = min(k_aux, self.n_local)
+            v, loc = ops.row_topk(pre, kk)                                              # (value desc, index asc)
+            lv[:, :kk] = v
+            lg[:, :kk] = loc + self.lo
+            S = 0
+        else:
+            dead_idx = torch.nonzero(subset).squeeze(1).to(torch.int32)
+            S = dead_idx.numel()
         if S > 0:
             ws_hi = ops.gather_rows(we_hi, dead_idx)
             ws_lo = ops.gather_rows(we_lo, dead_idx) if we_lo is not None else None
