@@ -222,3 +222,21 @@ def test_encoder_tail_split_plan_sizes():
         assert 2 <= S <= 16 and 2 * S <= -(-n // 256)
     with pytest.raises(RuntimeError):
         need(128, 8)                                                         # n < 64 is rejected like the encoder
+
+
+def test_fused_dp_flat_layout_plan():
+    """freud_b200.fused_dp.plan_flat_layout (pure host logic of the fused data-parallel optimiser): every tensor starts
+    on a 128-byte boundary, the per-rank slices tile the padded space without gaps or overlap and have equal,
+    128-byte-multiple lengths (the kernels' 16-byte vector paths and the 8-element bf16 stores rely on it)."""
+    from freud_b200.fused_dp import plan_flat_layout
+
+    for numels, world in (([24576 * 768, 24576, 24576 * 768, 768], 8), ([1000 * 33, 1001, 1000 * 33, 33], 2),
+                          ([7, 5, 3], 4), ([81920 * 1280, 81920, 81920 * 1280, 1280], 3)):
+        offs, total, slices = plan_flat_layout(numels, world)
+        assert all(o % 32 == 0 for o in offs)
+        assert all(offs[i] + numels[i] <= offs[i + 1] for i in range(len(numels) - 1))
+        assert offs[-1] + numels[-1] <= total
+        assert len(slices) == world and slices[0][0] == 0 and slices[-1][1] == total
+        assert all(slices[r][1] == slices[r + 1][0] for r in range(world - 1))
+        lens = {hi - lo for lo, hi in slices}
+        assert len(lens) == 1 and lens.pop() % 32 == 0
