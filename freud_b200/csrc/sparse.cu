@@ -793,8 +793,10 @@ __global__ void __launch_bounds__(256) csc_meta_kernel(const int32_t* __restrict
 // features, so the gradient matrices need no memset.  Rows of long lists are zeroed here and accumulated by the
 // chunk kernel.  Lanes past the row end (last slab of a row that is not a multiple of 32 slices) gather column 0
 // and skip the stores, so the warp never diverges.
+// (launch bound of four CTAs per SM: 64 registers with a 4-byte spill instead of 80 -- 32 resident warps instead of 24
+//  was worth 8 % on a kernel that lives on memory-level parallelism)
 template <typename GT, typename XT>
-__global__ void __launch_bounds__(256) sparse_grads_warp_kernel(
+__global__ void __launch_bounds__(256, 4) sparse_grads_warp_kernel(
     const int32_t* __restrict__ offsets, const int32_t* __restrict__ tok, const float* __restrict__ a_sc,
     const float* __restrict__ dp_sc, const GT* __restrict__ g, const XT* __restrict__ xc,
     const float* __restrict__ b_dec, float* __restrict__ dW_dec, float* __restrict__ dW_enc,
