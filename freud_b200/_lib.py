@@ -40,10 +40,7 @@ SIGNATURES = {
     "freud_index_map": [_p, _p, _p, _i64, _p],
     "freud_row_topk_mask": [_p, _p, _i64, _i64, _i64, _i64, _i64, _i, _p],
     "freud_col_sum_bf16": [_p, _p, _i64, _i64, _i64, _p],
-    "freud_transpose_bf16": [_p, _p, _i64, _i64, _i64, _i64, _p],
-    "freud_mask_grad": [_p, _p, _p, _p, _i64, _i64, _i64, _p],
     "freud_scatter_add_rows": [_p, _p, _p, _i64, _i64, _p],
-    "freud_gemm_nt_splitk": [_p, _p, _p, _i64, _i64, _i64, _i64, _p],
     "freud_sum_splits": [_p, _p, _i64, _i64, _p],
     "freud_gemm_nt_mask": [_p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _p],
     "freud_l1_encode_fused": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _p],
@@ -72,7 +69,6 @@ SIGNATURES = {
     "freud_l1_loss_reduce": [_p, _p, _p, _p, _p, _i64, _i64, _i64, _p],
     "freud_l1_dz": [_p, _p, _p, _p, _i64, _i64, _p],
     "freud_l1_weight_grad": [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _p],
-    "freud_l1_grad_operands": [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _p],
     "freud_grad_sumsq": [C.POINTER(TensorList), _p, _p],
     "freud_clip_grads": [C.POINTER(TensorList), _p, _f, _p, _p],
     "freud_adam_step": [C.POINTER(TensorList), _d, _d, _d, _d, _i64, _p, _f, _p],
@@ -91,11 +87,11 @@ SIGNATURES = {
 # CUDA kernels each entry point enqueues (memsets not counted); bench.py sums these into `gpu_launches`
 KERNELS_PER_CALL = {
     "freud_topk_prep_x": 1, "freud_split_operand": 1, "freud_topk_encode_workspace": 0, "freud_topk_encode": 2, "freud_topk_encode_stats": 0, "freud_gemm_nt": 1,
-    "freud_row_topk": 1, "freud_gather_rows": 1, "freud_index_map": 1, "freud_row_topk_mask": 1, "freud_col_sum_bf16": 1, "freud_transpose_bf16": 1, "freud_mask_grad": 1, "freud_scatter_add_rows": 1, "freud_gemm_nt_splitk": 1, "freud_sum_splits": 1, "freud_gemm_nt_mask": 1, "freud_l1_encode_fused": 1, "freud_l1_decode_fused": 1, "freud_gemm_tn_splitk": 1, "freud_gemm_nn": 1,
+    "freud_row_topk": 1, "freud_gather_rows": 1, "freud_index_map": 1, "freud_row_topk_mask": 1, "freud_col_sum_bf16": 1, "freud_scatter_add_rows": 1, "freud_sum_splits": 1, "freud_gemm_nt_mask": 1, "freud_l1_encode_fused": 1, "freud_l1_decode_fused": 1, "freud_gemm_tn_splitk": 1, "freud_gemm_nn": 1,
     "freud_topk_decode": 1, "freud_topk_dacts": 1, "freud_topk_decode_dacts": 1, "freud_topk_decode_dacts_supported": 0, "freud_topk_refine": 1, "freud_axpby": 1, "freud_shard_merge": 1, "freud_shard_localize": 1, "freud_residual": 1, "freud_csc_build": 5,
     "freud_csc_meta": 1, "freud_topk_sparse_grads": 3, "freud_topk_bdec_grad": 1, "freud_topk_loss_scalars": 1,
     "freud_dead_latent_update": 1, "freud_rownorm_project": 1, "freud_remove_parallel_grad": 1,
-    "freud_l1_colnorm": 1, "freud_l1_loss_scalars": 1, "freud_l1_loss_reduce": 1, "freud_l1_dz": 1, "freud_l1_weight_grad": 1, "freud_l1_grad_operands": 1,
+    "freud_l1_colnorm": 1, "freud_l1_loss_scalars": 1, "freud_l1_loss_reduce": 1, "freud_l1_dz": 1, "freud_l1_weight_grad": 1, 
     "freud_grad_sumsq": 1, "freud_clip_grads": 1, "freud_adam_step": 1, "freud_radam_step": 1,
     "freud_dp_reduce_scatter": 1, "freud_dp_adam_allgather": 1,
     "freud_feature_absmax": 1, "freud_col_absmax": 1,

@@ -375,27 +375,6 @@ extern "C" int freud_gemm_nt(const void* a_hi, const void* a_lo, const void* b_h
   FREUD_REQUIRE(false, "unknown precision");
 }
 
-// Split-K variant for "weight-gradient shaped" products (few output rows, very long K): `splits` partial results are
-// written to workspace [splits, M, N] and summed into out by freud_sum_splits.
-extern "C" int freud_gemm_nt_splitk(const void* a_hi, const void* b_hi, float* workspace, int64_t M, int64_t N, int64_t K,
-                                    int64_t splits, void* stream) {
-  FREUD_REQUIRE(M > 0 && N > 0 && K > 0 && splits >= 1, "empty split-K GEMM");
-  FREUD_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "sizes exceed int32");
-  FREUD_REQUIRE(K % 8 == 0, "K must be a multiple of 8 for bf16 operands");
-  GemmParams p{};
-  p.M = static_cast<int>(M);
-  p.N = static_cast<int>(N);
-  p.K = static_cast<int>(K);
-  p.out = workspace;
-  p.ldo = N;
-  const int total_kb = static_cast<int>((K + 63) / 64);
-  p.kb_per_split = static_cast<int>((total_kb + splits - 1) / splits);
-  FREUD_REQUIRE((total_kb + p.kb_per_split - 1) / p.kb_per_split == splits,
-                "splits must equal ceil(k_blocks / ceil(k_blocks / splits)) so that no partial is left unwritten");
-  p.split_stride = M * N;
-  return launch_gemm<256, 3, EPI_STORE, false, 2, 1>(a_hi, nullptr, b_hi, nullptr, p, 1, static_cast<cudaStream_t>(stream));
-}
-
 // Products whose operands are stored "the other way round" (MN-major operands, see sm100_gemm_kernel):
 //   freud_gemm_tn_splitk : out[M, N] = A^T B with A stored [K, lda >= M] and B stored [K, ldb >= N], both bf16 and
 //                          row-major -- the weight-gradient shape (K = tokens); `splits` fp32 partials go to

@@ -156,95 +156,8 @@ __global__ void __launch_bounds__(256) l1_weight_grad_kernel(const float* __rest
     }
 }
 
-// bf16 mode: the tied weight gradient is a real GEMM with K = tokens, so it runs on the tensor cores.  This kernel
-// builds its two K-major bf16 operands in one pass over the fp32 activations (128-token x 64-column tiles through shared memory):
-//   At [d, 2*Np]:  At[i, t] = s0 * x[t,i]            At[i, Np + t] = s1 * dxhat[t,i]
-//   Bt [n, 2*Np]:  Bt[j, t] = dz[t,j]                Bt[j, Np + t] = c[t,j]
-// with dz = c > 0 ? s_recon * dc + s_l1 : 0 formed on the fly (never stored in fp32) and its column sums -> db.
-// Np = tokens rounded up to a multiple of 64 (zero padded), so dW = At @ Bt^T with K = 2*Np.
-// grid: (ceil(max(d,n)/64), ceil(Np/128), 4);  blockIdx.z: 0 x, 1 dxhat, 2 dz, 3 latent.  scales = (s_recon, s_l1, s0, s1).
-constexpr int kPackTok = 128;  // tokens per tile
-__global__ void __launch_bounds__(256) l1_grad_pack_kernel(const float* __restrict__ x, const float* __restrict__ dxhat,
-                                                           const float* __restrict__ dc,
-                                                           const float* __restrict__ latent,
-                                                           const float* __restrict__ scales,
-                                                           __nv_bfloat16* __restrict__ At,
-                                                           __nv_bfloat16* __restrict__ Bt, float* __restrict__ db,
-                                                           int64_t N, int64_t Np, int d, int n) {
-  __shared__ float tile[kPackTok][65];
-  __shared__ float colsum_s[64];
-  const int which = blockIdx.z;
-  const int cols = which < 2 ? d : n;
-  const int c0 = blockIdx.x * 64;
-  if (c0 >= cols) return;
-  const int64_t t0 = static_cast<int64_t>(blockIdx.y) * kPackTok;
-  const int q = (threadIdx.x & 15) * 4, r0 = threadIdx.x >> 4;
-  const float s_recon = scales[0], s_l1 = scales[1];
-  const float mul = which == 0 ? scales[2] : (which == 1 ? scales[3] : 1.f);
-  const float* src = which == 0 ? x : (which == 1 ? dxhat : (which == 2 ? dc : latent));
-  if (which == 2 && threadIdx.x < 64) colsum_s[threadIdx.x] = 0.f;
-  const bool vec = (cols & 3) == 0 && c0 + q + 3 < cols;
-  float4 v[kPackTok / 16], lat[kPackTok / 16];
-#pragma unroll
-  for (int p = 0; p < kPackTok / 16; ++p) {
-    const int64_t t = t0 + r0 + 16 * p;
-    v[p] = make_float4(0, 0, 0, 0);
-    lat[p] = make_float4(0, 0, 0, 0);
-    if (t < N) {
-      const float* ps = src + t * cols + c0 + q;
-      const float* pl = latent + t * cols + c0 + q;
-      if (vec) {
-        v[p] = __ldcs(reinterpret_cast<const float4*>(ps));
-        if (which == 2) lat[p] = __ldcs(reinterpret_cast<const float4*>(pl));
-      } else {
-        float* pv = &v[p].x;
-        float* pq = &lat[p].x;
-        for (int u = 0; u < 4; ++u)
-          if (c0 + q + u < cols) {
-            pv[u] = ps[u];
-            if (which == 2) pq[u] = pl[u];
-          }
-      }
-    }
-  }
-  float cs[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int p = 0; p < kPackTok / 16; ++p) {
-    float e[4] = {v[p].x, v[p].y, v[p].z, v[p].w};
-    const float l[4] = {lat[p].x, lat[p].y, lat[p].z, lat[p].w};
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (which == 2) {
-        e[u] = l[u] > 0.f ? fmaf(s_recon, e[u], s_l1) : 0.f;  // zero for padding rows / columns: latent = 0 there
-        cs[u] += e[u];
-      } else {
-        e[u] *= mul;
-      }
-      tile[r0 + 16 * p][q + u] = e[u];
-    }
-  }
-  __syncthreads();
-  if (which == 2) {
-#pragma unroll
-    for (int u = 0; u < 4; ++u) atomicAdd(colsum_s + q + u, cs[u]);
-  }
-  __nv_bfloat16* dst = (which < 2 ? At : Bt) + ((which & 1) ? Np : 0) + t0;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int c = w; c < 64; c += 8) {
-    if (c0 + c >= cols) break;
-    __nv_bfloat16* row = dst + static_cast<int64_t>(c0 + c) * (2 * Np);
-#pragma unroll
-    for (int h = 0; h < kPackTok / 64; ++h) {
-      if (t0 + 64 * h >= Np) break;
-      const __nv_bfloat162 pr = __floats2bfloat162_rn(tile[64 * h + 2 * lane][c], tile[64 * h + 2 * lane + 1][c]);
-      __stcs(reinterpret_cast<unsigned int*>(row + 64 * h + 2 * lane), *reinterpret_cast<const unsigned int*>(&pr));
-    }
-  }
-  if (which == 2) {
-    __syncthreads();
-    if (threadIdx.x < 64 && c0 + threadIdx.x < cols) atomicAdd(db + c0 + threadIdx.x, colsum_s[threadIdx.x]);
-  }
-}
+// (bf16 mode forms the tied weight gradient on the tensor cores instead: two products over the token axis through
+//  MN-major operand descriptors, freud_gemm_tn_splitk -- no operand packing pass.)
 
 }  // namespace freud
 
@@ -294,19 +207,6 @@ extern "C" int freud_l1_weight_grad(const float* x, const float* dz, const float
   return 0;
 }
 
-extern "C" int freud_l1_grad_operands(const float* x, const float* dxhat, const float* dc, const float* latent,
-                                      const float* scales, void* At_bf16, void* Bt_bf16, float* db, int64_t N,
-                                      int64_t Np, int64_t d, int64_t n, void* stream) {
-  FREUD_REQUIRE(N > 0 && d > 0 && n > 0, "l1_grad_operands: empty");
-  FREUD_REQUIRE(Np % 64 == 0 && Np >= N, "l1_grad_operands: Np must be N rounded up to a multiple of 64");
-  FREUD_CHECK_CUDA(cudaMemsetAsync(db, 0, n * sizeof(float), STREAM));
-  const int64_t cmax = d > n ? d : n;
-  dim3 grid((unsigned)((cmax + 63) / 64), (unsigned)((Np + kPackTok - 1) / kPackTok), 4);
-  l1_grad_pack_kernel<<<grid, 256, 0, STREAM>>>(x, dxhat, dc, latent, scales, static_cast<__nv_bfloat16*>(At_bf16),
-                                                static_cast<__nv_bfloat16*>(Bt_bf16), db, N, Np, (int)d, (int)n);
-  FREUD_CHECK_CUDA(cudaGetLastError());
-  return 0;
-}
 
 // Loss values and gradient scales of the L1 SAE from the four accumulated sums (l1autoencoder.py:85-86,29-36):
 //   acc = [sum|c|, sum over x != -1 of (x_hat - x)^2, count of x != -1, sum (x_hat - x)^2]

@@ -413,42 +413,6 @@ __global__ void __launch_bounds__(256) col_sum_bf16_kernel(const __nv_bfloat16* 
   }
 }
 
-// out[c, r] = in[r, c] for a bf16 matrix in [rows, ld_in] -> [cols, ld_out]; columns [rows, ld_out) of out zeroed.
-__global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in,
-                                                             __nv_bfloat16* __restrict__ out, int64_t rows, int64_t cols,
-                                                             int64_t ld_in, int64_t ld_out) {
-  __shared__ __nv_bfloat16 tile[32][34];
-  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * 32, c0 = static_cast<int64_t>(blockIdx.x) * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-  for (int i = ty; i < 32; i += 8) {
-    const int64_t r = r0 + i, c = c0 + tx;
-    tile[i][tx] = (r < rows && c < cols) ? in[r * ld_in + c] : __float2bfloat16_rn(0.f);
-  }
-  __syncthreads();
-  for (int i = ty; i < 32; i += 8) {
-    const int64_t c = c0 + i, r = r0 + tx;
-    if (c < cols && r < ld_out) out[c * ld_out + r] = tile[tx][i];
-  }
-}
-
-// dpre[r, j] = (act[r, j] > 0) ? g[r, j] : 0 (bf16, pitch ld) with column sums into colsum[j] (fp32, caller zeroes):
-// the ReLU / selection mask of the AuxK branch applied to the dense activation gradient g [rows, n] fp32.
-__global__ void __launch_bounds__(256) mask_grad_kernel(const float* __restrict__ g, const __nv_bfloat16* __restrict__ act,
-                                                        __nv_bfloat16* __restrict__ dpre, float* __restrict__ colsum,
-                                                        int64_t rows, int n, int ld, int slab) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= ld) return;
-  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * slab, r1 = min(rows, r0 + slab);
-  float acc = 0.f;
-  for (int64_t r = r0; r < r1; ++r) {
-    float v = 0.f;
-    if (j < n && __bfloat162float(act[r * ld + j]) > 0.f) v = g[r * n + j];
-    const __nv_bfloat16 q = __float2bfloat16_rn(v);
-    dpre[r * ld + j] = q;
-    acc += __bfloat162float(q);
-  }
-  if (j < n) atomicAdd(colsum + j, acc);
-}
 
 // dst[rows_idx[r], :] += src[r, :]   (row scatter-add of the dead-subset gradients into the full matrices)
 __global__ void __launch_bounds__(256) scatter_add_rows_kernel(const float* __restrict__ src,
@@ -515,28 +479,6 @@ extern "C" int freud_col_sum_bf16(const void* x_bf16, float* colsum, int64_t row
   dim3 grid((unsigned)((n + 255) / 256), (unsigned)((rows + slab - 1) / slab));
   col_sum_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x_bf16), colsum,
                                                                           rows, (int)n, (int)ld, slab);
-  FREUD_CHECK_CUDA(cudaGetLastError());
-  return 0;
-}
-
-extern "C" int freud_transpose_bf16(const void* in, void* out, int64_t rows, int64_t cols, int64_t ld_in,
-                                    int64_t ld_out, void* stream) {
-  FREUD_REQUIRE(rows > 0 && cols > 0 && ld_in >= cols && ld_out >= rows, "transpose: bad sizes");
-  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((ld_out + 31) / 32));
-  transpose_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), rows, cols, ld_in, ld_out);
-  FREUD_CHECK_CUDA(cudaGetLastError());
-  return 0;
-}
-
-extern "C" int freud_mask_grad(const float* g, const void* act_bf16, void* dpre_bf16, float* colsum, int64_t rows,
-                               int64_t n, int64_t ld, void* stream) {
-  FREUD_REQUIRE(rows > 0 && n > 0 && ld >= n, "mask_grad: bad sizes");
-  const int slab = 256;
-  dim3 grid((unsigned)((ld + 255) / 256), (unsigned)((rows + slab - 1) / slab));
-  mask_grad_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      g, static_cast<const __nv_bfloat16*>(act_bf16), static_cast<__nv_bfloat16*>(dpre_bf16), colsum, rows, (int)n,
-      (int)ld, slab);
   FREUD_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

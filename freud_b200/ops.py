@@ -166,42 +166,10 @@ def col_sum_bf16(x: torch.Tensor, n: int):
     return out
 
 
-def transpose_bf16(x: torch.Tensor, cols: int, ld_out: int):
-    """x [rows, ld_in] bf16 (first `cols` columns valid) -> [cols, ld_out] with zero padding."""
-    rows, ld_in = x.shape
-    out = torch.empty((cols, ld_out), dtype=torch.bfloat16, device=x.device)
-    call("freud_transpose_bf16", _ptr(x), _ptr(out), rows, cols, ld_in, ld_out, _stream())
-    return out
-
-
-def mask_grad(g: torch.Tensor, act: torch.Tensor):
-    """dpre = (act > 0) ? g : 0 as bf16 [rows, ld] + fp32 column sums [n]; g fp32 [rows, n], act bf16 [rows, ld]."""
-    rows, n = g.shape
-    ld = act.shape[1]
-    dpre = torch.empty((rows, ld), dtype=torch.bfloat16, device=g.device)
-    colsum = torch.zeros(n, dtype=torch.float32, device=g.device)
-    call("freud_mask_grad", _ptr(g), _ptr(act), _ptr(dpre), _ptr(colsum), rows, n, ld, _stream())
-    return dpre, colsum
-
-
 def scatter_add_rows(src: torch.Tensor, rows_idx: torch.Tensor, dst: torch.Tensor):
     row_elems = 1 if src.dim() == 1 else src.shape[1]
     call("freud_scatter_add_rows", _ptr(_f32(src, "src")), _ptr(rows_idx), _ptr(_f32(dst, "dst")), rows_idx.numel(),
          row_elems, _stream())
-
-
-def gemm_nt_splitk(a: torch.Tensor, b: torch.Tensor, splits: int):
-    """A[M,K] @ B[N,K]^T (bf16, K long) via split-K partials on the tensor cores, summed in fp32."""
-    M, K = a.shape
-    Nn = b.shape[0]
-    total_kb = (K + 63) // 64
-    per = (total_kb + splits - 1) // splits
-    splits = (total_kb + per - 1) // per  # the split count the kernel will actually run (no empty partials)
-    ws = torch.empty((splits, M, Nn), dtype=torch.float32, device=a.device)
-    out = torch.empty((M, Nn), dtype=torch.float32, device=a.device)
-    call("freud_gemm_nt_splitk", _ptr(a), _ptr(b), _ptr(ws), M, Nn, K, splits, _stream())
-    call("freud_sum_splits", _ptr(ws), _ptr(out), splits, M * Nn, _stream())
-    return out
 
 
 def gemm_nt_mask(a: torch.Tensor, b: torch.Tensor, act: torch.Tensor, affine: torch.Tensor = None):
@@ -460,22 +428,6 @@ def l1_weight_grad(x, dz, dxhat, latent, scales):
     call("freud_l1_weight_grad", _ptr(x), _ptr(dz), _ptr(dxhat), _ptr(latent), _ptr(scales), _ptr(dW), N, d, n,
          _stream())
     return dW
-
-
-def l1_weight_grad_tc(x, dxhat, dc, latent, scales4):
-    """bf16-mode tied weight gradient on the tensor cores: (dW [d,n], db [n]) from one operand-packing pass over
-    the activations and a split-K GEMM over K = 2 * tokens.  scales4 = (s_recon, s_l1, s0, s1) device floats."""
-    N, d = x.shape
-    n = latent.shape[1]
-    Np = (N + 63) // 64 * 64
-    At = torch.empty((d, 2 * Np), dtype=torch.bfloat16, device=x.device)
-    Bt = torch.empty((n, 2 * Np), dtype=torch.bfloat16, device=x.device)
-    db = torch.empty(n, dtype=torch.float32, device=x.device)
-    call("freud_l1_grad_operands", _ptr(x), _ptr(dxhat), _ptr(dc), _ptr(latent), _ptr(scales4), _ptr(At), _ptr(Bt),
-         _ptr(db), N, Np, d, n, _stream())
-    row_blocks = (d + 127) // 128
-    splits = max(1, min((2 * Np) // 64, 148 // row_blocks))  # one wave of CTAs
-    return gemm_nt_splitk(At, Bt, splits), db
 
 
 # ------------------------------------------------------------------------------------------------ optimiser

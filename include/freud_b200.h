@@ -96,24 +96,14 @@ int freud_index_map(const int32_t* table, const int32_t* in, int32_t* out, int64
  *   freud_row_topk_mask   : out[r,j] = latents[r,j] if j is in row r's top-k else 0 (bf16, row pitch ld >= n;
  *                           latents fp32 with row pitch ld_in >= n; nonneg != 0 promises
  *                           latents >= 0 (post-ReLU), which selects the streaming warp-per-row kernel)
- *   freud_transpose_bf16  : out[c,r] = in[r,c] (pitches ld_in / ld_out, padding zeroed) -- K-major GEMM operands
- *   freud_mask_grad       : dpre = (act > 0) ? g : 0 (bf16) with fp32 column sums (autograd of relu + topk)
  *   freud_scatter_add_rows: dst[rows_idx[r],:] += src[r,:] (subset gradients back into the full matrices) */
 int freud_row_topk_mask(const float* latents, void* out_bf16, int64_t rows, int64_t n, int64_t k, int64_t ld_in,
                         int64_t ld, int nonneg, void* stream);
 /* colsum[j] = sum_r x[r,j] over a bf16 matrix [rows, ld] (first n columns): the bias gradient of the dense AuxK
  * branch (db_enc[dead] = sum_t dpre[t,:]). */
 int freud_col_sum_bf16(const void* x_bf16, float* colsum, int64_t rows, int64_t n, int64_t ld, void* stream);
-int freud_transpose_bf16(const void* in, void* out, int64_t rows, int64_t cols, int64_t ld_in, int64_t ld_out,
-                         void* stream);
-int freud_mask_grad(const float* g, const void* act_bf16, void* dpre_bf16, float* colsum, int64_t rows, int64_t n,
-                    int64_t ld, void* stream);
 int freud_scatter_add_rows(const float* src, const int32_t* rows_idx, float* dst, int64_t n_rows, int64_t row_elems,
                            void* stream);
-/* Split-K tensor-core product for few output rows and a very long K (the subset weight gradients, K = tokens):
- * workspace [splits, M, N] receives partial A[M,K] @ B[N,K]^T products (bf16 operands), freud_sum_splits adds them. */
-int freud_gemm_nt_splitk(const void* a_bf16, const void* b_bf16, float* workspace, int64_t M, int64_t N, int64_t K,
-                         int64_t splits, void* stream);
 /* Products with operands stored "the other way round" (read through MN-major tensor-core descriptors; nothing is
  * transposed in memory).  bf16 operands, fp32 accumulation / output.
  *   freud_gemm_tn_splitk: out[M,N] = A^T B, A stored [K, lda >= M], B stored [K, ldb >= N] (K = tokens: the
@@ -276,15 +266,6 @@ int freud_l1_dz(float* dc, const float* latent, const float* scales, float* db, 
  * (autograd of l1autoencoder.py:74,84) as one split-K kernel over the token axis. */
 int freud_l1_weight_grad(const float* x, const float* dz, const float* dxhat, const float* latent,
                          const float* scales, float* dW, int64_t N, int64_t d, int64_t n, void* stream);
-
-/* bf16 mode of the same gradient on the tensor cores: one pass builds the K-major bf16 operands
- *   At [d, 2*Np] = [ s0 * x^T | s1 * dxhat^T ]      Bt [n, 2*Np] = [ dz^T | c^T ]
- * (dz = c > 0 ? s_recon * dc + s_l1 : 0 formed on the fly; db[j] = sum_t dz[t,j]; Np = N rounded up to a multiple
- * of 64, zero padded), after which dW = At @ Bt^T is one freud_gemm_nt_splitk + freud_sum_splits over K = 2*Np.
- * scales = (s_recon, s_l1, s0, s1) device floats.  Replaces freud_l1_dz + freud_l1_weight_grad. */
-int freud_l1_grad_operands(const float* x, const float* dxhat, const float* dc, const float* latent,
-                           const float* scales, void* At_bf16, void* Bt_bf16, float* db, int64_t N, int64_t Np,
-                           int64_t d, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------ optimiser (train_sae.py:449-450) */
 
