@@ -12,6 +12,6 @@ python bench.py --workload c4 --no-cpu-baseline --no-eager --no-parity --profile
 python scripts/bench_extra.py > $OUT/bench_extra.json 2> $OUT/bench_extra.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_c3.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-eager --no-parity --no-extras > $OUT/ncu_launch.log 2>&1
-cuobjdump -sass freud_b200/libfreud_b200.so | grep -oE "UTCHMMA[A-Z0-9_.]*|UTCQMMA[A-Z0-9_.]*|LDTM[A-Z0-9_.]*|STTM[A-Z0-9_.]*|UTMALDG[A-Z0-9_.]*|UTMASTG[A-Z0-9_.]*|UBLKCP[A-Z0-9_.]*|UTCBAR[A-Z0-9_.]*|SYNCS[A-Z0-9_.]*|MULTIMEM[A-Z0-9_.]*|HMMA[A-Z0-9_.]*|REDUX[A-Z0-9_.]*|FFMA2" | sort | uniq -c | sort -rn > $OUT/sass_mnemonics.txt
+cuobjdump -sass freud_b200/libfreud_b200.so | grep -oE "UTCHMMA[A-Z0-9_.]*|UTCQMMA[A-Z0-9_.]*|LDTM[A-Z0-9_.]*|STTM[A-Z0-9_.]*|UTMALDG[A-Z0-9_.]*|UTMASTG[A-Z0-9_.]*|UBLKCP[A-Z0-9_.]*|UBLKPF[A-Z0-9_.]*|UTCBAR[A-Z0-9_.]*|SYNCS[A-Z0-9_.]*|LDGMC[A-Z0-9_.]*|HMMA[A-Z0-9_.]*|REDUX[A-Z0-9_.]*|FFMA2" | sort | uniq -c | sort -rn > $OUT/sass_mnemonics.txt
 FREUD_ENC_STATS=1 python scripts/enc_stats.py > $OUT/enc_stats.txt 2>&1
 ls -la $OUT

@@ -35,7 +35,7 @@ for rep in $OUT/*.ncu-rep; do
   ncu -i $rep --page raw --csv > ${rep%.ncu-rep}.raw.csv 2> /dev/null && rm -f $rep
 done
 # SASS evidence of the Blackwell-native path (tcgen05 / TMEM / TMA / multimem mnemonics in the shipped library)
-cuobjdump -sass freud_b200/libfreud_b200.so | grep -oE "UTCHMMA[A-Z0-9_.]*|UTCQMMA[A-Z0-9_.]*|LDTM[A-Z0-9_.]*|STTM[A-Z0-9_.]*|UTMALDG[A-Z0-9_.]*|UTMASTG[A-Z0-9_.]*|UBLKCP[A-Z0-9_.]*|UTCBAR[A-Z0-9_.]*|SYNCS[A-Z0-9_.]*|MULTIMEM[A-Z0-9_.]*|HMMA[A-Z0-9_.]*" | sort | uniq -c | sort -rn > $OUT/sass_mnemonics.txt
+cuobjdump -sass freud_b200/libfreud_b200.so | grep -oE "UTCHMMA[A-Z0-9_.]*|UTCQMMA[A-Z0-9_.]*|LDTM[A-Z0-9_.]*|STTM[A-Z0-9_.]*|UTMALDG[A-Z0-9_.]*|UTMASTG[A-Z0-9_.]*|UBLKCP[A-Z0-9_.]*|UBLKPF[A-Z0-9_.]*|UTCBAR[A-Z0-9_.]*|SYNCS[A-Z0-9_.]*|LDGMC[A-Z0-9_.]*|HMMA[A-Z0-9_.]*|REDUX[A-Z0-9_.]*|FFMA2" | sort | uniq -c | sort -rn > $OUT/sass_mnemonics.txt
 # compute-sanitizer over the kernels with hand-rolled synchronisation
 bash scripts/sanitize.sh memcheck racecheck > $OUT/sanitize.log 2>&1
 cp gpurun_out/sanitize_*.log $OUT/ 2>/dev/null
