@@ -536,7 +536,7 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
     uint64_t* my_in_bar = in_bar + ew * 2;
     constexpr int kInCols = EPI == EPI_RESID ? 32 : 64;         // columns per input box
     constexpr int kInPerTile = L::kHasIn ? kCols / kInCols : 1;  // boxes per tile and warp
-    uint32_t in_phase[2] = {0u, 0u};
+    uint32_t in_phase = 0u;  // bit b: phase parity of input buffer b
     auto in_issue = [&](int64_t g) {  // g: box ordinal over this CTA's tiles
       const int lt_g = static_cast<int>(g / kInPerTile);
       if (lt_g >= num_lt) return;
@@ -736,8 +736,8 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
               if (tma_in && cib == 0) {
                 __syncwarp();          // every lane is done with the other buffer (the previous box)
                 in_issue(in_g + 1);    // request the next box, then wait for this one
-                mbar_wait(my_in_bar + (in_g & 1), in_phase[in_g & 1]);
-                in_phase[in_g & 1] ^= 1u;
+                mbar_wait(my_in_bar + (in_g & 1), (in_phase >> (in_g & 1)) & 1u);
+                in_phase ^= 1u << (in_g & 1);
               }
               if (tma_in) {
                 if constexpr (EPI == EPI_RESID) {
@@ -753,30 +753,61 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                 }
               }
             }
+            // The running sums are fp64, but a chunk's 16 terms are first added in fp32 (four interleaved partial sums)
+            // and enter the fp64 sum once: per element that is one FADD instead of a conversion + a DADD on a serial
+            // chain, and no branch (the epilogue was bound by instruction issue and fixed-latency dependencies).
             if constexpr (EPI == EPI_RELU16) {
+              float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
               for (int j = 0; j < kChunk; ++j) {
                 v[j] = fmaxf(v[j], 0.f);  // columns past N carry a -inf bias: they come out as 0
                 o[j] = v[j];
-                if (rv) acc_sum[0] += v[j];
+                s4[j & 3] += v[j];
               }
+              if (rv) acc_sum[0] += static_cast<double>((s4[0] + s4[1]) + (s4[2] + s4[3]));
             } else if constexpr (EPI == EPI_RESID) {
               const float (&xt)[kChunk] = xin[h];
+              // valid columns of this chunk for this thread's row: kChunk everywhere but at the matrix edges
+              const int ncol = static_cast<int>(p.N) - static_cast<int>(col0);
+              const int nval = rv ? min(max(ncol, 0), kChunk) : 0;
+              bool ign = false;  // mse_loss(..., ignored_index=-1): exact comparison, as the reference (:31)
 #pragma unroll
-              for (int j = 0; j < kChunk; ++j) {
-                float ev = 0.f;
-                if (rv && col0 + j < p.N) {
-                  const float xv = xt[j];
+              for (int j = 0; j < kChunk; ++j) ign |= __float_as_uint(xt[j]) == 0xbf800000u;  // the one encoding of -1
+              if (__all_sync(0xffffffffu, nval == kChunk && !ign)) {
+                // the common chunk -- every column valid, no ignored target: a subtraction and an FMA per element
+                float sa[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int j = 0; j < kChunk; ++j) {
+                  const float d0 = v[j] - xt[j];
+                  sa[j & 3] = fmaf(d0, d0, sa[j & 3]);
+                  o[j] = d0;
+                }
+                const double sq = static_cast<double>((sa[0] + sa[1]) + (sa[2] + sa[3]));
+                acc_sum[2] += sq;
+                acc_sum[0] += sq;
+                acc_sum[1] += static_cast<double>(kChunk);
+              } else if (__all_sync(0xffffffffu, nval == 0)) {  // column range past N / rows past M
+#pragma unroll
+                for (int j = 0; j < kChunk; ++j) o[j] = 0.f;
+              } else {
+                float sa[4] = {0.f, 0.f, 0.f, 0.f}, sm[4] = {0.f, 0.f, 0.f, 0.f};
+                int cnt = 0;
+#pragma unroll
+                for (int j = 0; j < kChunk; ++j) {
+                  float xv = xt[j];
+                  asm volatile("" : "+f"(xv));  // keeps this rare path's compares out of the common path's schedule
                   const float d0 = v[j] - xv;
                   const float d2 = d0 * d0;
-                  acc_sum[2] += d2;
-                  if (xv != -1.0f) {  // mse_loss(..., ignored_index=-1): exact comparison, as the reference (:31)
-                    acc_sum[0] += d2;
-                    acc_sum[1] += 1.0;
-                    ev = d0;
-                  }
+                  const bool ok = j < nval;
+                  const bool keep = ok && xv != -1.0f;
+                  sa[j & 3] += ok ? d2 : 0.f;
+                  sm[j & 3] += keep ? d2 : 0.f;
+                  cnt += keep ? 1 : 0;
+                  o[j] = keep ? d0 : 0.f;
                 }
-                o[j] = ev;
+                acc_sum[2] += static_cast<double>((sa[0] + sa[1]) + (sa[2] + sa[3]));
+                acc_sum[0] += static_cast<double>((sm[0] + sm[1]) + (sm[2] + sm[3]));
+                acc_sum[1] += static_cast<double>(cnt);
               }
             } else {
 #pragma unroll
@@ -785,9 +816,9 @@ sm100_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_consta
                 const uint32_t aw[4] = {a8.x, a8.y, a8.z, a8.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                  // bf16 > 0  <=>  sign clear and not zero
-                  const bool p0 = (aw[j] & 0x8000u) == 0 && (aw[j] & 0x7fffu) != 0;
-                  const bool p1 = (aw[j] & 0x80000000u) == 0 && (aw[j] & 0x7fff0000u) != 0;
+                  // bf16 > 0  <=>  sign clear and not zero: as signed integers, (low half << 16) > 0 and word >= 2^16
+                  const bool p0 = static_cast<int32_t>(aw[j] << 16) > 0;
+                  const bool p1 = static_cast<int32_t>(aw[j]) >= 0x10000;
                   o[h8 + 2 * j] = p0 ? fmaf(aff_scale, v[h8 + 2 * j], aff_shift) : 0.f;
                   o[h8 + 2 * j + 1] = p1 ? fmaf(aff_scale, v[h8 + 2 * j + 1], aff_shift) : 0.f;
                 }
