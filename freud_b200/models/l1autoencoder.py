@@ -58,8 +58,11 @@ def _pad_cols_bf16(t: Tensor, mult: int = 8) -> Tensor:
     return out
 
 
-class _L1ForwardFn(torch.autograd.Function):
-    """(x, W, b) -> (x_hat, latent, l1_loss, reconstruction_loss, mse); losses carry gradient to W and b.
+def l1_forward(x2, W, b, recon_alpha, precision, dp=None, want_outputs=True, need_grad=True):
+    """Forward of the L1 SAE on [N, d] rows: returns (x_hat, latent, scal, saved) with
+    scal = [l1_loss, reconstruction_loss, mse, d recon / d x_hat scale, d l1 / d c scale] (device) and `saved` what
+    `l1_backward` needs.  Used by the autograd function below and, directly, by `SAETrainer` (whose loss is always
+    reconstruction_loss + l1_loss, train_sae.py:433-434: no autograd graph, no engine round trip).
 
     bf16 mode runs the step in five tensor-core launches and no elementwise passes over [N, n] / [N, d] matrices:
       encode GEMM  -> epilogue relu + bf16 latent (next GEMM's operand) + sum|c|
@@ -68,66 +71,78 @@ class _L1ForwardFn(torch.autograd.Function):
       two products over the token axis (x^T dz, dxhat^T c) reading their operands through MN-major descriptors.
     fp32 outputs (x_hat, latent) are only materialised when `want_outputs` (the module API returns them; the trainer
     does not need them).  fp32 mode keeps the 3-pass split-TF32 GEMMs and separate reduction kernels."""
+    N, d = x2.shape
+    n = W.shape[1]
+    Wt = ops.l1_colnorm(W.data)  # in place on decoder.weight.data + K-major transposed copy
+    if precision == BF16:
+        x16 = ops.split_operand(x2, BF16)[0]
+        wt16 = ops.split_operand(Wt, BF16)[0]                                   # [n, d]
+        w16 = _pad_cols_bf16(W.data)                                            # [d, ceil8(n)]
+        acc = torch.zeros(4, dtype=torch.float64, device=x2.device)  # [sum|c|, masked sse, count, sse]
+        c16, _, latent = ops.l1_encode_fused(x16, wt16, b, want_outputs, sums=acc[0:1])     # relu(x @ W + b)
+        dxh16, _, x_hat = ops.l1_decode_fused(c16, w16, n, x2, want_outputs, sums=acc[1:4])  # c @ W.T vs x
+        saved = (x16, c16, dxh16, wt16)
+    else:
+        x_ops = _gemm_operands(x2, precision)
+        wt_ops = _gemm_operands(Wt, precision)
+        w_ops = _gemm_operands(W.data, precision)
+        latent = ops.gemm_nt(x_ops[0], x_ops[1], wt_ops[0], wt_ops[1], b, True, precision)   # relu(x @ W + b)
+        c_ops = _gemm_operands(latent, precision)
+        x_hat = ops.gemm_nt(c_ops[0], c_ops[1], w_ops[0], w_ops[1], None, False, precision)  # c @ W.T
+        acc, dxhat = ops.l1_loss_reduce(latent, x_hat, x2, need_grad)
+        saved = (x2, latent, dxhat, wt_ops)
+    n_glob = N
+    if dp is not None:  # losses (and with them the gradient scales) of the batch concatenated over ranks
+        acc = dp.all_reduce_sum(acc)
+        n_glob = N * dp.world_size
+    # l1 = sum|c| / N, recon = alpha * masked mse, mse, and the two gradient scales: one launch (:85-86, :29-36)
+    scal = ops.l1_loss_scalars(acc, n_glob, d, recon_alpha)
+    return x_hat, latent, scal, saved + (precision, n, d)
+
+
+def l1_backward(saved, scales):
+    """(dW, db) of  g_recon * reconstruction_loss + g_l1 * l1_loss;  scales = [g_recon, g_l1] * scal[3:5] (device):
+    d recon / d x_hat = 2*alpha*(x_hat-x)/N_unmasked, d l1 / d c = 1[c>0]/N, times the incoming gradients."""
+    a0, a1, a2, a3, precision, n, d = saved
+    s_recon = scales[0]
+    if precision == BF16:
+        x16, c16, dxh16, wt16 = a0, a1, a2, a3
+        dz16 = ops.gemm_nt_mask(dxh16, wt16, c16, scales)  # (c>0) ? s_recon*(dxhat W) + s_l1 : 0
+        db = ops.col_sum_bf16(dz16, n)
+        Ga = ops.gemm_tn_splitk(x16, dz16, M=d, N=n)                             # x^T dz
+        Gb = ops.gemm_tn_splitk(dxh16, c16, M=d, N=n)                            # dxhat^T c   (dxhat unscaled)
+        dW = torch.addcmul(Ga, Gb, s_recon)
+    else:
+        x2, latent, dxhat, wt_ops = a0, a1, a2, a3
+        # dc (unscaled) = dxhat_raw @ W  as  A = dxhat [N, K=d], B = W^T [n, K=d]
+        dx_ops = _gemm_operands(dxhat, precision)
+        dc = ops.gemm_nt(dx_ops[0], dx_ops[1], wt_ops[0], wt_ops[1], None, False, precision)
+        db = ops.l1_dz(dc, latent, scales)          # dc becomes dz in place
+        dW = ops.l1_weight_grad(x2, dc, dxhat, latent, torch.stack((torch.ones_like(s_recon), s_recon)))
+    return dW, db
+
+
+class _L1ForwardFn(torch.autograd.Function):
+    """(x, W, b) -> (x_hat, latent, l1_loss, reconstruction_loss, mse); losses carry gradient to W and b
+    (`l1_forward` / `l1_backward` behind autograd, for callers that build their own loss on the module's outputs)."""
 
     @staticmethod
     def forward(ctx, x2, W, b, recon_alpha, precision, dp=None, want_outputs=True):
-        N, d = x2.shape
-        n = W.shape[1]
-        Wt = ops.l1_colnorm(W.data)  # in place on decoder.weight.data + K-major transposed copy
         need_grad = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
-        if precision == BF16:
-            x16 = ops.split_operand(x2, BF16)[0]
-            wt16 = ops.split_operand(Wt, BF16)[0]                                   # [n, d]
-            w16 = _pad_cols_bf16(W.data)                                            # [d, ceil8(n)]
-            acc = torch.zeros(4, dtype=torch.float64, device=x2.device)  # [sum|c|, masked sse, count, sse]
-            c16, _, latent = ops.l1_encode_fused(x16, wt16, b, want_outputs, sums=acc[0:1])     # relu(x @ W + b)
-            dxh16, _, x_hat = ops.l1_decode_fused(c16, w16, n, x2, want_outputs, sums=acc[1:4])  # c @ W.T vs x
-            saved = (x16, c16, dxh16, wt16)
-        else:
-            x_ops = _gemm_operands(x2, precision)
-            wt_ops = _gemm_operands(Wt, precision)
-            w_ops = _gemm_operands(W.data, precision)
-            latent = ops.gemm_nt(x_ops[0], x_ops[1], wt_ops[0], wt_ops[1], b, True, precision)   # relu(x @ W + b)
-            c_ops = _gemm_operands(latent, precision)
-            x_hat = ops.gemm_nt(c_ops[0], c_ops[1], w_ops[0], w_ops[1], None, False, precision)  # c @ W.T
-            acc, dxhat = ops.l1_loss_reduce(latent, x_hat, x2, need_grad)
-            saved = (x2, latent, dxhat, wt_ops)
-        n_glob = N
-        if dp is not None:  # losses (and with them the gradient scales) of the batch concatenated over ranks
-            acc = dp.all_reduce_sum(acc)
-            n_glob = N * dp.world_size
-        # l1 = sum|c| / N, recon = alpha * masked mse, mse, and the two gradient scales: one launch (:85-86, :29-36)
-        scal = ops.l1_loss_scalars(acc, n_glob, d, recon_alpha)
+        x_hat, latent, scal, saved = l1_forward(x2, W, b, recon_alpha, precision, dp, want_outputs, need_grad)
         l1, recon, mse = scal[0], scal[1], scal[2]
-        ctx.saved = saved + (scal, precision, recon_alpha, n_glob, n, d)
+        ctx.saved = (saved, scal)
         outs = [t for t in (x_hat, latent, mse) if t is not None]
         ctx.mark_non_differentiable(*outs)
         return x_hat, latent, l1, recon, mse
 
     @staticmethod
     def backward(ctx, g_xhat, g_latent, g_l1, g_recon, g_mse):
-        a0, a1, a2, a3, scal, precision, recon_alpha, n_glob, n, d = ctx.saved
-        dev = a0.device
-        zero = torch.zeros((), dtype=torch.float32, device=dev)
+        saved, scal = ctx.saved
+        zero = torch.zeros((), dtype=torch.float32, device=scal.device)
         g_l1 = zero if g_l1 is None else g_l1.float()
         g_recon = zero if g_recon is None else g_recon.float()
-        # (d recon / d x_hat = 2*alpha*(x_hat-x)/N_unmasked, d l1 / d c = 1[c>0]/N) times the incoming gradients
-        scales = torch.stack((g_recon, g_l1)) * scal[3:5]
-        s_recon, s_l1 = scales[0], scales[1]
-        if precision == BF16:
-            x16, c16, dxh16, wt16 = a0, a1, a2, a3
-            dz16 = ops.gemm_nt_mask(dxh16, wt16, c16, scales)  # (c>0) ? s_recon*(dxhat W) + s_l1 : 0
-            db = ops.col_sum_bf16(dz16, n)
-            Ga = ops.gemm_tn_splitk(x16, dz16, M=d, N=n)                             # x^T dz
-            Gb = ops.gemm_tn_splitk(dxh16, c16, M=d, N=n)                            # dxhat^T c   (dxhat unscaled)
-            dW = torch.addcmul(Ga, Gb, s_recon)
-        else:
-            x2, latent, dxhat, wt_ops = a0, a1, a2, a3
-            # dc (unscaled) = dxhat_raw @ W  as  A = dxhat [N, K=d], B = W^T [n, K=d]
-            dx_ops = _gemm_operands(dxhat, precision)
-            dc = ops.gemm_nt(dx_ops[0], dx_ops[1], wt_ops[0], wt_ops[1], None, False, precision)
-            db = ops.l1_dz(dc, latent, scales)          # dc becomes dz in place
-            dW = ops.l1_weight_grad(x2, dc, dxhat, latent, torch.stack((torch.ones_like(s_recon), s_recon)))
+        dW, db = l1_backward(saved, torch.stack((g_recon, g_l1)) * scal[3:5])
         ctx.saved = None
         return None, dW, db, None, None, None, None
 

@@ -250,18 +250,25 @@ class SAETrainer:
 
     # ------------------------------------------------------------------------------------------ L1
     def _l1_step(self, x):
-        self.optimizer.zero_grad(set_to_none=True)
-        self.model.dp = self.dp
-        self.model.materialize_outputs = self.materialize_outputs
-        out = self.model(x)
-        loss = out.reconstruction_loss + out.l1_loss  # train_sae.py:433-434
-        loss.backward()
+        # model(x); loss = reconstruction_loss + l1_loss; loss.backward()  (train_sae.py:433-434, :448) -- the loss is
+        # fixed, so forward and backward are called directly: no autograd graph, no engine round trip per step
+        from .models.l1autoencoder import l1_backward, l1_forward
+
+        m = self.model
+        m.dp, m.materialize_outputs = self.dp, self.materialize_outputs  # what a module call between steps would use
+        d = x.shape[-1]
+        W, b = m.decoder.weight, m.encoder_bias
+        x_hat, latent, scal, saved = l1_forward(x.view(-1, d), W, b, float(m.recon_alpha), self.precision, self.dp,
+                                                bool(self.materialize_outputs), True)
+        W.grad, b.grad = l1_backward(saved, scal[3:5])  # both incoming gradients are 1
         if self.dp is not None:  # rank-local sums of gradients whose scales already are those of the global batch
-            self.dp.all_reduce_grads([p.grad for p in self.model.parameters()])
+            self.dp.all_reduce_grads([p.grad for p in m.parameters()])
         self.optimizer.step()
         self.scheduler.step()
-        return {"loss": loss.detach(), "loss_recon": out.reconstruction_loss.detach(), "loss_l1": out.l1_loss.detach(),
-                "sae_out": out.sae_out, "latent": out.encoded.latent}  # None when materialize_outputs is False
+        lead = x.shape[:-1]
+        return {"loss": scal[0] + scal[1], "loss_recon": scal[1], "loss_l1": scal[0],
+                "sae_out": x_hat.view(*lead, d) if x_hat is not None else None,  # None when materialize_outputs is
+                "latent": latent.view(*lead, -1) if latent is not None else None}  # False (bf16 mode)
 
     def step(self, activations: torch.Tensor):
         """One optimisation step on a [B, T, d] CUDA batch (fp32, or fp16 / bf16 as stored).  Returns device tensors (no
