@@ -2,8 +2,8 @@
 
 `SAETrainer.step(activations)` = dead-mask, forward, loss, backward, global-norm clip, Adam/RAdam update,
 LR-scheduler step and dead-latent bookkeeping, with the same hyper-parameter schema as `train(**config)`
-(configs/train/*.json).  The TopK path drives the kernels directly (no autograd graph); the L1 path goes
-through the module's autograd.Function.  With `dp` (freud_b200.parallel.DataParallel) the step equals the
+(configs/train/*.json).  Both paths drive the kernels directly (no autograd graph: the train loop's loss is fixed);
+the modules keep their autograd functions for callers that build their own loss.  With `dp` (freud_b200.parallel.DataParallel) the step equals the
 single-GPU step on the batch concatenated over ranks.
 """
 from __future__ import annotations
@@ -13,7 +13,7 @@ from torch.optim.lr_scheduler import CosineAnnealingLR, LambdaLR
 
 from . import ops, topk_engine
 from ._lib import BF16, FP32
-from .models.l1autoencoder import L1AutoEncoder
+from .models.l1autoencoder import L1AutoEncoder, l1_backward, l1_forward
 from .models.topkautoencoder import TopKAutoEncoder
 from .optim import FusedAdam, FusedRAdam
 
@@ -252,8 +252,6 @@ class SAETrainer:
     def _l1_step(self, x):
         # model(x); loss = reconstruction_loss + l1_loss; loss.backward()  (train_sae.py:433-434, :448) -- the loss is
         # fixed, so forward and backward are called directly: no autograd graph, no engine round trip per step
-        from .models.l1autoencoder import l1_backward, l1_forward
-
         m = self.model
         m.dp, m.materialize_outputs = self.dp, self.materialize_outputs  # what a module call between steps would use
         d = x.shape[-1]
